@@ -1,0 +1,543 @@
+// kge_abi.cu -- the extern "C" surface of libkge_b200.so (include/kge_b200.h) and the per-step
+// orchestration: which kernels run, in which order, on which workspace.
+//
+// Step schedule (all on the caller's stream, no host sync):
+//   forward_backward:  k_prep -> k_score -> k_loss(+colsum, reduce_log) -> k_grad<A> -> k_grad<B> -> k_chain
+//   update:            k_upd_nodes -> k_state_add(negs) -> k_apply(negs) -> k_apply(rels)
+// The order of the update kernels reproduces ExternalEmbedding.update's trace-entry order
+// (tensor_models.py:316-361, general_models.py:586-588): entity [unique positive nodes, negatives],
+// then relation rows; within an entry every state_sum add lands before any row is scaled.
+#include <cstdio>
+#include <cstdarg>
+#include <cstring>
+#include <new>
+#include "kge_common.cuh"
+
+using namespace kge;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define KGE_CUDA_OK(expr)                                                                      \
+  do {                                                                                         \
+    cudaError_t e_ = (expr);                                                                   \
+    if (e_ != cudaSuccess) return fail(KGE_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
+  } while (0)
+
+}  // namespace
+
+struct kge_context {
+  int device = 0;
+  int num_sms = 0;
+  long long launches = 0;
+  int engine = -1;
+  // device arena (grown on demand, never inside a graph capture)
+  char* arena = nullptr;
+  size_t arena_bytes = 0;
+  // NG must be zero between steps: remember how much of it has been zeroed
+  float* ng_ptr = nullptr;
+  size_t ng_floats = 0;
+  bool ng_dirty = false;   // a forward_backward whose gradients were never consumed by kge_update
+  // pinned + device staging for the *_host entry points
+  char* pin = nullptr;
+  char* dev_stage = nullptr;
+  size_t stage_bytes = 0;
+  float* dev_log4 = nullptr;
+  // last step (for kge_update / kge_debug_read)
+  StepParams last_p{};
+  StepWs last_w{};
+  BatchView last_b{};
+  TableView last_ent{}, last_rel{};
+  bool have_last = false;
+};
+
+namespace {
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+int make_view(const kge_table_t* t, TableView* v, const char* what) {
+  if (!t || !t->shards) return fail(KGE_ERR_INVALID_ARG, "%s table is null", what);
+  if (t->n_shards < 1 || t->n_shards > KGE_MAX_SHARDS)
+    return fail(KGE_ERR_INVALID_ARG, "%s table: n_shards=%d out of [1,%d]", what, t->n_shards, KGE_MAX_SHARDS);
+  if (t->dim <= 0 || t->num_rows <= 0) return fail(KGE_ERR_INVALID_ARG, "%s table: empty", what);
+  memset(v, 0, sizeof(*v));
+  v->n_shards = t->n_shards;
+  v->dim = t->dim;
+  v->num_rows = t->num_rows;
+  v->rows_per_shard = (t->num_rows + t->n_shards - 1) / t->n_shards;
+  for (int s = 0; s < t->n_shards; ++s) {
+    const kge_shard_t& sh = t->shards[s];
+    long long begin = (long long)s * v->rows_per_shard;
+    long long end = begin + v->rows_per_shard;
+    if (end > t->num_rows) end = t->num_rows;
+    if (sh.row_begin != begin || sh.row_end != end || sh.dim != t->dim)
+      return fail(KGE_ERR_INVALID_ARG, "%s table: shard %d must cover rows [%lld,%lld) with dim %d", what, s, begin,
+                  end, t->dim);
+    if (!sh.emb || !sh.state_sum) return fail(KGE_ERR_INVALID_ARG, "%s table: shard %d has null pointers", what, s);
+    if (((uintptr_t)sh.emb & 15) != 0) return fail(KGE_ERR_INVALID_ARG, "%s table: shard %d not 16-byte aligned", what, s);
+    v->emb[s] = sh.emb;
+    v->state[s] = sh.state_sum;
+  }
+  return KGE_OK;
+}
+
+int make_params(const kge_step_cfg_t* cfg, long long n_nodes, StepParams* p, bool need_tables) {
+  if (!cfg) return fail(KGE_ERR_INVALID_ARG, "cfg is null");
+  if (cfg->model < KGE_TRANSE_L1 || cfg->model > KGE_ROTATE) return fail(KGE_ERR_INVALID_ARG, "unknown model %d", cfg->model);
+  if (cfg->batch <= 0 || cfg->chunk_size <= 0 || cfg->neg_sample_size <= 0)
+    return fail(KGE_ERR_INVALID_ARG, "batch/chunk_size/neg_sample_size must be positive");
+  // the reference skips ragged batches (dataloader/sampler.py:503-504)
+  if (cfg->batch % cfg->chunk_size != 0)
+    return fail(KGE_ERR_INVALID_ARG, "batch %lld is not a multiple of chunk_size %d", (long long)cfg->batch, cfg->chunk_size);
+  const int D = cfg->entity_dim, Dr = cfg->relation_dim;
+  if (D <= 0 || Dr <= 0) return fail(KGE_ERR_INVALID_ARG, "dims must be positive");
+  if (D % 4 != 0 || Dr % 4 != 0)
+    return fail(KGE_ERR_UNSUPPORTED, "row lengths must be multiples of 4 floats (16-byte vector/TMA access): D_e=%d D_r=%d", D, Dr);
+  switch (cfg->model) {
+    case KGE_TRANSE_L1: case KGE_TRANSE_L2: case KGE_DISTMULT:
+      if (Dr != D) return fail(KGE_ERR_INVALID_ARG, "model needs relation_dim == entity_dim (%d vs %d)", Dr, D);
+      break;
+    case KGE_COMPLEX:
+      if (Dr != D || D % 8 != 0) return fail(KGE_ERR_INVALID_ARG, "ComplEx needs relation_dim == entity_dim, a multiple of 8");
+      break;
+    case KGE_ROTATE:
+      if (D != 2 * Dr || D % 8 != 0) return fail(KGE_ERR_INVALID_ARG, "RotatE needs entity_dim == 2*relation_dim (-de), a multiple of 8");
+      break;
+    case KGE_RESCAL:
+      if (Dr != D * D) return fail(KGE_ERR_INVALID_ARG, "RESCAL needs relation_dim == entity_dim^2");
+      if (D > 512) return fail(KGE_ERR_UNSUPPORTED, "RESCAL entity_dim %d > 512 is not implemented", D);
+      break;
+  }
+  p->model = cfg->model; p->D = D; p->Dr = Dr;
+  p->gamma = cfg->gamma; p->emb_init = cfg->emb_init; p->lr = cfg->lr;
+  p->reg_coef = cfg->reg_coef; p->reg_norm = cfg->reg_norm;
+  p->adversarial = cfg->adversarial; p->adv_temperature = cfg->adv_temperature;
+  p->neg_head = cfg->neg_head ? 1 : 0;
+  p->B = cfg->batch; p->Cs = cfg->chunk_size; p->Ns = cfg->neg_sample_size;
+  p->C = (int)(cfg->batch / cfg->chunk_size);
+  p->Nn = (long long)p->C * p->Ns;
+  p->U = n_nodes;
+  (void)need_tables;
+  return KGE_OK;
+}
+
+size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+// Carves the step workspace out of the arena; grows the arena if needed.
+int carve(kge_context* h, const StepParams& p, StepWs* w, cudaStream_t stream) {
+  const size_t f = sizeof(float);
+  const size_t BD = (size_t)p.B * p.D, ND = (size_t)p.Nn * p.D, BNs = (size_t)p.B * p.Ns;
+  const size_t U = (size_t)(p.U > 0 ? p.U : 0);
+  const bool rescal = p.model == KGE_RESCAL;
+  size_t need = 0;
+  auto take = [&](size_t floats) { size_t off = need; need += align_up(floats * f); return off; };
+  size_t oNG = take(U * p.D);                 // first: stays at a fixed offset so the zero state survives
+  size_t oA = take(BD), oBn = take(ND), oGA = take(BD), oGR = take((size_t)p.B * p.Dr);
+  size_t oS = take(BNs), oV = take(BNs);
+  size_t opos = take(p.B), ogpos = take(p.B), opn = take(p.B), oa2 = take(p.B), ob2 = take(p.Nn);
+  size_t ors = take(p.B), ocs = take(p.Nn), opl = take(p.B), onl = take(p.B);
+  size_t oreg = take((size_t)p.B + p.Nn + U), owb = take(4);
+  size_t oMt = rescal ? take(BD) : 0;
+  if (need > h->arena_bytes) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(stream, &cs);
+    if (cs != cudaStreamCaptureStatusNone)
+      return fail(KGE_ERR_INVALID_ARG, "workspace must grow (%zu > %zu bytes) but the stream is capturing: run one eager step first", need, h->arena_bytes);
+    KGE_CUDA_OK(cudaStreamSynchronize(stream));
+    if (h->arena) KGE_CUDA_OK(cudaFree(h->arena));
+    h->arena = nullptr; h->arena_bytes = 0; h->ng_ptr = nullptr; h->ng_floats = 0;
+    size_t bytes = need + need / 4;
+    cudaError_t e = cudaMalloc(&h->arena, bytes);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(KGE_ERR_NOMEM, "cudaMalloc(%zu) for the step workspace failed: %s", bytes, cudaGetErrorString(e)); }
+    h->arena_bytes = bytes;
+  }
+  char* a = h->arena;
+  w->NG = (float*)(a + oNG); w->A = (float*)(a + oA); w->Bn = (float*)(a + oBn); w->GA = (float*)(a + oGA);
+  w->GR = (float*)(a + oGR); w->S = (float*)(a + oS); w->V = (float*)(a + oV);
+  w->pos = (float*)(a + opos); w->gpos = (float*)(a + ogpos); w->pnorm = (float*)(a + opn);
+  w->a2 = (float*)(a + oa2); w->b2 = (float*)(a + ob2); w->rowsum = (float*)(a + ors); w->colsum = (float*)(a + ocs);
+  w->pl = (float*)(a + opl); w->nl = (float*)(a + onl); w->regp = (float*)(a + oreg); w->wbar = (float*)(a + owb);
+  w->Mt = rescal ? (float*)(a + oMt) : nullptr;
+  return KGE_OK;
+}
+
+LaunchCtx lctx(kge_context* h, void* stream) { return LaunchCtx{(cudaStream_t)stream, &h->launches, h->num_sms}; }
+
+// NG (node-gradient accumulator) has to be zero when k_chain starts.  k_upd_nodes re-zeroes the
+// rows it consumes, so only a fresh / enlarged region needs an explicit fill.
+void ensure_ng_zero(kge_context* h, const StepParams& p, const StepWs& w, const LaunchCtx& c, bool force) {
+  size_t n = (size_t)p.U * p.D;
+  if (force || h->ng_dirty || h->ng_ptr != w.NG || h->ng_floats < n) {
+    launch_fill_zero(c, w.NG, (long long)n);
+    h->ng_ptr = w.NG;
+    h->ng_dirty = false;
+  }
+  h->ng_floats = n;   // only [0, n) is guaranteed zero after this step (the region beyond is reused)
+}
+
+int check_batch(const kge_batch_t* b, const StepParams& p) {
+  if (!b) return fail(KGE_ERR_INVALID_ARG, "batch is null");
+  if (!b->node_ids || !b->head_local || !b->tail_local || !b->rel_ids || !b->neg_ids)
+    return fail(KGE_ERR_INVALID_ARG, "batch has null index arrays");
+  if (b->n_nodes <= 0 || b->n_nodes > 2 * p.B) return fail(KGE_ERR_INVALID_ARG, "n_nodes=%lld out of (0, 2*batch]", (long long)b->n_nodes);
+  return KGE_OK;
+}
+
+BatchView bview(const kge_batch_t* b) {
+  return BatchView{(const long long*)b->node_ids, (const long long*)b->head_local, (const long long*)b->tail_local,
+                   (const long long*)b->rel_ids, (const long long*)b->neg_ids, b->edge_weight};
+}
+
+}  // namespace
+
+namespace kge {
+// RESCAL-specific row kernels (kge_rescal.cu)
+void launch_rescal_prep(const LaunchCtx&, const StepParams&, const TableView& ent, const TableView& rel,
+                        const BatchView&, const StepWs&);
+void launch_rescal_prep_dense(const LaunchCtx&, const StepParams&, const float* head, const float* relr,
+                              const float* tail, const StepWs&, bool want_pos, bool want_a);
+void launch_rescal_chain(const LaunchCtx&, const StepParams&, const TableView& ent, const TableView& rel,
+                         const BatchView&, const StepWs&);
+// tcgen05 engine (kge_umma.cu): returns false when the shape is not handled (caller falls back to engine 0)
+bool umma_supported(const StepParams&);
+int umma_score(const LaunchCtx&, const StepParams&, const StepWs&, char* err, size_t errlen);
+int umma_grad(const LaunchCtx&, const StepParams&, const StepWs&, bool side_b, char* err, size_t errlen);
+}  // namespace kge
+
+extern "C" {
+
+KGE_API int kge_abi_version(void) { return KGE_ABI_VERSION; }
+KGE_API const char* kge_last_error(void) { return g_err; }
+
+KGE_API int kge_create(int device, kge_handle_t* out) {
+  if (!out) return fail(KGE_ERR_INVALID_ARG, "out is null");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return fail(KGE_ERR_NO_DEVICE, "no CUDA device visible (%s); libkge_b200 has no CPU path", cudaGetErrorString(e));
+  }
+  if (device < 0 || device >= n) return fail(KGE_ERR_INVALID_ARG, "device %d out of range [0,%d)", device, n);
+  cudaDeviceProp prop;
+  KGE_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(KGE_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+  kge_context* h = new (std::nothrow) kge_context();
+  if (!h) return fail(KGE_ERR_NOMEM, "out of host memory");
+  h->device = device;
+  h->num_sms = prop.multiProcessorCount;
+  DeviceGuard g(device);
+  if (cudaMalloc(&h->dev_log4, 4 * sizeof(float)) != cudaSuccess) { delete h; return fail(KGE_ERR_NOMEM, "cudaMalloc failed"); }
+  *out = h;
+  return KGE_OK;
+}
+
+KGE_API int kge_destroy(kge_handle_t h) {
+  if (!h) return KGE_OK;
+  DeviceGuard g(h->device);
+  cudaDeviceSynchronize();
+  if (h->arena) cudaFree(h->arena);
+  if (h->dev_stage) cudaFree(h->dev_stage);
+  if (h->pin) cudaFreeHost(h->pin);
+  if (h->dev_log4) cudaFree(h->dev_log4);
+  delete h;
+  return KGE_OK;
+}
+
+KGE_API int64_t kge_launch_count(kge_handle_t h) { return h ? h->launches : 0; }
+
+KGE_API int kge_set_engine(kge_handle_t h, int engine) {
+  if (!h) return fail(KGE_ERR_INVALID_ARG, "handle is null");
+  if (engine < -1 || engine > 1) return fail(KGE_ERR_INVALID_ARG, "engine must be -1, 0 or 1");
+  h->engine = engine;
+  return KGE_OK;
+}
+
+KGE_API int kge_gather(kge_handle_t h, const kge_table_t* table, const int64_t* idx, int64_t n, float* out, void* stream) {
+  if (!h) return fail(KGE_ERR_INVALID_ARG, "handle is null");
+  if (n < 0) return fail(KGE_ERR_INVALID_ARG, "n < 0");
+  if (n == 0) return KGE_OK;
+  if (!idx || !out) return fail(KGE_ERR_INVALID_ARG, "idx/out is null");
+  TableView v;
+  int rc = make_view(table, &v, "gather");
+  if (rc) return rc;
+  DeviceGuard g(h->device);
+  launch_gather(lctx(h, stream), v, (const long long*)idx, n, out);
+  KGE_CUDA_OK(cudaGetLastError());
+  return KGE_OK;
+}
+
+static bool use_umma(kge_context* h, const StepParams& p) {
+  if (h->engine == 0) return false;
+  return umma_supported(p);
+}
+
+static int run_score(kge_context* h, const LaunchCtx& c, const StepParams& p, const StepWs& w) {
+  if (use_umma(h, p)) {
+    int rc = umma_score(c, p, w, g_err, sizeof(g_err));
+    if (rc) return rc;
+  } else {
+    launch_score(c, p, w);
+  }
+  return KGE_OK;
+}
+
+KGE_API int kge_score_pos(kge_handle_t h, const kge_step_cfg_t* cfg, const float* head, const float* rel, const float* tail,
+                  int64_t n, float* out, void* stream) {
+  if (!h) return fail(KGE_ERR_INVALID_ARG, "handle is null");
+  if (!cfg) return fail(KGE_ERR_INVALID_ARG, "cfg is null");
+  if (n == 0) return KGE_OK;
+  if (!head || !rel || !tail || !out || n < 0) return fail(KGE_ERR_INVALID_ARG, "bad arguments");
+  kge_step_cfg_t c2 = *cfg;
+  c2.batch = n; c2.chunk_size = (int32_t)1; c2.neg_sample_size = 1;
+  if (n > 0x7fffffffLL) return fail(KGE_ERR_INVALID_ARG, "n too large");
+  StepParams p;
+  int rc = make_params(&c2, 0, &p, false);
+  if (rc) return rc;
+  DeviceGuard g(h->device);
+  StepWs w{};
+  w.pos = out;
+  LaunchCtx c = lctx(h, stream);
+  if (p.model == KGE_RESCAL) launch_rescal_prep_dense(c, p, head, rel, tail, w, true, false);
+  else launch_prep_dense(c, p, head, rel, tail, nullptr, w, true, false);
+  KGE_CUDA_OK(cudaGetLastError());
+  return KGE_OK;
+}
+
+KGE_API int kge_score_neg(kge_handle_t h, const kge_step_cfg_t* cfg, const float* heads, const float* rel, const float* tails,
+                  float* out, void* stream) {
+  if (!h) return fail(KGE_ERR_INVALID_ARG, "handle is null");
+  if (!heads || !rel || !tails || !out) return fail(KGE_ERR_INVALID_ARG, "null pointer");
+  StepParams p;
+  int rc = make_params(cfg, 0, &p, false);
+  if (rc) return rc;
+  DeviceGuard g(h->device);
+  StepWs w{};
+  rc = carve(h, p, &w, (cudaStream_t)stream);
+  if (rc) return rc;
+  h->ng_ptr = nullptr;      // this carve overlays the node-gradient region
+  LaunchCtx c = lctx(h, stream);
+  // positives' entity rows / negative rows by corruption mode (general_models.py:405-406, 426-427)
+  const float* negrows = p.neg_head ? heads : tails;
+  if (p.model == KGE_RESCAL) launch_rescal_prep_dense(c, p, heads, rel, tails, w, false, true);
+  else launch_prep_dense(c, p, heads, rel, tails, negrows, w, false, true);
+  // the tile kernels read the negatives from w.Bn; point it at the caller's rows (read-only here)
+  StepWs w2 = w;
+  w2.Bn = const_cast<float*>(negrows);
+  w2.S = out;
+  rc = run_score(h, c, p, w2);
+  if (rc) return rc;
+  KGE_CUDA_OK(cudaGetLastError());
+  h->have_last = false;
+  return KGE_OK;
+}
+
+KGE_API int kge_loss_grad(kge_handle_t h, const kge_step_cfg_t* cfg, const float* pos, const float* neg, const float* wt,
+                  float* dpos, float* dneg, float* log4, void* stream) {
+  if (!h) return fail(KGE_ERR_INVALID_ARG, "handle is null");
+  if (!pos || !neg || !dpos || !dneg) return fail(KGE_ERR_INVALID_ARG, "null pointer");
+  StepParams p;
+  int rc = make_params(cfg, 0, &p, false);
+  if (rc) return rc;
+  p.model = KGE_DISTMULT;   // plain d loss / d score (no distance folding)
+  DeviceGuard g(h->device);
+  StepWs w{};
+  rc = carve(h, p, &w, (cudaStream_t)stream);
+  if (rc) return rc;
+  h->ng_ptr = nullptr;      // this carve overlays the node-gradient region
+  w.V = dneg;
+  w.gpos = dpos;
+  launch_loss(lctx(h, stream), p, pos, neg, wt, w, log4, false);
+  KGE_CUDA_OK(cudaGetLastError());
+  h->have_last = false;
+  return KGE_OK;
+}
+
+KGE_API int kge_adagrad(kge_handle_t h, const kge_table_t* table, const int64_t* idx, const float* grad, int64_t n, float lr,
+                void* stream) {
+  if (!h) return fail(KGE_ERR_INVALID_ARG, "handle is null");
+  if (n < 0) return fail(KGE_ERR_INVALID_ARG, "n < 0");
+  if (n == 0) return KGE_OK;
+  if (!idx || !grad) return fail(KGE_ERR_INVALID_ARG, "null pointer");
+  TableView v;
+  int rc = make_view(table, &v, "adagrad");
+  if (rc) return rc;
+  DeviceGuard g(h->device);
+  launch_adagrad(lctx(h, stream), v, (const long long*)idx, grad, n, lr);
+  KGE_CUDA_OK(cudaGetLastError());
+  return KGE_OK;
+}
+
+KGE_API int kge_forward_backward(kge_handle_t h, const kge_step_cfg_t* cfg, const kge_table_t* ent, const kge_table_t* rel,
+                         const kge_batch_t* batch, float* log4, void* stream) {
+  if (!h) return fail(KGE_ERR_INVALID_ARG, "handle is null");
+  StepParams p;
+  int rc = make_params(cfg, batch ? batch->n_nodes : 0, &p, true);
+  if (rc) return rc;
+  rc = check_batch(batch, p);
+  if (rc) return rc;
+  TableView ve, vr;
+  if ((rc = make_view(ent, &ve, "entity"))) return rc;
+  if ((rc = make_view(rel, &vr, "relation"))) return rc;
+  if (ve.dim != p.D || vr.dim != p.Dr)
+    return fail(KGE_ERR_INVALID_ARG, "table dims (%d,%d) do not match cfg (%d,%d)", ve.dim, vr.dim, p.D, p.Dr);
+  DeviceGuard g(h->device);
+  StepWs w{};
+  if ((rc = carve(h, p, &w, (cudaStream_t)stream))) return rc;
+  LaunchCtx c = lctx(h, stream);
+  BatchView b = bview(batch);
+  ensure_ng_zero(h, p, w, c, false);
+  if (p.model == KGE_RESCAL) launch_rescal_prep(c, p, ve, vr, b, w);
+  else launch_prep(c, p, ve, vr, b, w);
+  if ((rc = run_score(h, c, p, w))) return rc;
+  launch_loss(c, p, w.pos, w.S, b.edge_weight, w, log4 ? log4 : h->dev_log4, true);
+  if (use_umma(h, p)) {
+    if ((rc = umma_grad(c, p, w, false, g_err, sizeof(g_err)))) return rc;
+    if ((rc = umma_grad(c, p, w, true, g_err, sizeof(g_err)))) return rc;
+  } else {
+    launch_grad_a(c, p, w);
+    launch_grad_b(c, p, w);
+  }
+  if (p.model == KGE_RESCAL) launch_rescal_chain(c, p, ve, vr, b, w);
+  else launch_chain(c, p, ve, vr, b, w);
+  KGE_CUDA_OK(cudaGetLastError());
+  h->last_p = p; h->last_w = w; h->last_b = b; h->last_ent = ve; h->last_rel = vr; h->have_last = true;
+  h->ng_dirty = true;
+  return KGE_OK;
+}
+
+KGE_API int kge_update(kge_handle_t h, const kge_step_cfg_t* cfg, const kge_table_t* ent, const kge_table_t* rel,
+               const kge_batch_t* batch, void* stream) {
+  if (!h) return fail(KGE_ERR_INVALID_ARG, "handle is null");
+  if (!h->have_last) return fail(KGE_ERR_INVALID_ARG, "kge_update without a preceding kge_forward_backward");
+  StepParams p;
+  int rc = make_params(cfg, batch ? batch->n_nodes : 0, &p, true);
+  if (rc) return rc;
+  if ((rc = check_batch(batch, p))) return rc;
+  if (p.B != h->last_p.B || p.Nn != h->last_p.Nn || p.U != h->last_p.U || p.model != h->last_p.model)
+    return fail(KGE_ERR_INVALID_ARG, "kge_update cfg/batch differ from the preceding kge_forward_backward");
+  TableView ve, vr;
+  if ((rc = make_view(ent, &ve, "entity"))) return rc;
+  if ((rc = make_view(rel, &vr, "relation"))) return rc;
+  DeviceGuard g(h->device);
+  p.lr = cfg->lr;
+  launch_update(lctx(h, stream), p, ve, vr, bview(batch), h->last_w);
+  KGE_CUDA_OK(cudaGetLastError());
+  h->ng_dirty = false;
+  h->have_last = false;   // gradients consumed (NG re-zeroed, like `self.trace = []`, tensor_models.py:362)
+  return KGE_OK;
+}
+
+KGE_API int kge_step_fused(kge_handle_t h, const kge_step_cfg_t* cfg, const kge_table_t* ent, const kge_table_t* rel,
+                   const kge_batch_t* batch, float* log4, void* stream) {
+  int rc = kge_forward_backward(h, cfg, ent, rel, batch, log4, stream);
+  if (rc) return rc;
+  return kge_update(h, cfg, ent, rel, batch, stream);
+}
+
+KGE_API int kge_step_fused_host(kge_handle_t h, const kge_step_cfg_t* cfg, const kge_table_t* ent, const kge_table_t* rel,
+                        const kge_batch_t* bh, float* log4_host, void* stream) {
+  if (!h) return fail(KGE_ERR_INVALID_ARG, "handle is null");
+  if (!cfg || !bh) return fail(KGE_ERR_INVALID_ARG, "cfg/batch is null");
+  if (!bh->node_ids || !bh->head_local || !bh->tail_local || !bh->rel_ids || !bh->neg_ids)
+    return fail(KGE_ERR_INVALID_ARG, "batch has null index arrays");
+  if (cfg->batch <= 0 || cfg->chunk_size <= 0 || cfg->neg_sample_size <= 0 || cfg->batch % cfg->chunk_size)
+    return fail(KGE_ERR_INVALID_ARG, "bad batch/chunk sizes");
+  DeviceGuard g(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long B = cfg->batch, Nn = B / cfg->chunk_size * cfg->neg_sample_size, U = bh->n_nodes;
+  if (U <= 0 || U > 2 * B) return fail(KGE_ERR_INVALID_ARG, "n_nodes out of range");
+  const size_t n64 = (size_t)(U + 3 * B + Nn);
+  const size_t bytes = align_up(n64 * 8) + align_up(bh->edge_weight ? (size_t)B * 4 : 0) + 256;
+  if (bytes > h->stage_bytes) {
+    KGE_CUDA_OK(cudaStreamSynchronize(st));
+    if (h->pin) cudaFreeHost(h->pin);
+    if (h->dev_stage) cudaFree(h->dev_stage);
+    h->pin = nullptr; h->dev_stage = nullptr; h->stage_bytes = 0;
+    size_t cap = bytes + bytes / 2;
+    if (cudaMallocHost(&h->pin, cap) != cudaSuccess) { cudaGetLastError(); return fail(KGE_ERR_NOMEM, "cudaMallocHost(%zu) failed", cap); }
+    if (cudaMalloc(&h->dev_stage, cap) != cudaSuccess) { cudaGetLastError(); return fail(KGE_ERR_NOMEM, "cudaMalloc(%zu) failed", cap); }
+    h->stage_bytes = cap;
+  } else {
+    // the previous step's H2D copy must have drained before the pinned buffer is overwritten
+    KGE_CUDA_OK(cudaStreamSynchronize(st));
+  }
+  long long* ph = (long long*)h->pin;
+  long long* pd = (long long*)h->dev_stage;
+  size_t o = 0;
+  kge_batch_t bd{};
+  auto put = [&](const int64_t* src, long long n) { memcpy(ph + o, src, (size_t)n * 8); const int64_t* d = (const int64_t*)(pd + o); o += (size_t)n; return d; };
+  bd.node_ids = put(bh->node_ids, U); bd.n_nodes = U;
+  bd.head_local = put(bh->head_local, B);
+  bd.tail_local = put(bh->tail_local, B);
+  bd.rel_ids = put(bh->rel_ids, B);
+  bd.neg_ids = put(bh->neg_ids, Nn);
+  size_t wbytes = 0;
+  if (bh->edge_weight) {
+    size_t woff = align_up(n64 * 8);
+    memcpy(h->pin + woff, bh->edge_weight, (size_t)B * 4);
+    bd.edge_weight = (const float*)(h->dev_stage + woff);
+    wbytes = woff + (size_t)B * 4;
+  }
+  size_t copy_bytes = bh->edge_weight ? wbytes : n64 * 8;
+  KGE_CUDA_OK(cudaMemcpyAsync(h->dev_stage, h->pin, copy_bytes, cudaMemcpyHostToDevice, st));
+  int rc = kge_step_fused(h, cfg, ent, rel, &bd, h->dev_log4, stream);
+  if (rc) return rc;
+  if (log4_host) KGE_CUDA_OK(cudaMemcpyAsync(log4_host, h->dev_log4, 4 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  return KGE_OK;
+}
+
+KGE_API int kge_sync(kge_handle_t h, void* stream) {
+  if (!h) return fail(KGE_ERR_INVALID_ARG, "handle is null");
+  DeviceGuard g(h->device);
+  KGE_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
+  return KGE_OK;
+}
+
+KGE_API int kge_debug_read(kge_handle_t h, int which, float* out, int64_t n_floats, void* stream) {
+  if (!h || !out) return fail(KGE_ERR_INVALID_ARG, "null argument");
+  if (!h->have_last) return fail(KGE_ERR_INVALID_ARG, "no forward_backward result to read");
+  const StepParams& p = h->last_p;
+  const StepWs& w = h->last_w;
+  DeviceGuard g(h->device);
+  const float* src = nullptr;
+  long long n = 0;
+  switch (which) {
+    case KGE_BUF_POS_SCORE: src = w.pos; n = p.B; break;
+    case KGE_BUF_NEG_SCORE: src = w.S; n = p.B * p.Ns; break;
+    case KGE_BUF_NEG_GRAD: src = w.Bn; n = p.Nn * p.D; break;
+    case KGE_BUF_REL_GRAD: src = w.GR; n = p.B * (long long)p.Dr; break;
+    case KGE_BUF_NODE_GRAD:
+      n = p.U * p.D;
+      if (n_floats != n) return fail(KGE_ERR_INVALID_ARG, "expected %lld floats, got %lld", n, (long long)n_floats);
+      launch_node_grad_with_reg(lctx(h, stream), p, h->last_ent, h->last_b, w, out);
+      KGE_CUDA_OK(cudaGetLastError());
+      return KGE_OK;
+    default: return fail(KGE_ERR_INVALID_ARG, "unknown buffer %d", which);
+  }
+  if (n_floats != n) return fail(KGE_ERR_INVALID_ARG, "expected %lld floats, got %lld", n, (long long)n_floats);
+  KGE_CUDA_OK(cudaMemcpyAsync(out, src, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return KGE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,195 @@
+// kge_common.cuh -- shared device helpers for libkge_b200 (sm_100a only).
+//
+// Data model (DESIGN.md "HBM layout"):
+//   * embedding tables: fp32 row-major, row-range sharded over <= 8 GPUs (TableView); a row
+//     address on a remote shard is a peer-mapped pointer, so every kernel below works unchanged
+//     over NVLink (loads for the gather, red.add for the Adagrad scatter).
+//   * per-step workspace (StepWs): dense fp32 matrices that stay L2-resident between phases.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/kge_b200.h"
+
+namespace kge {
+
+constexpr int kWarp = 32;
+
+struct TableView {
+  float* emb[KGE_MAX_SHARDS];
+  float* state[KGE_MAX_SHARDS];
+  long long rows_per_shard;
+  long long num_rows;
+  int n_shards;
+  int dim;
+};
+
+__device__ __forceinline__ float* row_ptr(const TableView& t, long long id) {
+  if (t.n_shards == 1) return t.emb[0] + id * (long long)t.dim;
+  int s = (int)(id / t.rows_per_shard);
+  return t.emb[s] + (id - (long long)s * t.rows_per_shard) * (long long)t.dim;
+}
+__device__ __forceinline__ float* state_ptr(const TableView& t, long long id) {
+  if (t.n_shards == 1) return t.state[0] + id;
+  int s = (int)(id / t.rows_per_shard);
+  return t.state[s] + (id - (long long)s * t.rows_per_shard);
+}
+
+// Scalars of one step, passed by value to every kernel.
+struct StepParams {
+  int model;
+  int D;        // entity row length
+  int Dr;       // relation row length
+  float gamma, emb_init, lr, reg_coef;
+  int reg_norm;
+  int adversarial;
+  float adv_temperature;
+  int neg_head;
+  long long B;  // positives
+  int C, Cs, Ns;
+  long long Nn; // C * Ns negative rows
+  long long U;  // unique positive nodes
+};
+
+// Device workspace of one step (all pointers into the handle's arena).
+struct StepWs {
+  float* A;        // [B, D]   a-side rows (h+r, t-r, h*r, ...)
+  float* Bn;       // [Nn, D]  gathered negative rows; overwritten by their gradient
+  float* GA;       // [B, D]   d loss / d a
+  float* GR;       // [B, Dr]  d loss / d relation rows (per edge)
+  float* NG;       // [U, D]   d loss / d unique positive nodes (without reg), zero between steps
+  float* S;        // [B, Ns]  negative scores
+  float* V;        // [B, Ns]  backward coefficients
+  float* pos;      // [B]
+  float* gpos;     // [B]      d loss / d pos
+  float* pnorm;    // [B]      |h+r-t| (TransE_l2)
+  float* a2;       // [B]      |a|^2 (TransE_l2)
+  float* b2;       // [Nn]     |b|^2 (TransE_l2)
+  float* rowsum;   // [B]      sum_j V_ij (TransE_l2)
+  float* colsum;   // [Nn]     sum_i V_ij (TransE_l2)
+  float* pl;       // [B]      positive loss terms
+  float* nl;       // [B]      negative loss terms (already reduced over j)
+  float* regp;     // [B + Nn + U] partial sums of |x|^p
+  float* wbar;     // [1]      mean edge weight
+  float* Mt;       // [B, D]   RESCAL: M_r t  (tail mode needs it next to A = M_r h)
+};
+
+struct BatchView {
+  const long long* node_ids;
+  const long long* head_local;
+  const long long* tail_local;
+  const long long* rel_ids;
+  const long long* neg_ids;
+  const float* edge_weight;
+};
+
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+// streaming (read-once) table row load: do not allocate in L1
+__device__ __forceinline__ float4 ld4_stream(const float* p) {
+  float4 r;
+  asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+// vector fp32 reduction into global / peer memory (sm_90+: one 16-byte RED instead of four)
+__device__ __forceinline__ void red_add4(float* p, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};"
+               :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+#define KGE_F4_OP2(name, expr)                                                     \
+  __device__ __forceinline__ float4 name(float4 a, float4 b) {                     \
+    float4 r;                                                                      \
+    { float x = a.x, y = b.x; r.x = (expr); } { float x = a.y, y = b.y; r.y = (expr); } \
+    { float x = a.z, y = b.z; r.z = (expr); } { float x = a.w, y = b.w; r.w = (expr); } \
+    return r;                                                                      \
+  }
+KGE_F4_OP2(f4_add, x + y)
+KGE_F4_OP2(f4_sub, x - y)
+KGE_F4_OP2(f4_mul, x* y)
+#undef KGE_F4_OP2
+__device__ __forceinline__ float4 f4_scale(float4 a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
+__device__ __forceinline__ float4 f4_neg(float4 a) { return make_float4(-a.x, -a.y, -a.z, -a.w); }
+__device__ __forceinline__ float4 f4_fma(float4 a, float s, float4 c) {
+  return make_float4(fmaf(a.x, s, c.x), fmaf(a.y, s, c.y), fmaf(a.z, s, c.z), fmaf(a.w, s, c.w));
+}
+__device__ __forceinline__ float f4_hsum(float4 a) { return (a.x + a.y) + (a.z + a.w); }
+__device__ __forceinline__ float f4_dot(float4 a, float4 b) { return f4_hsum(f4_mul(a, b)); }
+__device__ __forceinline__ float sgnf(float x) { return (x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : 0.f); }
+
+// |x|^p  and  d/dx coef*|x|^p  (general_models.py:572-576: coef * norm(x, p)**p)
+__device__ __forceinline__ float abs_pow(float x, int p) {
+  float ax = fabsf(x);
+  if (p == 3) return ax * ax * ax;
+  if (p == 2) return ax * ax;
+  if (p == 1) return ax;
+  return powf(ax, (float)p);
+}
+__device__ __forceinline__ float reg_grad(float x, int p, float coef) {
+  if (coef == 0.f || p <= 0) return 0.f;
+  float ax = fabsf(x);
+  if (p == 3) return 3.f * coef * ax * x;
+  if (p == 2) return 2.f * coef * x;
+  if (p == 1) return coef * sgnf(x);
+  return coef * (float)p * powf(ax, (float)(p - 1)) * sgnf(x);
+}
+__device__ __forceinline__ float4 reg_grad4(float4 x, int p, float coef) {
+  return make_float4(reg_grad(x.x, p, coef), reg_grad(x.y, p, coef), reg_grad(x.z, p, coef), reg_grad(x.w, p, coef));
+}
+__device__ __forceinline__ float abs_pow4_sum(float4 x, int p) {
+  return (abs_pow(x.x, p) + abs_pow(x.y, p)) + (abs_pow(x.z, p) + abs_pow(x.w, p));
+}
+
+// -logsigmoid(-s) = softplus(s);  sigmoid(s)
+__device__ __forceinline__ float softplusf(float s) { return fmaxf(s, 0.f) + log1pf(expf(-fabsf(s))); }
+__device__ __forceinline__ float sigmoidf(float s) {
+  // stable on both tails
+  if (s >= 0.f) return 1.f / (1.f + expf(-s));
+  float e = expf(s);
+  return e / (1.f + e);
+}
+
+inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ------------------------------------------------------------------------------------------
+// host-side launchers (defined in kge_rows.cu / kge_tiles.cu / kge_rescal.cu)
+struct LaunchCtx {
+  cudaStream_t stream;
+  long long* launch_counter;
+  int num_sms;
+};
+
+void launch_gather(const LaunchCtx&, const TableView& t, const long long* idx, long long n, float* out);
+void launch_prep(const LaunchCtx&, const StepParams&, const TableView& ent, const TableView& rel,
+                 const BatchView&, const StepWs&);
+// dense-row variant used by kge_score_pos / kge_score_neg (rows already gathered)
+void launch_prep_dense(const LaunchCtx&, const StepParams&, const float* head, const float* relr,
+                       const float* tail, const float* negrows, const StepWs&, bool want_pos, bool want_a);
+void launch_score(const LaunchCtx&, const StepParams&, const StepWs&);
+void launch_loss(const LaunchCtx&, const StepParams&, const float* pos, const float* S, const float* w,
+                 const StepWs&, float* log4, bool want_reg);
+void launch_grad_a(const LaunchCtx&, const StepParams&, const StepWs&);
+void launch_grad_b(const LaunchCtx&, const StepParams&, const StepWs&);
+void launch_chain(const LaunchCtx&, const StepParams&, const TableView& ent, const TableView& rel,
+                  const BatchView&, const StepWs&);
+void launch_update(const LaunchCtx&, const StepParams&, const TableView& ent, const TableView& rel,
+                   const BatchView&, const StepWs&);
+void launch_adagrad(const LaunchCtx&, const TableView& t, const long long* idx, const float* grad,
+                    long long n, float lr);
+void launch_node_grad_with_reg(const LaunchCtx&, const StepParams&, const TableView& ent,
+                               const BatchView&, const StepWs&, float* out);
+void launch_fill_zero(const LaunchCtx&, float* p, long long n);
+
+}  // namespace kge

@@ -1,0 +1,601 @@
+// kge_rows.cu -- the row-streaming (HBM-bound) kernels of the step: one warp per embedding row,
+// 16-byte vector loads, warp-shuffle reductions for the per-row dot / norm.
+//
+//   k_gather      ExternalEmbedding.__call__            tensor_models.py:270-302
+//   k_prep        gather + edge_func + a-side of create_neg   score_fun.py:54-59,91-108,229-235,
+//                 268-286,297-307,345-376,460-472,512-554 ; general_models.py:548-553
+//   k_loss        LossGenerator.get_total_loss + its gradient loss.py:69-98
+//   k_chain       autograd of edge_func / a-side back to h, r, t  (loss.backward(), train_pytorch.py:145)
+//   k_upd_*       ExternalEmbedding.update              tensor_models.py:304-362
+#include "kge_common.cuh"
+
+namespace kge {
+
+#define KGE_LAUNCH(ctx, kernel, grid, block, smem, ...)                         \
+  do {                                                                          \
+    kernel<<<(grid), (block), (smem), (ctx).stream>>>(__VA_ARGS__);             \
+    if ((ctx).launch_counter) ++*(ctx).launch_counter;                          \
+  } while (0)
+
+constexpr int kRowBlock = 256;               // 8 warps = 8 row jobs per CTA
+constexpr int kWarpsPerBlock = kRowBlock / kWarp;
+
+// ------------------------------------------------------------------------------------------ a3
+__global__ void __launch_bounds__(kRowBlock) k_gather(TableView t, const long long* __restrict__ idx,
+                                                       long long n, float* __restrict__ out) {
+  long long job = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (job >= n) return;
+  int lane = threadIdx.x & 31;
+  const float* src = row_ptr(t, idx[job]);
+  float* dst = out + job * (long long)t.dim;
+  int nv = t.dim >> 2;
+  for (int v = lane; v < nv; v += kWarp) st4(dst + 4 * v, ld4_stream(src + 4 * v));
+  for (int k = (nv << 2) + lane; k < t.dim; k += kWarp) dst[k] = src[k];   // dim % 4 tail
+}
+
+void launch_gather(const LaunchCtx& c, const TableView& t, const long long* idx, long long n, float* out) {
+  if (n <= 0) return;
+  KGE_LAUNCH(c, k_gather, ceil_div(n, kWarpsPerBlock), kRowBlock, 0, t, idx, n, out);
+}
+
+__global__ void k_fill_zero(float* p, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) p[i] = 0.f;
+}
+void launch_fill_zero(const LaunchCtx& c, float* p, long long n) {
+  if (n <= 0) return;
+  int grid = (int)((n + 1023) / 1024);
+  if (grid > c.num_sms * 8) grid = c.num_sms * 8;
+  KGE_LAUNCH(c, k_fill_zero, grid, 256, 0, p, n);
+}
+
+// ------------------------------------------------------------------------------------ a4 + a5(a)
+// Per-edge model math on one 4-wide slice.  For the complex models a "slice" is 4 real parts plus
+// the 4 matching imaginary parts (rows are [re | im]).
+struct EdgeAcc {
+  float pos;   // running sum for the positive score
+  float a2;    // |a|^2 (TransE_l2)
+  float reg;   // sum |r|^p
+};
+
+template <int MODEL>
+__device__ __forceinline__ void edge_slice_real(float4 h, float4 r, float4 t, int neg_head, float4& a,
+                                                EdgeAcc& acc) {
+  if (MODEL == KGE_TRANSE_L1 || MODEL == KGE_TRANSE_L2) {
+    float4 e = f4_sub(f4_add(h, r), t);
+    if (MODEL == KGE_TRANSE_L2) acc.pos += f4_dot(e, e);
+    else acc.pos += (fabsf(e.x) + fabsf(e.y)) + (fabsf(e.z) + fabsf(e.w));
+    a = neg_head ? f4_sub(t, r) : f4_add(h, r);
+    if (MODEL == KGE_TRANSE_L2) acc.a2 += f4_dot(a, a);
+  } else {  // DistMult
+    acc.pos += f4_hsum(f4_mul(f4_mul(h, r), t));
+    a = neg_head ? f4_mul(t, r) : f4_mul(h, r);
+  }
+}
+
+// complex slice: (hr,hi) head, (tr,ti) tail, (cr,ci) = relation as complex number
+// (ComplEx: the row itself; RotatE: cos/sin of the phase)
+template <int MODEL>
+__device__ __forceinline__ void edge_slice_cplx(float4 hr, float4 hi, float4 tr, float4 ti, float4 cr, float4 ci,
+                                                int neg_head, float4& are, float4& aim, EdgeAcc& acc) {
+  if (MODEL == KGE_COMPLEX) {
+    // score_fun.py:297-307
+    float4 s = f4_sub(f4_add(f4_add(f4_mul(f4_mul(hr, tr), cr), f4_mul(f4_mul(hi, ti), cr)),
+                             f4_mul(f4_mul(hr, ti), ci)),
+                      f4_mul(f4_mul(hi, tr), ci));
+    acc.pos += f4_hsum(s);
+  } else {
+    // score_fun.py:460-472
+    float4 dre = f4_sub(f4_sub(f4_mul(hr, cr), f4_mul(hi, ci)), tr);
+    float4 dim = f4_sub(f4_add(f4_mul(hr, ci), f4_mul(hi, cr)), ti);
+    acc.pos += (sqrtf(dre.x * dre.x + dim.x * dim.x) + sqrtf(dre.y * dre.y + dim.y * dim.y)) +
+               (sqrtf(dre.z * dre.z + dim.z * dim.z) + sqrtf(dre.w * dre.w + dim.w * dim.w));
+  }
+  if (neg_head) {   // conj(rel) * tail   (score_fun.py:353-355, 523-524)
+    are = f4_add(f4_mul(tr, cr), f4_mul(ti, ci));
+    aim = f4_add(f4_mul(f4_neg(tr), ci), f4_mul(ti, cr));
+  } else {          // head * rel         (score_fun.py:369-371, 542-543)
+    are = f4_sub(f4_mul(hr, cr), f4_mul(hi, ci));
+    aim = f4_add(f4_mul(hr, ci), f4_mul(hi, cr));
+  }
+}
+
+__device__ __forceinline__ void phase_cos_sin(float4 r, float inv_scale_den, float4& c, float4& s) {
+  // phase = r / (emb_init / pi)   (score_fun.py:464)
+  float p0 = r.x / inv_scale_den, p1 = r.y / inv_scale_den, p2 = r.z / inv_scale_den, p3 = r.w / inv_scale_den;
+  sincosf(p0, &s.x, &c.x); sincosf(p1, &s.y, &c.y); sincosf(p2, &s.z, &c.z); sincosf(p3, &s.w, &c.w);
+}
+
+// One warp = one edge.  h/r/t are row pointers (table rows or dense rows).
+template <int MODEL>
+__device__ __forceinline__ void edge_forward(const StepParams& p, const float* __restrict__ h,
+                                             const float* __restrict__ r, const float* __restrict__ t,
+                                             float* __restrict__ a_out, int lane, float& pos_out, float& a2_out,
+                                             float& reg_out, float& nrm_out, bool want_a) {
+  EdgeAcc acc{0.f, 0.f, 0.f};
+  const bool reg_on = (p.reg_coef > 0.f && p.reg_norm > 0);
+  if (MODEL == KGE_COMPLEX || MODEL == KGE_ROTATE) {
+    const int half = p.D >> 1, nvh = half >> 2;
+    const float den = p.emb_init / 3.14159265358979323846f;
+    for (int v = lane; v < nvh; v += kWarp) {
+      float4 hr = ld4(h + 4 * v), hi = ld4(h + half + 4 * v);
+      float4 tr = ld4(t + 4 * v), ti = ld4(t + half + 4 * v);
+      float4 cr, ci;
+      if (MODEL == KGE_COMPLEX) {
+        cr = ld4(r + 4 * v); ci = ld4(r + half + 4 * v);
+        if (reg_on) acc.reg += abs_pow4_sum(cr, p.reg_norm) + abs_pow4_sum(ci, p.reg_norm);
+      } else {
+        float4 ph = ld4(r + 4 * v);
+        if (reg_on) acc.reg += abs_pow4_sum(ph, p.reg_norm);
+        phase_cos_sin(ph, den, cr, ci);
+      }
+      float4 are, aim;
+      edge_slice_cplx<MODEL>(hr, hi, tr, ti, cr, ci, p.neg_head, are, aim, acc);
+      if (want_a) { st4(a_out + 4 * v, are); st4(a_out + half + 4 * v, aim); }
+    }
+  } else {
+    const int nv = p.D >> 2;
+    for (int v = lane; v < nv; v += kWarp) {
+      float4 h4 = ld4(h + 4 * v), r4 = ld4(r + 4 * v), t4 = ld4(t + 4 * v);
+      if (reg_on) acc.reg += abs_pow4_sum(r4, p.reg_norm);
+      float4 a;
+      edge_slice_real<MODEL>(h4, r4, t4, p.neg_head, a, acc);
+      if (want_a) st4(a_out + 4 * v, a);
+    }
+  }
+  float s = warp_sum(acc.pos);
+  a2_out = warp_sum(acc.a2);
+  reg_out = warp_sum(acc.reg);
+  nrm_out = 0.f;
+  if (MODEL == KGE_TRANSE_L2) { nrm_out = sqrtf(s); pos_out = p.gamma - nrm_out; }
+  else if (MODEL == KGE_TRANSE_L1 || MODEL == KGE_ROTATE) pos_out = p.gamma - s;
+  else pos_out = s;
+}
+
+// Job space of k_prep: [0,B) edges | [B, B+Nn) negatives | [B+Nn, B+Nn+U) unique nodes (reg only)
+template <int MODEL>
+__global__ void __launch_bounds__(kRowBlock) k_prep(StepParams p, TableView ent, TableView rel, BatchView b, StepWs w,
+                                                     long long job0) {
+  long long job = job0 + (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const bool reg_on = (p.reg_coef > 0.f && p.reg_norm > 0);
+  if (job < p.B) {
+    const float* h = row_ptr(ent, b.node_ids[b.head_local[job]]);
+    const float* t = row_ptr(ent, b.node_ids[b.tail_local[job]]);
+    const float* r = row_ptr(rel, b.rel_ids[job]);
+    float pos, a2, reg, nrm;
+    edge_forward<MODEL>(p, h, r, t, w.A + job * (long long)p.D, lane, pos, a2, reg, nrm, true);
+    if (lane == 0) {
+      w.pos[job] = pos;
+      if (MODEL == KGE_TRANSE_L2) { w.a2[job] = a2; w.pnorm[job] = nrm; }
+      w.regp[job] = reg;
+    }
+    return;
+  }
+  job -= p.B;
+  if (job < p.Nn) {
+    const float* src = row_ptr(ent, b.neg_ids[job]);
+    float* dst = w.Bn + job * (long long)p.D;
+    float b2 = 0.f, reg = 0.f;
+    for (int v = lane; v < (p.D >> 2); v += kWarp) {
+      float4 x = ld4_stream(src + 4 * v);
+      st4(dst + 4 * v, x);
+      if (MODEL == KGE_TRANSE_L2) b2 += f4_dot(x, x);
+      if (reg_on) reg += abs_pow4_sum(x, p.reg_norm);
+    }
+    b2 = warp_sum(b2); reg = warp_sum(reg);
+    if (lane == 0) {
+      if (MODEL == KGE_TRANSE_L2) w.b2[job] = b2;
+      w.regp[p.B + job] = reg;
+    }
+    return;
+  }
+  job -= p.Nn;
+  if (job < p.U && reg_on) {
+    const float* src = row_ptr(ent, b.node_ids[job]);
+    float reg = 0.f;
+    for (int v = lane; v < (p.D >> 2); v += kWarp) reg += abs_pow4_sum(ld4(src + 4 * v), p.reg_norm);
+    reg = warp_sum(reg);
+    if (lane == 0) w.regp[p.B + p.Nn + job] = reg;
+  }
+}
+
+// dense-row variant: kge_score_pos (want_pos) / kge_score_neg (want_a + negatives' norms)
+template <int MODEL>
+__global__ void __launch_bounds__(kRowBlock) k_prep_dense(StepParams p, const float* __restrict__ head,
+                                                           const float* __restrict__ relr,
+                                                           const float* __restrict__ tail,
+                                                           const float* __restrict__ negrows, StepWs w,
+                                                           bool want_pos, bool want_a) {
+  long long job = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (job < p.B) {
+    float pos, a2, reg, nrm;
+    const float* hrow = head + job * (long long)p.D;
+    const float* trow = tail + job * (long long)p.D;
+    // kge_score_neg passes the negatives in place of the corrupted side: only the kept side is read
+    if (!want_pos) { if (p.neg_head) hrow = trow; else trow = hrow; }
+    edge_forward<MODEL>(p, hrow, relr + job * (long long)p.Dr, trow,
+                        want_a ? w.A + job * (long long)p.D : nullptr, lane, pos, a2, reg, nrm, want_a);
+    if (lane == 0) {
+      if (want_pos) w.pos[job] = pos;
+      if (want_a && MODEL == KGE_TRANSE_L2) w.a2[job] = a2;
+    }
+    return;
+  }
+  job -= p.B;
+  if (job < p.Nn && negrows != nullptr && MODEL == KGE_TRANSE_L2) {
+    const float* src = negrows + job * (long long)p.D;
+    float b2 = 0.f;
+    for (int v = lane; v < (p.D >> 2); v += kWarp) { float4 x = ld4(src + 4 * v); b2 += f4_dot(x, x); }
+    b2 = warp_sum(b2);
+    if (lane == 0) w.b2[job] = b2;
+  }
+}
+
+#define KGE_DISPATCH_MODEL(model, ...)                                      \
+  switch (model) {                                                          \
+    case KGE_TRANSE_L1: { constexpr int M = KGE_TRANSE_L1; __VA_ARGS__; } break; \
+    case KGE_TRANSE_L2: { constexpr int M = KGE_TRANSE_L2; __VA_ARGS__; } break; \
+    case KGE_DISTMULT:  { constexpr int M = KGE_DISTMULT;  __VA_ARGS__; } break; \
+    case KGE_COMPLEX:   { constexpr int M = KGE_COMPLEX;   __VA_ARGS__; } break; \
+    case KGE_ROTATE:    { constexpr int M = KGE_ROTATE;    __VA_ARGS__; } break; \
+    default: break;                                                         \
+  }
+
+void launch_prep(const LaunchCtx& c, const StepParams& p, const TableView& ent, const TableView& rel,
+                 const BatchView& b, const StepWs& w) {
+  const bool reg_on = (p.reg_coef > 0.f && p.reg_norm > 0);
+  long long jobs = p.B + p.Nn + (reg_on ? p.U : 0);
+  KGE_DISPATCH_MODEL(p.model, KGE_LAUNCH(c, k_prep<M>, ceil_div(jobs, kWarpsPerBlock), kRowBlock, 0, p, ent, rel, b, w, 0LL));
+}
+
+// negatives + unique-node jobs only (RESCAL runs its own per-edge kernel)
+void launch_prep_nonedge(const LaunchCtx& c, const StepParams& p, const TableView& ent, const TableView& rel,
+                         const BatchView& b, const StepWs& w) {
+  const bool reg_on = (p.reg_coef > 0.f && p.reg_norm > 0);
+  long long jobs = p.Nn + (reg_on ? p.U : 0);
+  KGE_LAUNCH(c, k_prep<KGE_DISTMULT>, ceil_div(jobs, kWarpsPerBlock), kRowBlock, 0, p, ent, rel, b, w, p.B);
+}
+
+void launch_prep_dense(const LaunchCtx& c, const StepParams& p, const float* head, const float* relr,
+                       const float* tail, const float* negrows, const StepWs& w, bool want_pos, bool want_a) {
+  long long jobs = p.B + ((negrows && p.model == KGE_TRANSE_L2) ? p.Nn : 0);
+  KGE_DISPATCH_MODEL(p.model, KGE_LAUNCH(c, k_prep_dense<M>, ceil_div(jobs, kWarpsPerBlock), kRowBlock, 0, p, head,
+                                         relr, tail, negrows, w, want_pos, want_a));
+}
+
+// ------------------------------------------------------------------------------------------ a7
+// One warp per positive i: reads its Ns negative scores, writes the backward coefficients
+//   V_ij = dL/dneg_ij (bilinear, l1, RotatE)  |  dL/dneg_ij / dist_ij (TransE_l2),
+// the per-row loss terms, dL/dpos_i, and (TransE_l2) sum_j V_ij.
+__global__ void __launch_bounds__(kRowBlock) k_loss(StepParams p, const float* __restrict__ pos,
+                                                     const float* __restrict__ S, const float* __restrict__ wt,
+                                                     const float* __restrict__ wbar, float* __restrict__ V,
+                                                     float* __restrict__ gpos, float* __restrict__ rowsum,
+                                                     float* __restrict__ pl, float* __restrict__ nl) {
+  long long i = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (i >= p.B) return;
+  const int lane = threadIdx.x & 31;
+  const float* s = S + i * (long long)p.Ns;
+  float* v = V + i * (long long)p.Ns;
+  const float w_i = wt ? wt[i] : 1.f;
+  const float inv2B = 0.5f / (float)p.B;
+  float mx = -INFINITY, den = 1.f;
+  if (p.adversarial) {
+    for (int j = lane; j < p.Ns; j += kWarp) mx = fmaxf(mx, s[j] * p.adv_temperature);
+    mx = warp_max(mx);
+    float d = 0.f;
+    for (int j = lane; j < p.Ns; j += kWarp) d += expf(s[j] * p.adv_temperature - mx);
+    den = warp_sum(d);
+  }
+  float nls = 0.f, rs = 0.f;
+  const float uni = 1.f / (float)p.Ns;
+  for (int j = lane; j < p.Ns; j += kWarp) {
+    float sc = s[j];
+    float pij = p.adversarial ? expf(sc * p.adv_temperature - mx) / den : uni;
+    nls += pij * (softplusf(sc) * w_i);
+    float g = pij * sigmoidf(sc) * w_i * inv2B;       // dL/dneg_ij
+    float coef = g;
+    if (p.model == KGE_TRANSE_L2) { float dist = v[j]; coef = g / dist; rs += coef; }   // v[j] = |a-b| from k_score
+    v[j] = coef;
+  }
+  nls = warp_sum(nls);
+  rs = warp_sum(rs);
+  if (lane == 0) {
+    float ps = pos[i];
+    float wb = wt ? *wbar : 1.f;        // loss.py:75,82: [B] * [B,1] -> mean(pl) * mean(w)
+    pl[i] = softplusf(-ps);
+    nl[i] = nls;
+    gpos[i] = -sigmoidf(-ps) * wb * inv2B;
+    if (p.model == KGE_TRANSE_L2) rowsum[i] = rs;
+  }
+}
+
+__global__ void k_colsum(StepParams p, const float* __restrict__ V, float* __restrict__ colsum) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= p.Nn) return;
+  long long c = t / p.Ns; int j = (int)(t - c * p.Ns);
+  const float* v = V + (c * p.Cs) * (long long)p.Ns + j;
+  float s = 0.f;
+  for (int i = 0; i < p.Cs; ++i) s += v[(long long)i * p.Ns];
+  colsum[t] = s;
+}
+
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+  v = warp_sum(v);
+  int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  float r = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0.f;
+  if (w == 0) r = warp_sum(r);
+  return r;   // valid in warp 0
+}
+
+__global__ void __launch_bounds__(1024) k_mean(const float* __restrict__ x, long long n, float* __restrict__ out) {
+  __shared__ float sh[32];
+  float s = 0.f;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) s += x[i];
+  s = block_sum(s, sh);
+  if (threadIdx.x == 0) *out = s / (float)n;
+}
+
+// log4 = {pos_loss, neg_loss, loss (no reg), reg}
+__global__ void __launch_bounds__(1024) k_reduce_log(StepParams p, const float* __restrict__ pl,
+                                                      const float* __restrict__ nl, const float* __restrict__ regp,
+                                                      long long nreg, const float* __restrict__ wbar,
+                                                      float* __restrict__ log4) {
+  __shared__ float sh[32];
+  float a = 0.f, b = 0.f, r = 0.f;
+  for (long long i = threadIdx.x; i < p.B; i += blockDim.x) { a += pl[i]; b += nl[i]; }
+  for (long long i = threadIdx.x; i < nreg; i += blockDim.x) r += regp[i];
+  a = block_sum(a, sh);
+  b = block_sum(b, sh);
+  r = block_sum(r, sh);
+  if (threadIdx.x == 0) {
+    float pos_loss = a / (float)p.B * (wbar ? *wbar : 1.f);
+    float neg_loss = b / (float)p.B;
+    log4[0] = pos_loss; log4[1] = neg_loss; log4[2] = (neg_loss + pos_loss) / 2.f;
+    log4[3] = p.reg_coef * r;
+  }
+}
+
+void launch_loss(const LaunchCtx& c, const StepParams& p, const float* pos, const float* S, const float* wt,
+                 const StepWs& w, float* log4, bool want_reg) {
+  if (wt) KGE_LAUNCH(c, k_mean, 1, 1024, 0, wt, p.B, w.wbar);
+  KGE_LAUNCH(c, k_loss, ceil_div(p.B, kWarpsPerBlock), kRowBlock, 0, p, pos, S, wt, w.wbar, w.V, w.gpos, w.rowsum,
+             w.pl, w.nl);
+  if (p.model == KGE_TRANSE_L2) KGE_LAUNCH(c, k_colsum, ceil_div(p.Nn, 256), 256, 0, p, w.V, w.colsum);
+  const bool reg_on = want_reg && (p.reg_coef > 0.f && p.reg_norm > 0);
+  if (log4)
+    KGE_LAUNCH(c, k_reduce_log, 1, 1024, 0, p, w.pl, w.nl, w.regp, reg_on ? (p.B + p.Nn + p.U) : 0,
+               wt ? w.wbar : nullptr, log4);
+}
+
+// ------------------------------------------------------------------------------------------ a9
+// One warp per edge: autograd of edge_func and of the a-side, given GA = dL/da (from the
+// contraction kernels) and gpos = dL/dpos.  Emits
+//   NG[head_local] += dL/dh,  NG[tail_local] += dL/dt          (red.add, L2-resident workspace)
+//   GR[i] = dL/dr_i + reg'(r_i),  rel.state_sum[rel_id] += mean(GR[i]^2)   (Adagrad phase 1, a10)
+template <int MODEL>
+__global__ void __launch_bounds__(kRowBlock) k_chain(StepParams p, TableView ent, TableView rel, BatchView b, StepWs w) {
+  const long long i = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (i >= p.B) return;
+  const int lane = threadIdx.x & 31;
+  const long long hl = b.head_local[i], tl = b.tail_local[i], rid = b.rel_ids[i];
+  const float* h = row_ptr(ent, b.node_ids[hl]);
+  const float* t = row_ptr(ent, b.node_ids[tl]);
+  const float* r = row_ptr(rel, rid);
+  const float* ga = w.GA + i * (long long)p.D;
+  float* ngh = w.NG + hl * (long long)p.D;
+  float* ngt = w.NG + tl * (long long)p.D;
+  float* gr = w.GR + i * (long long)p.Dr;
+  const float gp = w.gpos[i];
+  float gs = 0.f;
+
+  if (MODEL == KGE_COMPLEX || MODEL == KGE_ROTATE) {
+    const int half = p.D >> 1, nvh = half >> 2;
+    const float den = p.emb_init / 3.14159265358979323846f;
+    for (int v = lane; v < nvh; v += kWarp) {
+      float4 hr = ld4(h + 4 * v), hi = ld4(h + half + 4 * v);
+      float4 tr = ld4(t + 4 * v), ti = ld4(t + half + 4 * v);
+      float4 gre = ld4(ga + 4 * v), gim = ld4(ga + half + 4 * v);
+      float4 cr, ci, ph;
+      if (MODEL == KGE_COMPLEX) { cr = ld4(r + 4 * v); ci = ld4(r + half + 4 * v); }
+      else { ph = ld4(r + 4 * v); phase_cos_sin(ph, den, cr, ci); }
+      float4 dhr, dhi, dtr, dti, dcr, dci;   // d/d(head), d/d(tail), d/d(rel as complex)
+      if (MODEL == KGE_COMPLEX) {
+        // pos = sum hr*tr*cr + hi*ti*cr + hr*ti*ci - hi*tr*ci
+        dhr = f4_scale(f4_add(f4_mul(tr, cr), f4_mul(ti, ci)), gp);
+        dhi = f4_scale(f4_sub(f4_mul(ti, cr), f4_mul(tr, ci)), gp);
+        dtr = f4_scale(f4_sub(f4_mul(hr, cr), f4_mul(hi, ci)), gp);
+        dti = f4_scale(f4_add(f4_mul(hi, cr), f4_mul(hr, ci)), gp);
+        dcr = f4_scale(f4_add(f4_mul(hr, tr), f4_mul(hi, ti)), gp);
+        dci = f4_scale(f4_sub(f4_mul(hr, ti), f4_mul(hi, tr)), gp);
+      } else {
+        // pos = gamma - sum sqrt(dre^2 + dim^2)
+        float4 dre = f4_sub(f4_sub(f4_mul(hr, cr), f4_mul(hi, ci)), tr);
+        float4 dim = f4_sub(f4_add(f4_mul(hr, ci), f4_mul(hi, cr)), ti);
+        float4 qre, qim;
+#define KGE_Q(c_)                                                                    \
+        { float m = sqrtf(dre.c_ * dre.c_ + dim.c_ * dim.c_); float s_ = (m > 0.f) ? (-gp / m) : 0.f; \
+          qre.c_ = dre.c_ * s_; qim.c_ = dim.c_ * s_; }
+        KGE_Q(x) KGE_Q(y) KGE_Q(z) KGE_Q(w)
+#undef KGE_Q
+        dhr = f4_add(f4_mul(qre, cr), f4_mul(qim, ci));
+        dhi = f4_sub(f4_mul(qim, cr), f4_mul(qre, ci));
+        dtr = f4_neg(qre);
+        dti = f4_neg(qim);
+        dcr = f4_add(f4_mul(qre, hr), f4_mul(qim, hi));
+        dci = f4_sub(f4_mul(qim, hr), f4_mul(qre, hi));
+      }
+      if (p.neg_head) {   // a = conj(c) * t
+        dtr = f4_add(dtr, f4_sub(f4_mul(gre, cr), f4_mul(gim, ci)));
+        dti = f4_add(dti, f4_add(f4_mul(gre, ci), f4_mul(gim, cr)));
+        dcr = f4_add(dcr, f4_add(f4_mul(gre, tr), f4_mul(gim, ti)));
+        dci = f4_add(dci, f4_sub(f4_mul(gre, ti), f4_mul(gim, tr)));
+      } else {            // a = h * c
+        dhr = f4_add(dhr, f4_add(f4_mul(gre, cr), f4_mul(gim, ci)));
+        dhi = f4_add(dhi, f4_sub(f4_mul(gim, cr), f4_mul(gre, ci)));
+        dcr = f4_add(dcr, f4_add(f4_mul(gre, hr), f4_mul(gim, hi)));
+        dci = f4_add(dci, f4_sub(f4_mul(gim, hr), f4_mul(gre, hi)));
+      }
+      red_add4(ngh + 4 * v, dhr); red_add4(ngh + half + 4 * v, dhi);
+      red_add4(ngt + 4 * v, dtr); red_add4(ngt + half + 4 * v, dti);
+      if (MODEL == KGE_COMPLEX) {
+        float4 g0 = f4_add(dcr, reg_grad4(cr, p.reg_norm, p.reg_coef));
+        float4 g1 = f4_add(dci, reg_grad4(ci, p.reg_norm, p.reg_coef));
+        st4(gr + 4 * v, g0); st4(gr + half + 4 * v, g1);
+        gs += f4_dot(g0, g0) + f4_dot(g1, g1);
+      } else {
+        // d/dphase = -dc*sin + ds*cos ; d/dr = d/dphase / (emb_init/pi)
+        float4 dth = f4_sub(f4_mul(dci, cr), f4_mul(dcr, ci));
+        float4 g0 = make_float4(dth.x / den, dth.y / den, dth.z / den, dth.w / den);
+        g0 = f4_add(g0, reg_grad4(ph, p.reg_norm, p.reg_coef));
+        st4(gr + 4 * v, g0);
+        gs += f4_dot(g0, g0);
+      }
+    }
+  } else {
+    const int nv = p.D >> 2;
+    float nrm_scale = 0.f, rsum = 0.f;
+    if (MODEL == KGE_TRANSE_L2) {
+      float n = w.pnorm[i];                  // |h + r - t| as computed by the forward
+      nrm_scale = (n > 0.f) ? (-gp / n) : 0.f;
+      rsum = w.rowsum[i];
+    }
+    for (int v = lane; v < nv; v += kWarp) {
+      float4 h4 = ld4(h + 4 * v), r4 = ld4(r + 4 * v), t4 = ld4(t + 4 * v), g4 = ld4(ga + 4 * v);
+      float4 dh, dt, dr;
+      if (MODEL == KGE_TRANSE_L1 || MODEL == KGE_TRANSE_L2) {
+        float4 e = f4_sub(f4_add(h4, r4), t4);
+        float4 u;   // gpos * dpos/dh
+        if (MODEL == KGE_TRANSE_L2) u = f4_scale(e, nrm_scale);
+        else u = make_float4(-gp * sgnf(e.x), -gp * sgnf(e.y), -gp * sgnf(e.z), -gp * sgnf(e.w));
+        float4 a = p.neg_head ? f4_sub(t4, r4) : f4_add(h4, r4);
+        float4 gA = (MODEL == KGE_TRANSE_L2) ? f4_fma(a, -rsum, g4) : g4;   // GA - rowsum * a
+        if (p.neg_head) { dt = f4_sub(gA, u); dr = f4_sub(u, gA); dh = u; }
+        else            { dh = f4_add(u, gA); dr = dh; dt = f4_neg(u); }
+      } else {  // DistMult
+        dh = f4_scale(f4_mul(r4, t4), gp);
+        dr = f4_scale(f4_mul(h4, t4), gp);
+        dt = f4_scale(f4_mul(h4, r4), gp);
+        if (p.neg_head) { dt = f4_add(dt, f4_mul(g4, r4)); dr = f4_add(dr, f4_mul(g4, t4)); }
+        else            { dh = f4_add(dh, f4_mul(g4, r4)); dr = f4_add(dr, f4_mul(g4, h4)); }
+      }
+      red_add4(ngh + 4 * v, dh);
+      red_add4(ngt + 4 * v, dt);
+      dr = f4_add(dr, reg_grad4(r4, p.reg_norm, p.reg_coef));
+      st4(gr + 4 * v, dr);
+      gs += f4_dot(dr, dr);
+    }
+  }
+  gs = warp_sum(gs);
+  if (lane == 0) atomicAdd(state_ptr(rel, rid), gs / (float)p.Dr);
+}
+
+void launch_chain(const LaunchCtx& c, const StepParams& p, const TableView& ent, const TableView& rel,
+                  const BatchView& b, const StepWs& w) {
+  KGE_DISPATCH_MODEL(p.model, KGE_LAUNCH(c, k_chain<M>, ceil_div(p.B, kWarpsPerBlock), kRowBlock, 0, p, ent, rel, b, w));
+}
+
+// ------------------------------------------------------------------------------------------ a10
+// Entity entry 1: the unique positive nodes (indices unique => no atomics, state and row are
+// updated by the same warp).  Also re-zeroes NG for the next step.
+__global__ void __launch_bounds__(kRowBlock) k_upd_nodes(StepParams p, TableView ent, BatchView b, StepWs w) {
+  const long long u = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (u >= p.U) return;
+  const int lane = threadIdx.x & 31;
+  const long long id = b.node_ids[u];
+  float* row = row_ptr(ent, id);
+  float* ng = w.NG + u * (long long)p.D;
+  const int nv = p.D >> 2;
+  float gs = 0.f;
+  for (int v = lane; v < nv; v += kWarp) {
+    float4 g = f4_add(ld4(ng + 4 * v), reg_grad4(ld4(row + 4 * v), p.reg_norm, p.reg_coef));
+    gs += f4_dot(g, g);
+  }
+  gs = warp_sum(gs) / (float)p.D;
+  float* st = state_ptr(ent, id);
+  float s_new = 0.f;
+  if (lane == 0) { s_new = *st + gs; *st = s_new; }
+  s_new = __shfl_sync(0xffffffffu, s_new, 0);
+  const float stdv = sqrtf(s_new) + 1e-10f;
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int v = lane; v < nv; v += kWarp) {
+    float4 x = ld4(row + 4 * v);
+    float4 g = f4_add(ld4(ng + 4 * v), reg_grad4(x, p.reg_norm, p.reg_coef));
+    float4 tmp = make_float4((-p.lr * g.x) / stdv, (-p.lr * g.y) / stdv, (-p.lr * g.z) / stdv, (-p.lr * g.w) / stdv);
+    st4(row + 4 * v, f4_add(x, tmp));
+    st4(ng + 4 * v, z);
+  }
+}
+
+// Entity entry 2, phase 1: state_sum[neg_id] += mean(G_neg^2)   (duplicates accumulate)
+__global__ void __launch_bounds__(kRowBlock) k_state_add(TableView t, const long long* __restrict__ idx,
+                                                          const float* __restrict__ grad, long long n, int dim) {
+  const long long j = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (j >= n) return;
+  const int lane = threadIdx.x & 31;
+  const float* g = grad + j * (long long)dim;
+  float gs = 0.f;
+  for (int v = lane; v < (dim >> 2); v += kWarp) { float4 x = ld4(g + 4 * v); gs += f4_dot(x, x); }
+  for (int k = ((dim >> 2) << 2) + lane; k < dim; k += kWarp) gs += g[k] * g[k];
+  gs = warp_sum(gs);
+  if (lane == 0) atomicAdd(state_ptr(t, idx[j]), gs / (float)dim);
+}
+
+// phase 2 of an entry with possibly duplicated indices: emb[idx] += -lr * g / (sqrt(state[idx]) + 1e-10)
+__global__ void __launch_bounds__(kRowBlock) k_apply(TableView t, const long long* __restrict__ idx,
+                                                      const float* __restrict__ grad, long long n, int dim, float lr) {
+  const long long j = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (j >= n) return;
+  const int lane = threadIdx.x & 31;
+  const long long id = idx[j];
+  const float stdv = sqrtf(*state_ptr(t, id)) + 1e-10f;
+  const float* g = grad + j * (long long)dim;
+  float* row = row_ptr(t, id);
+  for (int v = lane; v < (dim >> 2); v += kWarp) {
+    float4 x = ld4(g + 4 * v);
+    red_add4(row + 4 * v, make_float4((-lr * x.x) / stdv, (-lr * x.y) / stdv, (-lr * x.z) / stdv, (-lr * x.w) / stdv));
+  }
+  for (int k = ((dim >> 2) << 2) + lane; k < dim; k += kWarp) atomicAdd(row + k, (-lr * g[k]) / stdv);
+}
+
+void launch_update(const LaunchCtx& c, const StepParams& p, const TableView& ent, const TableView& rel,
+                   const BatchView& b, const StepWs& w) {
+  // entity entry 1 (unique positive nodes) -- must finish before entry 2 touches state_sum
+  KGE_LAUNCH(c, k_upd_nodes, ceil_div(p.U, kWarpsPerBlock), kRowBlock, 0, p, ent, b, w);
+  // entity entry 2 (negatives; their gradient lives where the gathered rows were)
+  KGE_LAUNCH(c, k_state_add, ceil_div(p.Nn, kWarpsPerBlock), kRowBlock, 0, ent, b.neg_ids, w.Bn, p.Nn, p.D);
+  KGE_LAUNCH(c, k_apply, ceil_div(p.Nn, kWarpsPerBlock), kRowBlock, 0, ent, b.neg_ids, w.Bn, p.Nn, p.D, p.lr);
+  // relation entry: state was accumulated by k_chain
+  KGE_LAUNCH(c, k_apply, ceil_div(p.B, kWarpsPerBlock), kRowBlock, 0, rel, b.rel_ids, w.GR, p.B, p.Dr, p.lr);
+}
+
+void launch_adagrad(const LaunchCtx& c, const TableView& t, const long long* idx, const float* grad, long long n,
+                    float lr) {
+  if (n <= 0) return;
+  KGE_LAUNCH(c, k_state_add, ceil_div(n, kWarpsPerBlock), kRowBlock, 0, t, idx, grad, n, t.dim);
+  KGE_LAUNCH(c, k_apply, ceil_div(n, kWarpsPerBlock), kRowBlock, 0, t, idx, grad, n, t.dim, lr);
+}
+
+// debug: out[u,:] = NG[u,:] + reg'(emb[node_ids[u],:])  (what the reference exposes as data.grad)
+__global__ void __launch_bounds__(kRowBlock) k_node_grad_reg(StepParams p, TableView ent, BatchView b, StepWs w,
+                                                              float* __restrict__ out) {
+  const long long u = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (u >= p.U) return;
+  const int lane = threadIdx.x & 31;
+  const float* row = row_ptr(ent, b.node_ids[u]);
+  for (int v = lane; v < (p.D >> 2); v += kWarp)
+    st4(out + u * (long long)p.D + 4 * v,
+        f4_add(ld4(w.NG + u * (long long)p.D + 4 * v), reg_grad4(ld4(row + 4 * v), p.reg_norm, p.reg_coef)));
+}
+void launch_node_grad_with_reg(const LaunchCtx& c, const StepParams& p, const TableView& ent, const BatchView& b,
+                               const StepWs& w, float* out) {
+  KGE_LAUNCH(c, k_node_grad_reg, ceil_div(p.U, kWarpsPerBlock), kRowBlock, 0, p, ent, b, w, out);
+}
+
+}  // namespace kge

@@ -1,0 +1,207 @@
+/*
+ * kge_b200.h -- C ABI of libkge_b200.so: the B200-native (sm_100a) replacement for the
+ * per-step hot path of awslabs/dgl-ke's `dglke_train`:
+ *
+ *   ExternalEmbedding gather  ->  score_func over 1 positive + chunk-shared negatives
+ *   ->  logsigmoid (+ self-adversarial) loss gradient  ->  row-sparse Adagrad scatter update
+ *
+ * The reference has no native layer (it is pure Python on top of PyTorch ATen); each entry
+ * point below therefore cites the *Python* function it replaces, with file:line relative to
+ * /root/reference/python/dglke.  The host side (dgl-ke_b200/dglke_b200) binds this header with
+ * ctypes and mirrors the reference's KEModel / score_func / ExternalEmbedding surface.
+ *
+ * Conventions
+ *   - every data pointer is a CUDA device pointer unless the name ends in `_host`
+ *   - tables are fp32 row-major [num_rows, dim]; all indices are int64
+ *   - calls enqueue work on `stream` (a cudaStream_t passed as void*) and return immediately;
+ *     the *_host variants copy through pinned staging buffers owned by the handle
+ *   - return value: 0 = KGE_OK, negative = kge_status; nothing throws across the ABI;
+ *     kge_last_error() returns a thread-local description of the last failure
+ *   - a handle is bound to one device and is not thread-safe; use one handle per GPU/process
+ *   - chunk layout: chunk c owns positives [c*chunk_size, (c+1)*chunk_size) and negative ids
+ *     [c*neg_sample_size, (c+1)*neg_sample_size); only same-chunk pairs are scored
+ *     (dataloader/sampler.py:459-512)
+ */
+#ifndef KGE_B200_H_
+#define KGE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define KGE_API __attribute__((visibility("default")))
+#else
+#define KGE_API
+#endif
+
+#define KGE_ABI_VERSION 1
+#define KGE_MAX_SHARDS 8
+
+typedef enum {
+  KGE_OK = 0,
+  KGE_ERR_INVALID_ARG = -1,   /* null pointer, negative size, batch not a multiple of chunk_size ... */
+  KGE_ERR_UNSUPPORTED = -2,   /* model/dim combination this build does not implement              */
+  KGE_ERR_CUDA = -3,          /* a CUDA runtime call failed; see kge_last_error()                  */
+  KGE_ERR_NOMEM = -4,         /* workspace allocation failed                                       */
+  KGE_ERR_NO_DEVICE = -5      /* no usable sm_100 device                                           */
+} kge_status;
+
+/* models/general_models.py:238-258 (model_name -> score_func) */
+typedef enum {
+  KGE_TRANSE_L1 = 0,
+  KGE_TRANSE_L2 = 1,
+  KGE_DISTMULT = 2,
+  KGE_COMPLEX = 3,
+  KGE_RESCAL = 4,
+  KGE_ROTATE = 5
+} kge_model_t;
+
+/* One row-range shard of an embedding table.  `emb`/`state_sum` may be peer-mapped pointers to
+ * another GPU's HBM (NVLink): kernels then load / red.add over the fabric.
+ * Replaces ExternalEmbedding.emb / .state_sum (models/pytorch/tensor_models.py:210-238). */
+typedef struct {
+  float* emb;          /* [row_end-row_begin, dim] */
+  float* state_sum;    /* [row_end-row_begin]      */
+  int64_t row_begin, row_end;
+  int32_t dim;
+  int32_t device;
+} kge_shard_t;
+
+/* A table = n_shards contiguous row ranges of equal size ceil(num_rows / n_shards). */
+typedef struct {
+  const kge_shard_t* shards;   /* host array */
+  int32_t n_shards;
+  int64_t num_rows;
+  int32_t dim;
+} kge_table_t;
+
+/* Per-step configuration.  Mirrors the fields KEModel/LossGenerator/ExternalEmbedding read from
+ * `args` (models/general_models.py:208-236,572-576; models/pytorch/loss.py:41-62;
+ * models/pytorch/tensor_models.py:320). */
+typedef struct {
+  int32_t model;            /* kge_model_t */
+  int32_t entity_dim;       /* D_e: fp32 per entity row                                   */
+  int32_t relation_dim;     /* D_r: fp32 per relation row (RESCAL: rel_dim * entity_dim)  */
+  float gamma;              /* TransE / RotatE margin                                     */
+  float emb_init;           /* (gamma + 2) / hidden_dim; RotatE phase scale               */
+  float lr;                 /* Adagrad learning rate                                      */
+  float reg_coef;           /* regularization_coef (0 disables)                           */
+  int32_t reg_norm;         /* regularization_norm p (0 disables)                         */
+  int32_t adversarial;      /* -adv: self-adversarial negative weighting                  */
+  float adv_temperature;
+  int32_t neg_head;         /* 1: this step corrupts heads, 0: tails (sampler.py:853-859) */
+  int64_t batch;            /* B positives; must equal num_chunks * chunk_size            */
+  int32_t chunk_size;       /* positives per chunk                                        */
+  int32_t neg_sample_size;  /* negatives per chunk                                        */
+} kge_step_cfg_t;
+
+/* The sampled batch, exactly the tensors KEModel.forward pulls out of (pos_g, neg_g)
+ * (models/general_models.py:376-427,548-549):
+ *   node_ids   = pos_g.ndata['id']              int64[n_nodes]  unique entity ids of the batch
+ *   head_local,
+ *   tail_local = pos_g.all_edges(order='eid')   int64[batch]    indices into node_ids
+ *   rel_ids    = pos_g.edata['id']              int64[batch]
+ *   neg_ids    = neg_g.ndata['id'][neg_g.head_nid | tail_nid]   int64[num_chunks*neg_sample_size]
+ *   edge_weight= pos_g.edata['impts']           float[batch] or NULL */
+typedef struct {
+  const int64_t* node_ids;
+  int64_t n_nodes;
+  const int64_t* head_local;
+  const int64_t* tail_local;
+  const int64_t* rel_ids;
+  const int64_t* neg_ids;
+  const float* edge_weight;
+} kge_batch_t;
+
+typedef struct kge_context* kge_handle_t;
+
+KGE_API int kge_abi_version(void);
+KGE_API const char* kge_last_error(void);
+
+/* Creates the per-device context (workspace, pinned staging, SM count).  `device` is a CUDA
+ * ordinal.  Fails with KGE_ERR_NO_DEVICE when no sm_100 GPU is present -- there is no CPU path. */
+KGE_API int kge_create(int device, kge_handle_t* out);
+KGE_API int kge_destroy(kge_handle_t h);
+
+/* --- unfused pieces: one per reference function, used by the plugin classes and parity tests --- */
+
+/* ExternalEmbedding.__call__  (tensor_models.py:270-302): out[i,:] = table[idx[i],:]  (bit exact) */
+KGE_API int kge_gather(kge_handle_t h, const kge_table_t* table, const int64_t* idx, int64_t n,
+               float* out, void* stream);
+
+/* score_func.edge_func (score_fun.py:54-59,229-235,297-307,387-394,460-472) on gathered rows
+ * head/tail [n, D_e], rel [n, D_r] -> out[n] */
+KGE_API int kge_score_pos(kge_handle_t h, const kge_step_cfg_t* cfg, const float* head, const float* rel,
+                  const float* tail, int64_t n, float* out, void* stream);
+
+/* score_func.create_neg(neg_head)(heads, relations, tails, C, Cs, Ns)
+ * (score_fun.py:91-108,268-286,345-376,427-449,512-554).
+ *   cfg->neg_head == 0: heads/rel are the positives' rows [batch,.], tails = negative rows [C*Ns, D_e]
+ *   cfg->neg_head == 1: heads = negative rows [C*Ns, D_e], tails/rel the positives' rows
+ * out: [C, chunk_size, neg_sample_size] */
+KGE_API int kge_score_neg(kge_handle_t h, const kge_step_cfg_t* cfg, const float* heads, const float* rel,
+                  const float* tails, float* out, void* stream);
+
+/* LossGenerator.get_total_loss, Logsigmoid criterion, + d loss / d score (loss.py:69-98).
+ * pos [batch], neg [batch, Ns], w [batch] or NULL.  dpos [batch], dneg [batch, Ns],
+ * log4 = {pos_loss, neg_loss, loss, 0} (device) */
+KGE_API int kge_loss_grad(kge_handle_t h, const kge_step_cfg_t* cfg, const float* pos, const float* neg,
+                  const float* w, float* dpos, float* dneg, float* log4, void* stream);
+
+/* One trace entry of ExternalEmbedding.update (tensor_models.py:316-361; identical math in
+ * async_update :154-175 and kvserver.py:41-50): state_sum[idx] += mean(g^2) for every row
+ * (duplicates accumulate), THEN emb[idx] += -lr * g / (sqrt(state_sum[idx]) + 1e-10). */
+KGE_API int kge_adagrad(kge_handle_t h, const kge_table_t* table, const int64_t* idx, const float* grad,
+                int64_t n, float lr, void* stream);
+
+/* --- the step -------------------------------------------------------------------------------- */
+
+/* KEModel.forward + loss.backward() (general_models.py:529-578, train_pytorch.py:141-145):
+ * gathers, scores, loss, and all gradients; leaves the gradients in the handle's workspace and
+ * writes log4 = {pos_loss, neg_loss, loss (without reg), regularization} to device memory. */
+KGE_API int kge_forward_backward(kge_handle_t h, const kge_step_cfg_t* cfg, const kge_table_t* ent,
+                         const kge_table_t* rel, const kge_batch_t* batch, float* log4, void* stream);
+
+/* KEModel.update (general_models.py:580-588): applies the gradients of the last
+ * kge_forward_backward: entity entries [unique positive nodes, negatives], then relations. */
+KGE_API int kge_update(kge_handle_t h, const kge_step_cfg_t* cfg, const kge_table_t* ent,
+               const kge_table_t* rel, const kge_batch_t* batch, void* stream);
+
+/* forward + backward + update in one call (train_pytorch.py:141-152). */
+KGE_API int kge_step_fused(kge_handle_t h, const kge_step_cfg_t* cfg, const kge_table_t* ent,
+                   const kge_table_t* rel, const kge_batch_t* batch, float* log4, void* stream);
+
+/* Same as kge_step_fused but the batch index arrays (and edge weights) are HOST memory, as they
+ * come out of the sampler: they are staged through pinned memory and copied H2D on `stream`,
+ * and the four log scalars are copied back to log4_host (D2H) -- call kge_sync to read them. */
+KGE_API int kge_step_fused_host(kge_handle_t h, const kge_step_cfg_t* cfg, const kge_table_t* ent,
+                        const kge_table_t* rel, const kge_batch_t* batch_host, float* log4_host,
+                        void* stream);
+KGE_API int kge_sync(kge_handle_t h, void* stream);
+
+/* --- introspection (parity tests read the traced gradients the way the reference exposes
+ *     `data.grad` of each trace entry, tensor_models.py:318) ---------------------------------- */
+typedef enum {
+  KGE_BUF_POS_SCORE = 0,   /* [batch]                                     */
+  KGE_BUF_NEG_SCORE = 1,   /* [batch, Ns]  (overwritten by backward coefficients after the loss) */
+  KGE_BUF_NODE_GRAD = 2,   /* [n_nodes, D_e]  d loss / d unique positive node rows (incl. reg)   */
+  KGE_BUF_NEG_GRAD = 3,    /* [C*Ns, D_e]                                                        */
+  KGE_BUF_REL_GRAD = 4     /* [batch, D_r]                                                       */
+} kge_buffer_t;
+/* Copies a workspace buffer of the last kge_forward_backward to `out` (device). For
+ * KGE_BUF_NEG_SCORE call with cfg of that step *before* kge_update. */
+KGE_API int kge_debug_read(kge_handle_t h, int which, float* out, int64_t n_floats, void* stream);
+
+/* Number of kernels the library has launched on this handle since creation. */
+KGE_API int64_t kge_launch_count(kge_handle_t h);
+/* Selects the contraction engine: 0 = fp32 CUDA-core tiles, 1 = tcgen05 3xTF32 tensor-core tiles
+ * (bilinear models), -1 = library default. */
+KGE_API int kge_set_engine(kge_handle_t h, int engine);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KGE_B200_H_ */

@@ -1,0 +1,224 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against
+  (1) the golden vectors produced by the unmodified reference (tests/golden, tiny shapes), and
+  (2) the CPU oracle (oracle/kge_oracle.py) on seeded inputs at hot-path shapes (d=400, neg=200).
+Tolerances are the fp32 ones stated in DESIGN.md: gathers bit exact; scores 1e-5 (the reference's own
+test tolerance, tests/test_score.py:181); gradients / updated rows 2e-5 relative to the tensor scale."""
+import numpy as np
+import pytest
+import torch as th
+
+import kge_oracle as ko
+from golden_util import golden_cases, load_case, hyper_from_meta, step_inputs, tables_before
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(hp, ent, ent_s, rel, rel_s):
+    from dglke_b200.engine import StepEngine, DeviceTable, Hyper
+    dev = th.device("cuda", 0)
+    e, es, r, rs = (x.to(dev).contiguous() for x in (ent, ent_s, rel, rel_s))
+    hyper = Hyper(model=hp.model, hidden_dim=hp.hidden_dim, gamma=hp.gamma, lr=hp.lr, reg_coef=hp.reg_coef,
+                  reg_norm=hp.reg_norm, adversarial=hp.adversarial, adv_temperature=hp.adv_temperature,
+                  double_ent=hp.double_ent, double_rel=hp.double_rel)
+    eng = StepEngine(hyper, DeviceTable.from_tensors(e, es), DeviceTable.from_tensors(r, rs), 0)
+    return eng, (e, es, r, rs)
+
+
+def _close(got, want, rtol, atol_scale=1e-6, what=""):
+    want = np.asarray(want)
+    scale = float(np.abs(want).max()) if want.size else 1.0
+    np.testing.assert_allclose(got, want, rtol=rtol, atol=atol_scale * max(scale, 1e-30) + 1e-12, err_msg=what)
+
+
+def _run_and_check(hp, tables, si, C, Cs, Ns, ref, tol=2e-5):
+    """ref: dict with the reference/oracle outputs for this step (numpy)."""
+    from dglke_b200 import _lib
+    eng, (e, es, r, rs) = _engine(hp, *tables)
+    dev = e.device
+    d = lambda t: t.to(dev)
+    w = d(si["edge_weight"]) if si.get("edge_weight") is not None else None
+    log4 = eng.forward_backward(d(si["node_ids"]), d(si["head_local"]), d(si["tail_local"]), d(si["rel_ids"]),
+                                d(si["neg_ids"]), Cs, Ns, si["neg_head"], w)
+    B, U, Nn = si["head_local"].numel(), si["node_ids"].numel(), si["neg_ids"].numel()
+    pos = eng.read(_lib.BUF_POS_SCORE, (B,)).cpu().numpy()
+    neg = eng.read(_lib.BUF_NEG_SCORE, (B, Ns)).cpu().numpy()
+    gn = eng.read(_lib.BUF_NODE_GRAD, (U, hp.entity_dim)).cpu().numpy()
+    gg = eng.read(_lib.BUF_NEG_GRAD, (Nn, hp.entity_dim)).cpu().numpy()
+    gr = eng.read(_lib.BUF_REL_GRAD, (B, hp.relation_dim)).cpu().numpy()
+    log = log4.cpu().numpy()
+    eng.update()
+    th.cuda.synchronize()
+    # distance models report gamma - |.|: the fp32 rounding that matters is that of the distance
+    # (~gamma), so the absolute tolerance scales with gamma (a few fp32 ulps of the accumulated sum)
+    sc = 2e-6 * (1.0 + (hp.gamma if hp.model in ("TransE_l1", "TransE_l2", "RotatE") else 0.0) / max(float(np.abs(ref["pos_score"]).max()), 1e-30))
+    _close(pos, ref["pos_score"], 1e-5, sc, "pos_score")
+    _close(neg, ref["neg_score"], 1e-5, sc, "neg_score")
+    for i, k in enumerate(("pos_loss", "neg_loss", "loss", "regularization")):
+        if k in ref["log"]:
+            np.testing.assert_allclose(log[i], ref["log"][k], rtol=2e-5, atol=1e-9, err_msg=k)
+    _close(gn, ref["nodes_grad"], tol, 2e-6, "nodes_grad")
+    _close(gg, ref["negs_grad"], tol, 2e-6, "negs_grad")
+    _close(gr, ref["rels_grad"], tol, 2e-6, "rels_grad")
+    _close(e.cpu().numpy(), ref["ent_emb"], tol, 1e-6, "entity table after update")
+    _close(es.cpu().numpy(), ref["ent_state"], tol, 1e-6, "entity state_sum")
+    _close(r.cpu().numpy(), ref["rel_emb"], tol, 1e-6, "relation table after update")
+    _close(rs.cpu().numpy(), ref["rel_state"], tol, 1e-6, "relation state_sum")
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_cuda_step_matches_reference_golden(name):
+    meta, z = load_case(name)
+    hp = hyper_from_meta(meta)
+    C, Cs, Ns = meta["num_chunks"], meta["chunk_size"], meta["neg_sample_size"]
+    for step in range(meta["steps"]):
+        p = "s%d_" % step
+        si = step_inputs(z, step)
+        ref = dict(pos_score=z[p + "pos_score"], neg_score=z[p + "neg_score"],
+                   log={k: float(z[p + "log_" + k]) for k in ("pos_loss", "neg_loss", "loss", "regularization")},
+                   nodes_grad=z[p + "nodes_grad"], negs_grad=z[p + "negs_grad"], rels_grad=z[p + "rels_grad"],
+                   ent_emb=z[p + "ent_emb"], ent_state=z[p + "ent_state"], rel_emb=z[p + "rel_emb"],
+                   rel_state=z[p + "rel_state"])
+        if meta["reg_coef"] == 0.0:
+            ref["log"].pop("regularization")
+        _run_and_check(hp, tables_before(z, step), si, C, Cs, Ns, ref)
+
+
+def _random_step(hp, n_ent, n_rel, B, Cs, Ns, neg_head, seed, zipf=False):
+    rng = np.random.default_rng(seed)
+    C = B // Cs
+    if zipf:   # long-tailed ids: heavy duplication stresses the atomics
+        h = np.minimum(rng.zipf(1.3, B) - 1, n_ent - 1)
+        t = np.minimum(rng.zipf(1.3, B) - 1, n_ent - 1)
+        r = np.minimum(rng.zipf(1.5, B) - 1, n_rel - 1)
+        ng = np.minimum(rng.zipf(1.3, C * Ns) - 1, n_ent - 1)
+    else:
+        h, t = rng.integers(0, n_ent, B), rng.integers(0, n_ent, B)
+        r, ng = rng.integers(0, n_rel, B), rng.integers(0, n_ent, C * Ns)
+    nodes, inv = np.unique(np.concatenate([h, t]), return_inverse=True)
+    T = lambda a: th.from_numpy(np.ascontiguousarray(a.astype(np.int64)))
+    return dict(node_ids=T(nodes), head_local=T(inv[:B]), tail_local=T(inv[B:]), rel_ids=T(r), neg_ids=T(ng),
+                neg_head=neg_head, edge_weight=None), C
+
+
+HOT = [  # (model, hidden, gamma, double_ent, n_ent, n_rel, B, Cs, Ns, adv)
+    ("TransE_l2", 400, 19.9, False, 14951, 1345, 1000, 200, 200, True),    # BASELINE configs[0/1] shape
+    ("TransE_l1", 400, 19.9, False, 3000, 50, 400, 200, 200, True),
+    ("DistMult", 400, 143.0, False, 5000, 100, 600, 200, 200, True),
+    ("ComplEx", 400, 143.0, False, 5000, 100, 600, 200, 200, True),
+    ("RotatE", 200, 12.0, True, 5000, 53, 512, 256, 256, True),            # configs[2] shape: D_e=400, D_r=200
+    ("RESCAL", 64, 12.0, False, 2000, 20, 128, 64, 64, False),
+    ("TransE_l2", 100, 10.0, False, 977, 13, 300, 100, 60, False),         # ragged: Cs != Ns, D % 64 != 0
+    ("DistMult", 36, 5.0, False, 500, 7, 70, 70, 33, True),                # single chunk, odd Ns
+]
+
+
+@pytest.mark.parametrize("cfg", HOT, ids=lambda c: "%s_d%d_B%d_%dx%d" % (c[0], c[1], c[6], c[7], c[8]))
+@pytest.mark.parametrize("neg_head", [False, True])
+def test_cuda_step_matches_oracle_hot_shapes(cfg, neg_head):
+    model, hidden, gamma, de, n_ent, n_rel, B, Cs, Ns, adv = cfg
+    hp = ko.Hyper(model=model, hidden_dim=hidden, gamma=gamma, lr=0.1, reg_coef=1e-6, reg_norm=3, adversarial=adv,
+                  adv_temperature=1.0, double_ent=de)
+    ent, es, rel, rs = ko.init_tables(hp, n_ent, n_rel, seed=3)
+    es.uniform_(0.0, 1e-3)      # non-trivial Adagrad state
+    rs.uniform_(0.0, 1e-3)
+    si, C = _random_step(hp, n_ent, n_rel, B, Cs, Ns, neg_head, seed=11)
+    o_ent, o_es, o_rel, o_rs = ent.clone(), es.clone(), rel.clone(), rs.clone()
+    fb = ko.train_step(hp, o_ent, o_es, o_rel, o_rs, si["node_ids"], si["head_local"], si["tail_local"],
+                       si["rel_ids"], si["neg_ids"], C, Cs, Ns, neg_head)
+    ref = dict(pos_score=fb["pos_score"].numpy(), neg_score=fb["neg_score"].numpy(), log=fb["log"],
+               nodes_grad=fb["nodes_grad"].numpy(), negs_grad=fb["negs_grad"].numpy(),
+               rels_grad=fb["rels_grad"].numpy(), ent_emb=o_ent.numpy(), ent_state=o_es.numpy(),
+               rel_emb=o_rel.numpy(), rel_state=o_rs.numpy())
+    _run_and_check(hp, (ent, es, rel, rs), si, C, Cs, Ns, ref, tol=5e-5)
+
+
+def test_cuda_step_duplicates_zipf():
+    hp = ko.Hyper(model="TransE_l2", hidden_dim=64, gamma=12.0, lr=0.25, reg_coef=1e-5, adversarial=True)
+    ent, es, rel, rs = ko.init_tables(hp, 300, 5, seed=5)
+    si, C = _random_step(hp, 300, 5, 256, 64, 64, False, seed=2, zipf=True)
+    o = [x.clone() for x in (ent, es, rel, rs)]
+    fb = ko.train_step(hp, o[0], o[1], o[2], o[3], si["node_ids"], si["head_local"], si["tail_local"], si["rel_ids"],
+                       si["neg_ids"], C, 64, 64, False)
+    ref = dict(pos_score=fb["pos_score"].numpy(), neg_score=fb["neg_score"].numpy(), log=fb["log"],
+               nodes_grad=fb["nodes_grad"].numpy(), negs_grad=fb["negs_grad"].numpy(), rels_grad=fb["rels_grad"].numpy(),
+               ent_emb=o[0].numpy(), ent_state=o[1].numpy(), rel_emb=o[2].numpy(), rel_state=o[3].numpy())
+    _run_and_check(hp, (ent, es, rel, rs), si, C, 64, 64, ref, tol=5e-5)
+
+
+def test_gather_bit_exact_and_unfused_ops():
+    from dglke_b200 import engine as E
+    dev = th.device("cuda", 0)
+    hp = ko.Hyper(model="ComplEx", hidden_dim=40, gamma=12.0, adversarial=True, adv_temperature=0.7)
+    ent, es, rel, rs = ko.init_tables(hp, 1000, 11, seed=1)
+    tab = E.DeviceTable.from_tensors(ent.to(dev), es.to(dev))
+    idx = th.from_numpy(np.random.default_rng(0).integers(0, 1000, 777)).to(dev)
+    got = E.gather(tab, idx).cpu()
+    assert th.equal(got, ent[idx.cpu()])                     # bit exact, duplicates included
+    # score_pos / score_neg / loss_grad against the oracle
+    rng = np.random.default_rng(1)
+    B, Cs, Ns = 24, 8, 12
+    h, t, n = (ent[th.from_numpy(rng.integers(0, 1000, k))] for k in (B, B, B // Cs * Ns))
+    r = rel[th.from_numpy(rng.integers(0, 11, B))]
+    hyper = E.Hyper(model=hp.model, hidden_dim=40, gamma=12.0, adversarial=True, adv_temperature=0.7)
+    np.testing.assert_allclose(E.score_pos(hyper, h.to(dev), r.to(dev), t.to(dev)).cpu().numpy(),
+                               ko.positive_score(hp, h, r, t).numpy(), rtol=1e-5, atol=1e-6)
+    for neg_head in (False, True):
+        args = (n, r, t) if neg_head else (h, r, n)
+        want = ko.negative_score(hp, *args, B // Cs, Cs, Ns, neg_head)
+        got = E.score_neg(hyper, *(a.to(dev) for a in args), B // Cs, Cs, Ns, neg_head).cpu()
+        np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=1e-5, atol=1e-6)
+    pos = th.randn(B)
+    neg = th.randn(B, Ns)
+    pl = pos.clone().requires_grad_(True)
+    nl = neg.clone().requires_grad_(True)
+    loss, log = ko.loss_terms(hp, pl, nl)
+    loss.backward()
+    log4, dpos, dneg = E.loss_grad(hyper, pos.to(dev), neg.to(dev))
+    np.testing.assert_allclose(log4.cpu().numpy()[:3], [log["pos_loss"], log["neg_loss"], log["loss"]], rtol=1e-5)
+    np.testing.assert_allclose(dpos.cpu().numpy(), pl.grad.numpy(), rtol=1e-5, atol=1e-9)
+    np.testing.assert_allclose(dneg.cpu().numpy(), nl.grad.numpy(), rtol=1e-5, atol=1e-9)
+    # adagrad with duplicated indices
+    g = th.randn(50, 40)
+    ii = th.from_numpy(rng.integers(0, 20, 50))
+    e2, s2 = ent.clone(), th.rand(1000) * 1e-3
+    tab2 = E.DeviceTable.from_tensors(e2.to(dev), s2.to(dev))
+    ko.adagrad_entry(e2, s2, ii, g, 0.3)
+    E.adagrad(tab2, ii.to(dev), g.to(dev), 0.3)
+    np.testing.assert_allclose(tab2.emb_shards[0].cpu().numpy(), e2.numpy(), rtol=2e-5, atol=1e-7)
+    np.testing.assert_allclose(tab2.state_shards[0].cpu().numpy(), s2.numpy(), rtol=2e-5, atol=1e-9)
+
+
+def test_host_entry_point_and_repeat_steps():
+    """kge_step_fused_host (pinned staging + H2D/D2H) over several alternating steps vs the oracle."""
+    hp = ko.Hyper(model="DistMult", hidden_dim=48, gamma=12.0, lr=0.1, reg_coef=1e-6, adversarial=True)
+    ent, es, rel, rs = ko.init_tables(hp, 800, 9, seed=9)
+    eng, (e, e_s, r, r_s) = _engine(hp, ent, es, rel, rs)
+    o = [x.clone() for x in (ent, es, rel, rs)]
+    for step in range(4):
+        neg_head = step % 2 == 1
+        si, C = _random_step(hp, 800, 9, 96, 32, 32, neg_head, seed=100 + step)
+        fb = ko.train_step(hp, o[0], o[1], o[2], o[3], si["node_ids"], si["head_local"], si["tail_local"],
+                           si["rel_ids"], si["neg_ids"], C, 32, 32, neg_head)
+        log = eng.step_host(si["node_ids"], si["head_local"], si["tail_local"], si["rel_ids"], si["neg_ids"], 32, 32,
+                            neg_head)
+        eng.sync()
+        np.testing.assert_allclose(log.numpy()[2], fb["log"]["loss"], rtol=5e-5)
+    np.testing.assert_allclose(e.cpu().numpy(), o[0].numpy(), rtol=2e-4, atol=1e-6)
+    np.testing.assert_allclose(r.cpu().numpy(), o[2].numpy(), rtol=2e-4, atol=1e-6)
+
+
+def test_error_paths():
+    from dglke_b200 import _lib
+    from dglke_b200.engine import Hyper, score_pos
+    dev = th.device("cuda", 0)
+    with pytest.raises(_lib.KgeError):       # D % 4 != 0
+        score_pos(Hyper(model="TransE_l2", hidden_dim=6), th.zeros(2, 6, device=dev), th.zeros(2, 6, device=dev),
+                  th.zeros(2, 6, device=dev))
+    hp = ko.Hyper(model="TransE_l2", hidden_dim=8)
+    ent, es, rel, rs = ko.init_tables(hp, 10, 2)
+    eng, _ = _engine(hp, ent, es, rel, rs)
+    i = lambda *v: th.tensor(v, dtype=th.int64, device=dev)
+    with pytest.raises(_lib.KgeError):       # ragged batch: 3 positives, chunk 2 (reference skips such batches)
+        eng.forward_backward(i(0, 1, 2), i(0, 1, 2), i(1, 2, 0), i(0, 1, 0), i(3, 4), 2, 1, False)
+    with pytest.raises(_lib.KgeError):       # update without forward
+        eng.update()
