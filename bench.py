@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""bench.py -- edges/sec of the KGE training hot path (BASELINE.json metric) on N B200s.
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run)
+  python bench.py --impl reference --gpus N --steps K --warmup W
+
+A "step" is one pass of the hot path (gather -> score over 1 positive + chunk-shared negatives ->
+logsigmoid/self-adversarial loss gradient -> row-sparse Adagrad) over one batch of B synthetic edges.
+Workload (default): BASELINE.json configs[1] -- TransE_l2, FB15k shape (14 951 entities, 1 345 relations),
+d=400, neg=200, -adv, gamma 19.9, lr 0.25, rc 1e-9 (examples/fb15k/multi_gpu.sh:84-86).
+
+One JSON line on stdout (rank 0).  Sampling is excluded on both arms (DGL's C++ sampler is not
+available offline): batches are pre-generated from seeded numpy draws.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "dgl-ke_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+WORKLOADS = {
+    # name: (model, n_ent, n_rel, hidden, gamma, lr, rc, neg, double_ent, default batch, description)
+    "fb15k_transe_l2": ("TransE_l2", 14951, 1345, 400, 19.9, 0.25, 1e-9, 200, False, 4000,
+                        "TransE_l2 FB15k-shape d=400 neg=200 -adv (BASELINE configs[1])"),
+    "wikikg2_rotate": ("RotatE", 2500604, 535, 200, 12.0, 0.01, 1e-9, 256, True, 4096,
+                       "RotatE wikikg2-shape d=200 -de neg=256 -adv (BASELINE configs[2])"),
+    "freebase_complex": ("ComplEx", 86054151, 14824, 400, 143.0, 0.1, 2e-6, 200, False, 4000,
+                         "ComplEx Freebase-shape 86M entities d=400 neg=200 -adv (BASELINE configs[3])"),
+    "synth_distmult": ("DistMult", 100000000, 10000, 512, 143.0, 0.08, 2e-6, 1024, False, 4096,
+                       "DistMult synthetic 100M entities d=512 neg=1024 -adv (BASELINE configs[4])"),
+    "big_transe_l2": ("TransE_l2", 20000000, 1345, 400, 19.9, 0.25, 1e-9, 200, False, 4000,
+                      "TransE_l2 d=400 neg=200 -adv on a 20M-entity (32 GB) table: HBM-resident variant of configs[1]"),
+}
+METRIC = "edges/sec TransE_l2 d=400 neg=200 at 1/2/4/8 B200 vs ref CPU; HBM GB/s %peak"
+
+
+def bytes_per_edge(de, dr):
+    # read (head, tail, neg, rel rows + 4 state scalars) + write of the same
+    return 2 * (4 * (3 * de + dr) + 16)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="fb15k_transe_l2", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="edges per step per GPU (0 = workload default)")
+    ap.add_argument("--n-ent", type=int, default=0, help="override the entity count (capacity experiments)")
+    ap.add_argument("--engine", type=int, default=-1, help="-1 library default, 0 fp32 tiles, 1 tcgen05")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
+    ap.add_argument("--cpu-procs", type=int, default=0, help="reference arm: worker processes (0 = all host threads)")
+    ap.add_argument("--cpu-batch", type=int, default=1000, help="reference arm: batch per worker (dglke_train's 1000)")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle port of its PyTorch
+    step, Hogwild num_proc workers) on the host cores.  Rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import cpu_bench
+    import kge_oracle as ko
+    model, n_ent, n_rel, hidden, gamma, lr, rc, neg, de, _, desc = WORKLOADS[args.workload]
+    if args.n_ent:
+        n_ent = args.n_ent
+    # host RAM bound for the huge shapes: a stated scaled-down entity count
+    cap = 20_000_000
+    scaled = n_ent > cap
+    n_ent_cpu = min(n_ent, cap)
+    hp = ko.Hyper(model=model, hidden_dim=hidden, gamma=gamma, lr=lr, reg_coef=rc, reg_norm=3, adversarial=True,
+                  adv_temperature=1.0, double_ent=de)
+    nproc = args.cpu_procs or (os.cpu_count() or 1)
+    B = args.cpu_batch // neg * neg or neg
+    steps, warm = max(1, args.steps), max(1, args.warmup)
+    t0 = time.time()
+    eps, wall = cpu_bench.hogwild_edges_per_sec(hp, n_ent_cpu, n_rel, B, neg, steps, warm, nproc)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": eps, "unit": "edges/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": warm, "ms_per_step": wall / steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "batch_per_worker": B, "workers": nproc,
+                   "entities": n_ent_cpu, "entities_scaled_down": scaled,
+                   "note": "oracle port of the reference's PyTorch step (oracle/kge_oracle.py), dglke_train's "
+                           "process model: Hogwild workers on shared-memory tables, 1 thread each; sampling excluded"},
+        "cpu_baseline": {"value": eps, "unit": "edges/s", "cores": nproc, "kind": "port",
+                         "sample": "%d workers x %d steps x %d edges (%.1f s wall incl. setup)" % (nproc, steps, B, time.time() - t0)},
+        "e2e": {"value": eps, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
+        os.unlink(self.f.name)
+        sm, reasons, mx = [], set(), None
+        for r in rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1])); mx = float(r[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.strip().lower() == "active":
+                    reasons.add(name)
+        if sm:
+            sm.sort()
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def cpu_baseline_subprocess(args):
+    """Times the CPU oracle on a bounded sample in a fresh process (before CUDA is initialised here)."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", args.workload,
+           "--steps", "8", "--warmup", "2"]
+    if args.n_ent:
+        cmd += ["--n-ent", str(args.n_ent)]
+    env = dict(os.environ)
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        env.pop(k, None)
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+        for l in reversed(out.stdout.strip().splitlines()):
+            if l.startswith("{"):
+                return json.loads(l)["cpu_baseline"]
+        return {"value": None, "unit": "edges/s", "cores": 0, "kind": "port", "sample": "failed: " + out.stderr[-200:]}
+    except Exception as e:  # noqa
+        return {"value": None, "unit": "edges/s", "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
+
+
+def run_ours(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_base = cpu_baseline_subprocess(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from dglke_b200.engine import StepEngine, DeviceTable, Hyper
+    from dglke_b200.graph import SyntheticSampler
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (libkge_b200 has no CPU path); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    model, n_ent, n_rel, hidden, gamma, lr, rc, neg, de, bdef, desc = WORKLOADS[args.workload]
+    if args.n_ent:
+        n_ent = args.n_ent
+    B = (args.batch or bdef) // neg * neg
+    hp = Hyper(model=model, hidden_dim=hidden, gamma=gamma, lr=lr, reg_coef=rc, reg_norm=3, adversarial=True,
+               adv_temperature=1.0, double_ent=de)
+    De, Dr = hp.entity_dim, hp.relation_dim
+
+    # ---- tables (resident in HBM before the clock starts) ------------------------------------
+    gen = torch.Generator(device=dev).manual_seed(0)
+    if world == 1:
+        ent = torch.empty((n_ent, De), dtype=torch.float32, device=dev).uniform_(-hp.emb_init, hp.emb_init, generator=gen)
+        ent_state = torch.zeros(n_ent, dtype=torch.float32, device=dev)
+        rel = torch.empty((n_rel, Dr), dtype=torch.float32, device=dev).uniform_(-hp.emb_init, hp.emb_init, generator=gen)
+        rel_state = torch.zeros(n_rel, dtype=torch.float32, device=dev)
+        eng = StepEngine(hp, DeviceTable.from_tensors(ent, ent_state), DeviceTable.from_tensors(rel, rel_state), local_rank)
+        parallelism = "1 GPU"
+    else:
+        from dglke_b200.dist import ShardedTrainer
+        eng = ShardedTrainer(hp, n_ent, n_rel, dev, seed=0)
+        parallelism = "entity rows sharded over %d GPUs (P2P over NVLink), relations replicated + NCCL all-reduce" % world
+    if args.engine >= 0:
+        eng.h.set_engine(args.engine)
+
+    # ---- batches: NB distinct pre-sampled batches per rank, device and pinned-host copies --------
+    NB = 8
+    sampler = SyntheticSampler(n_ent, n_rel, B, neg, seed=0, rank=rank)
+    host, devb = [], []
+    for k in range(NB):
+        pg, ng = sampler.batch(k)
+        hb = [pg.ndata["id"], pg.all_edges()[0], pg.all_edges()[1], pg.edata["id"], ng.ndata["id"]]
+        hb = [t.pin_memory() for t in hb]
+        host.append((hb, ng.neg_head))
+        devb.append(([t.to(dev) for t in hb], ng.neg_head))
+    Cs = sampler.chunk_size
+    h2d = sum(t.numel() * 8 for t in host[0][0])
+
+    def step_dev(k):
+        b, nh = devb[k % NB]
+        return eng.step(b[0], b[1], b[2], b[3], b[4], Cs, neg, nh)
+
+    def step_host(k):
+        b, nh = host[k % NB]
+        return eng.step_host(b[0], b[1], b[2], b[3], b[4], Cs, neg, nh)
+
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def flush():
+        if not args.no_flush:
+            flush_buf.fill_(1)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    W, K = max(3, args.warmup), max(1, args.steps)
+    for k in range(W):
+        step_dev(k)
+    torch.cuda.synchronize()
+
+    # ---- CUDA graphs of the device-resident step (one per batch): no launch gaps inside a step ----
+    graphs = None
+    if world == 1:
+        try:
+            graphs = []
+            for k in range(NB):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    step_dev(k)
+                graphs.append(g)
+        except Exception as e:  # noqa
+            sys.stderr.write("graph capture failed (%r); timing eager launches\n" % (e,))
+            graphs = None
+            torch.cuda.synchronize()
+
+    def timed(run_step, after=None):
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        barrier()
+        for k in range(K):
+            flush()
+            ev[k][0].record()
+            run_step(k)
+            if after:
+                after()
+            ev[k][1].record()
+        barrier()
+        t = sum(a.elapsed_time(b) for a, b in ev)   # ms of device time inside the K steps
+        tt = torch.tensor([t], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    launches0 = eng.h.launch_count()
+    clk = ClockSampler(local_rank) if rank == 0 else None
+    if graphs is not None:
+        ms_dev = timed(lambda k: graphs[k % NB].replay())
+        launches = (eng.h.launch_count() - launches0)  # graph replays do not pass through the library
+        launches = None
+    else:
+        ms_dev = timed(step_dev)
+        launches = eng.h.launch_count() - launches0
+    clocks = clk.stop() if clk else None
+
+    # launches per step, counted from one eager step
+    c0 = eng.h.launch_count()
+    step_dev(0)
+    torch.cuda.synchronize()
+    per_step_launches = eng.h.launch_count() - c0
+    gpu_launches = per_step_launches * K
+
+    # ---- end to end: host index buffers -> pinned staging -> H2D -> step -> D2H log ---------------
+    ms_e2e = timed(step_host, after=eng.sync)
+
+    # ---- per-kernel device time of one step (CUDA events around every launch, L2 flushed) --------
+    eng.h.profile_enable(True)
+    prof = {}
+    nprof = 5
+    for k in range(nprof):
+        flush()
+        step_dev(k)
+        for name, ms in eng.h.profile_read():
+            prof[name] = prof.get(name, 0.0) + ms / nprof
+    eng.h.profile_enable(False)
+    kern_ms = sum(prof.values())
+    dominant = max(prof.items(), key=lambda kv: kv[1]) if prof else ("", 0.0)
+
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    bpe = bytes_per_edge(De, Dr)
+    edges = world * K * B
+    value = edges / (ms_dev * 1e-3)
+    e2e = edges / (ms_e2e * 1e-3)
+    # roofline of the step's kernels: algorithmic bytes of one launch set (= one step) / summed kernel time
+    achieved = B * bpe / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else 0.0
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(args.workload)
+    except Exception:
+        pass
+    line = {
+        "metric": METRIC, "value": value, "unit": "edges/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "batch_per_gpu": B, "global_batch": B * world, "chunk_size": Cs,
+                   "neg_sample_size": neg, "entities": n_ent, "relations": n_rel, "parallelism": parallelism,
+                   "l2": "cold: 256 MiB written between timed steps" if not args.no_flush else "warm (no flush)",
+                   "launch": "one CUDA graph per step" if graphs is not None else "eager launches",
+                   "sampling": "excluded (pre-generated seeded batches), as on the reference arm",
+                   "bytes_per_edge": bpe},
+        "e2e": {"value": e2e, "unit": "edges/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 16,
+                "ms_per_step": ms_e2e / K},
+        "gpu_launches": gpu_launches,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                     "kernel": "all %d kernels of one step (CUDA events around each launch, L2 flushed)" % per_step_launches,
+                     "algorithmic_bytes_per_launch_set": B * bpe,
+                     "kernel_ms": {k: round(v, 5) for k, v in sorted(prof.items(), key=lambda kv: -kv[1])},
+                     "dominant_kernel": {"name": dominant[0], "share": dominant[1] / kern_ms if kern_ms else 0.0}},
+        "cpu_baseline": cpu_base,
+        "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

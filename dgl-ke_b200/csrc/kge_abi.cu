@@ -11,6 +11,7 @@
 #include <cstdarg>
 #include <cstring>
 #include <new>
+#include <cuda.h>
 #include "kge_common.cuh"
 
 using namespace kge;
@@ -40,6 +41,7 @@ struct kge_context {
   int num_sms = 0;
   long long launches = 0;
   int engine = -1;
+  int rel_deferred = 0;
   // device arena (grown on demand, never inside a graph capture)
   char* arena = nullptr;
   size_t arena_bytes = 0;
@@ -58,6 +60,7 @@ struct kge_context {
   BatchView last_b{};
   TableView last_ent{}, last_rel{};
   bool have_last = false;
+  Profiler prof;
 };
 
 namespace {
@@ -136,6 +139,7 @@ int make_params(const kge_step_cfg_t* cfg, long long n_nodes, StepParams* p, boo
   p->C = (int)(cfg->batch / cfg->chunk_size);
   p->Nn = (long long)p->C * p->Ns;
   p->U = n_nodes;
+  p->rel_deferred = 0;
   (void)need_tables;
   return KGE_OK;
 }
@@ -155,7 +159,7 @@ int carve(kge_context* h, const StepParams& p, StepWs* w, cudaStream_t stream) {
   size_t oS = take(BNs), oV = take(BNs);
   size_t opos = take(p.B), ogpos = take(p.B), opn = take(p.B), oa2 = take(p.B), ob2 = take(p.Nn);
   size_t ors = take(p.B), ocs = take(p.Nn), opl = take(p.B), onl = take(p.B);
-  size_t oreg = take((size_t)p.B + p.Nn + U), owb = take(4);
+  size_t oreg = take((size_t)p.B + p.Nn + U), owb = take(4), ogsr = take(p.B);
   size_t oMt = rescal ? take(BD) : 0;
   if (need > h->arena_bytes) {
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
@@ -175,12 +179,12 @@ int carve(kge_context* h, const StepParams& p, StepWs* w, cudaStream_t stream) {
   w->GR = (float*)(a + oGR); w->S = (float*)(a + oS); w->V = (float*)(a + oV);
   w->pos = (float*)(a + opos); w->gpos = (float*)(a + ogpos); w->pnorm = (float*)(a + opn);
   w->a2 = (float*)(a + oa2); w->b2 = (float*)(a + ob2); w->rowsum = (float*)(a + ors); w->colsum = (float*)(a + ocs);
-  w->pl = (float*)(a + opl); w->nl = (float*)(a + onl); w->regp = (float*)(a + oreg); w->wbar = (float*)(a + owb);
+  w->pl = (float*)(a + opl); w->nl = (float*)(a + onl); w->regp = (float*)(a + oreg); w->wbar = (float*)(a + owb); w->gsr = (float*)(a + ogsr);
   w->Mt = rescal ? (float*)(a + oMt) : nullptr;
   return KGE_OK;
 }
 
-LaunchCtx lctx(kge_context* h, void* stream) { return LaunchCtx{(cudaStream_t)stream, &h->launches, h->num_sms}; }
+LaunchCtx lctx(kge_context* h, void* stream) { return LaunchCtx{(cudaStream_t)stream, &h->launches, h->num_sms, &h->prof}; }
 
 // NG (node-gradient accumulator) has to be zero when k_chain starts.  k_upd_nodes re-zeroes the
 // rows it consumes, so only a fresh / enlarged region needs an explicit fill.
@@ -260,11 +264,46 @@ KGE_API int kge_destroy(kge_handle_t h) {
   if (h->dev_stage) cudaFree(h->dev_stage);
   if (h->pin) cudaFreeHost(h->pin);
   if (h->dev_log4) cudaFree(h->dev_log4);
+  if (h->prof.created)
+    for (int i = 0; i < Profiler::kMax; ++i) { cudaEventDestroy(h->prof.ev0[i]); cudaEventDestroy(h->prof.ev1[i]); }
   delete h;
   return KGE_OK;
 }
 
 KGE_API int64_t kge_launch_count(kge_handle_t h) { return h ? h->launches : 0; }
+
+KGE_API int kge_profile_enable(kge_handle_t h, int on) {
+  if (!h) return fail(KGE_ERR_INVALID_ARG, "handle is null");
+  DeviceGuard g(h->device);
+  Profiler& p = h->prof;
+  if (on && !p.created) {
+    for (int i = 0; i < Profiler::kMax; ++i) {
+      KGE_CUDA_OK(cudaEventCreate(&p.ev0[i]));
+      KGE_CUDA_OK(cudaEventCreate(&p.ev1[i]));
+    }
+    p.created = true;
+  }
+  p.enabled = on != 0;
+  p.n = 0;
+  return KGE_OK;
+}
+
+KGE_API int kge_profile_read(kge_handle_t h, char* names, int names_len, float* ms, int max_records) {
+  if (!h || !names || !ms) return fail(KGE_ERR_INVALID_ARG, "null argument");
+  DeviceGuard g(h->device);
+  Profiler& p = h->prof;
+  KGE_CUDA_OK(cudaDeviceSynchronize());
+  int n = p.n < max_records ? p.n : max_records, off = 0;
+  names[0] = 0;
+  for (int i = 0; i < n; ++i) {
+    KGE_CUDA_OK(cudaEventElapsedTime(&ms[i], p.ev0[i], p.ev1[i]));
+    int w = snprintf(names + off, names_len - off, "%s%s", i ? "," : "", p.names[i]);
+    if (w < 0 || off + w >= names_len) break;
+    off += w;
+  }
+  p.n = 0;   // start a new record set
+  return n;
+}
 
 KGE_API int kge_set_engine(kge_handle_t h, int engine) {
   if (!h) return fail(KGE_ERR_INVALID_ARG, "handle is null");
@@ -396,6 +435,7 @@ KGE_API int kge_forward_backward(kge_handle_t h, const kge_step_cfg_t* cfg, cons
   if (rc) return rc;
   rc = check_batch(batch, p);
   if (rc) return rc;
+  p.rel_deferred = h->rel_deferred;
   TableView ve, vr;
   if ((rc = make_view(ent, &ve, "entity"))) return rc;
   if ((rc = make_view(rel, &vr, "relation"))) return rc;
@@ -441,6 +481,7 @@ KGE_API int kge_update(kge_handle_t h, const kge_step_cfg_t* cfg, const kge_tabl
   if ((rc = make_view(rel, &vr, "relation"))) return rc;
   DeviceGuard g(h->device);
   p.lr = cfg->lr;
+  p.rel_deferred = h->last_p.rel_deferred;
   launch_update(lctx(h, stream), p, ve, vr, bview(batch), h->last_w);
   KGE_CUDA_OK(cudaGetLastError());
   h->ng_dirty = false;
@@ -537,6 +578,81 @@ KGE_API int kge_debug_read(kge_handle_t h, int which, float* out, int64_t n_floa
   }
   if (n_floats != n) return fail(KGE_ERR_INVALID_ARG, "expected %lld floats, got %lld", n, (long long)n_floats);
   KGE_CUDA_OK(cudaMemcpyAsync(out, src, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return KGE_OK;
+}
+
+// ---- multi-GPU support ------------------------------------------------------------------------
+KGE_API int kge_set_relation_mode(kge_handle_t h, int deferred) {
+  if (!h) return fail(KGE_ERR_INVALID_ARG, "handle is null");
+  h->rel_deferred = deferred ? 1 : 0;
+  return KGE_OK;
+}
+
+KGE_API int kge_rel_grad_dense(kge_handle_t h, float* rg, float* rgs, void* stream) {
+  if (!h || !rg || !rgs) return fail(KGE_ERR_INVALID_ARG, "null argument");
+  if (!h->have_last || !h->last_p.rel_deferred)
+    return fail(KGE_ERR_INVALID_ARG, "kge_rel_grad_dense needs a preceding kge_forward_backward in deferred relation mode");
+  DeviceGuard g(h->device);
+  launch_rel_grad_dense(lctx(h, stream), h->last_p, h->last_b, h->last_w, rg, rgs);
+  KGE_CUDA_OK(cudaGetLastError());
+  return KGE_OK;
+}
+
+KGE_API int kge_rel_apply_dense(kge_handle_t h, const kge_table_t* rel, float* rg, float* rgs, float lr, void* stream) {
+  if (!h || !rg || !rgs) return fail(KGE_ERR_INVALID_ARG, "null argument");
+  TableView vr;
+  int rc = make_view(rel, &vr, "relation");
+  if (rc) return rc;
+  DeviceGuard g(h->device);
+  launch_rel_apply_dense(lctx(h, stream), vr, rg, rgs, lr);
+  KGE_CUDA_OK(cudaGetLastError());
+  return KGE_OK;
+}
+
+KGE_API int kge_device_alloc(kge_handle_t h, int64_t bytes, void** out) {
+  if (!h || !out || bytes <= 0) return fail(KGE_ERR_INVALID_ARG, "bad argument");
+  DeviceGuard g(h->device);
+  cudaError_t e = cudaMalloc(out, (size_t)bytes);
+  if (e != cudaSuccess) { cudaGetLastError(); return fail(KGE_ERR_NOMEM, "cudaMalloc(%lld) failed: %s", (long long)bytes, cudaGetErrorString(e)); }
+  return KGE_OK;
+}
+
+KGE_API int kge_device_free(kge_handle_t h, void* p) {
+  if (!h) return fail(KGE_ERR_INVALID_ARG, "handle is null");
+  DeviceGuard g(h->device);
+  KGE_CUDA_OK(cudaFree(p));
+  return KGE_OK;
+}
+
+KGE_API int kge_ipc_export(kge_handle_t h, const void* dev_ptr, uint8_t handle_out[64], int64_t* offset_out) {
+  if (!h || !dev_ptr || !handle_out || !offset_out) return fail(KGE_ERR_INVALID_ARG, "null argument");
+  DeviceGuard g(h->device);
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  CUdeviceptr base = 0;
+  size_t size = 0;
+  // resolved through the runtime so that the library does not link libcuda (it must load on CPU-only hosts)
+  typedef CUresult (*get_range_fn)(CUdeviceptr*, size_t*, CUdeviceptr);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  KGE_CUDA_OK(cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qres));
+  if (!fn || qres != cudaDriverEntryPointSuccess) return fail(KGE_ERR_CUDA, "cuMemGetAddressRange not available");
+  CUresult r = ((get_range_fn)fn)(&base, &size, (CUdeviceptr)dev_ptr);
+  if (r != CUDA_SUCCESS) return fail(KGE_ERR_CUDA, "cuMemGetAddressRange failed (%d)", (int)r);
+  cudaIpcMemHandle_t hd;
+  KGE_CUDA_OK(cudaIpcGetMemHandle(&hd, (void*)base));
+  memcpy(handle_out, &hd, 64);
+  *offset_out = (int64_t)((CUdeviceptr)dev_ptr - base);
+  return KGE_OK;
+}
+
+KGE_API int kge_ipc_open(kge_handle_t h, const uint8_t handle[64], int64_t offset, void** out) {
+  if (!h || !handle || !out) return fail(KGE_ERR_INVALID_ARG, "null argument");
+  DeviceGuard g(h->device);
+  cudaIpcMemHandle_t hd;
+  memcpy(&hd, handle, 64);
+  void* base = nullptr;
+  KGE_CUDA_OK(cudaIpcOpenMemHandle(&base, hd, cudaIpcMemLazyEnablePeerAccess));
+  *out = (char*)base + offset;
   return KGE_OK;
 }
 

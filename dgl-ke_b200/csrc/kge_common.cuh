@@ -48,6 +48,7 @@ struct StepParams {
   int C, Cs, Ns;
   long long Nn; // C * Ns negative rows
   long long U;  // unique positive nodes
+  int rel_deferred;  // 1: relation Adagrad is applied later from dense all-reduced buffers (multi-GPU)
 };
 
 // Device workspace of one step (all pointers into the handle's arena).
@@ -70,6 +71,7 @@ struct StepWs {
   float* nl;       // [B]      negative loss terms (already reduced over j)
   float* regp;     // [B + Nn + U] partial sums of |x|^p
   float* wbar;     // [1]      mean edge weight
+  float* gsr;      // [B]      mean(GR_i^2) per edge (deferred relation update)
   float* Mt;       // [B, D]   RESCAL: M_r t  (tail mode needs it next to A = M_r h)
 };
 
@@ -107,6 +109,18 @@ __device__ __forceinline__ float4 ld4_stream(const float* p) {
 __device__ __forceinline__ void red_add4(float* p, float4 v) {
   asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};"
                :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// system-scope variants for rows that may live in a peer GPU's HBM (NVLink atomics)
+__device__ __forceinline__ void red_add4_sys(float* p, float4 v) {
+  asm volatile("red.relaxed.sys.global.add.v4.f32 [%0], {%1,%2,%3,%4};"
+               :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void table_red_add4(const TableView& t, float* p, float4 v) {
+  if (t.n_shards > 1) red_add4_sys(p, v); else red_add4(p, v);
+}
+__device__ __forceinline__ void table_atomic_add(const TableView& t, float* p, float v) {
+  if (t.n_shards > 1) atomicAdd_system(p, v); else atomicAdd(p, v);
 }
 
 #define KGE_F4_OP2(name, expr)                                                     \
@@ -165,11 +179,44 @@ inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // ------------------------------------------------------------------------------------------
 // host-side launchers (defined in kge_rows.cu / kge_tiles.cu / kge_rescal.cu)
+// Optional per-launch timing (kge_profile_*): CUDA events recorded on the launching stream
+// around every kernel of a step; read back after a stream sync.
+struct Profiler {
+  static constexpr int kMax = 64;
+  bool enabled = false;
+  int n = 0;
+  const char* names[kMax];
+  cudaEvent_t ev0[kMax], ev1[kMax];
+  bool created = false;
+};
+
 struct LaunchCtx {
   cudaStream_t stream;
   long long* launch_counter;
   int num_sms;
+  Profiler* prof;
 };
+
+inline void prof_begin(const LaunchCtx& c, const char* name) {
+  Profiler* p = c.prof;
+  if (!p || !p->enabled || p->n >= Profiler::kMax) return;
+  p->names[p->n] = name;
+  cudaEventRecord(p->ev0[p->n], c.stream);
+}
+inline void prof_end(const LaunchCtx& c) {
+  Profiler* p = c.prof;
+  if (!p || !p->enabled || p->n >= Profiler::kMax) return;
+  cudaEventRecord(p->ev1[p->n], c.stream);
+  ++p->n;
+}
+
+#define KGE_LAUNCH(ctx, kernel, grid, block, smem, ...)                         \
+  do {                                                                          \
+    prof_begin((ctx), #kernel);                                                 \
+    kernel<<<(grid), (block), (smem), (ctx).stream>>>(__VA_ARGS__);             \
+    prof_end((ctx));                                                            \
+    if ((ctx).launch_counter) ++*(ctx).launch_counter;                          \
+  } while (0)
 
 void launch_gather(const LaunchCtx&, const TableView& t, const long long* idx, long long n, float* out);
 void launch_prep(const LaunchCtx&, const StepParams&, const TableView& ent, const TableView& rel,
@@ -191,5 +238,8 @@ void launch_adagrad(const LaunchCtx&, const TableView& t, const long long* idx, 
 void launch_node_grad_with_reg(const LaunchCtx&, const StepParams&, const TableView& ent,
                                const BatchView&, const StepWs&, float* out);
 void launch_fill_zero(const LaunchCtx&, float* p, long long n);
+void launch_update_entities(const LaunchCtx&, const StepParams&, const TableView& ent, const BatchView&, const StepWs&);
+void launch_rel_grad_dense(const LaunchCtx&, const StepParams&, const BatchView&, const StepWs&, float* rg, float* rgs);
+void launch_rel_apply_dense(const LaunchCtx&, const TableView& rel, float* rg, float* rgs, float lr);
 
 }  // namespace kge

@@ -8,11 +8,6 @@
 
 namespace kge {
 
-#define KGE_LAUNCH(ctx, kernel, grid, block, smem, ...)                         \
-  do {                                                                          \
-    kernel<<<(grid), (block), (smem), (ctx).stream>>>(__VA_ARGS__);             \
-    if ((ctx).launch_counter) ++*(ctx).launch_counter;                          \
-  } while (0)
 
 constexpr int kBlock = 256;
 constexpr int kWarps = kBlock / 32;
@@ -186,7 +181,8 @@ __global__ void __launch_bounds__(kBlock) k_rescal_bwd(StepParams p, TableView e
   if (threadIdx.x == 0) {
     float s = 0.f;
     for (int q = 0; q < kWarps; ++q) s += red[q];
-    atomicAdd(state_ptr(rel, rid), s / (float)p.Dr);
+    if (p.rel_deferred) w.gsr[i] = s / (float)p.Dr;
+    else table_atomic_add(rel, state_ptr(rel, rid), s / (float)p.Dr);
   }
 }
 

@@ -11,11 +11,6 @@
 
 namespace kge {
 
-#define KGE_LAUNCH(ctx, kernel, grid, block, smem, ...)                         \
-  do {                                                                          \
-    kernel<<<(grid), (block), (smem), (ctx).stream>>>(__VA_ARGS__);             \
-    if ((ctx).launch_counter) ++*(ctx).launch_counter;                          \
-  } while (0)
 
 constexpr int kRowBlock = 256;               // 8 warps = 8 row jobs per CTA
 constexpr int kWarpsPerBlock = kRowBlock / kWarp;
@@ -493,7 +488,10 @@ __global__ void __launch_bounds__(kRowBlock) k_chain(StepParams p, TableView ent
     }
   }
   gs = warp_sum(gs);
-  if (lane == 0) atomicAdd(state_ptr(rel, rid), gs / (float)p.Dr);
+  if (lane == 0) {
+    if (p.rel_deferred) w.gsr[i] = gs / (float)p.Dr;
+    else table_atomic_add(rel, state_ptr(rel, rid), gs / (float)p.Dr);
+  }
 }
 
 void launch_chain(const LaunchCtx& c, const StepParams& p, const TableView& ent, const TableView& rel,
@@ -544,7 +542,7 @@ __global__ void __launch_bounds__(kRowBlock) k_state_add(TableView t, const long
   for (int v = lane; v < (dim >> 2); v += kWarp) { float4 x = ld4(g + 4 * v); gs += f4_dot(x, x); }
   for (int k = ((dim >> 2) << 2) + lane; k < dim; k += kWarp) gs += g[k] * g[k];
   gs = warp_sum(gs);
-  if (lane == 0) atomicAdd(state_ptr(t, idx[j]), gs / (float)dim);
+  if (lane == 0) table_atomic_add(t, state_ptr(t, idx[j]), gs / (float)dim);
 }
 
 // phase 2 of an entry with possibly duplicated indices: emb[idx] += -lr * g / (sqrt(state[idx]) + 1e-10)
@@ -559,20 +557,71 @@ __global__ void __launch_bounds__(kRowBlock) k_apply(TableView t, const long lon
   float* row = row_ptr(t, id);
   for (int v = lane; v < (dim >> 2); v += kWarp) {
     float4 x = ld4(g + 4 * v);
-    red_add4(row + 4 * v, make_float4((-lr * x.x) / stdv, (-lr * x.y) / stdv, (-lr * x.z) / stdv, (-lr * x.w) / stdv));
+    table_red_add4(t, row + 4 * v, make_float4((-lr * x.x) / stdv, (-lr * x.y) / stdv, (-lr * x.z) / stdv, (-lr * x.w) / stdv));
   }
   for (int k = ((dim >> 2) << 2) + lane; k < dim; k += kWarp) atomicAdd(row + k, (-lr * g[k]) / stdv);
 }
 
-void launch_update(const LaunchCtx& c, const StepParams& p, const TableView& ent, const TableView& rel,
-                   const BatchView& b, const StepWs& w) {
+void launch_update_entities(const LaunchCtx& c, const StepParams& p, const TableView& ent, const BatchView& b,
+                            const StepWs& w) {
   // entity entry 1 (unique positive nodes) -- must finish before entry 2 touches state_sum
   KGE_LAUNCH(c, k_upd_nodes, ceil_div(p.U, kWarpsPerBlock), kRowBlock, 0, p, ent, b, w);
   // entity entry 2 (negatives; their gradient lives where the gathered rows were)
   KGE_LAUNCH(c, k_state_add, ceil_div(p.Nn, kWarpsPerBlock), kRowBlock, 0, ent, b.neg_ids, w.Bn, p.Nn, p.D);
   KGE_LAUNCH(c, k_apply, ceil_div(p.Nn, kWarpsPerBlock), kRowBlock, 0, ent, b.neg_ids, w.Bn, p.Nn, p.D, p.lr);
+}
+
+void launch_update(const LaunchCtx& c, const StepParams& p, const TableView& ent, const TableView& rel,
+                   const BatchView& b, const StepWs& w) {
+  launch_update_entities(c, p, ent, b, w);
   // relation entry: state was accumulated by k_chain
-  KGE_LAUNCH(c, k_apply, ceil_div(p.B, kWarpsPerBlock), kRowBlock, 0, rel, b.rel_ids, w.GR, p.B, p.Dr, p.lr);
+  if (!p.rel_deferred)
+    KGE_LAUNCH(c, k_apply, ceil_div(p.B, kWarpsPerBlock), kRowBlock, 0, rel, b.rel_ids, w.GR, p.B, p.Dr, p.lr);
+}
+
+// ---- multi-GPU relation path: per-edge gradients -> dense per-relation sums (all-reduced by the host
+// with NCCL) -> identical Adagrad on every replica.  Summing the occurrences first is the same math as
+// ExternalEmbedding.update: every occurrence is scaled by the same final state (tensor_models.py:352-361).
+__global__ void __launch_bounds__(kRowBlock) k_rel_accumulate(StepParams p, BatchView b, StepWs w,
+                                                               float* __restrict__ rg, float* __restrict__ rgs) {
+  const long long i = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (i >= p.B) return;
+  const int lane = threadIdx.x & 31;
+  const long long rid = b.rel_ids[i];
+  const float* g = w.GR + i * (long long)p.Dr;
+  float* dst = rg + rid * (long long)p.Dr;
+  for (int v = lane; v < (p.Dr >> 2); v += kWarp) red_add4(dst + 4 * v, ld4(g + 4 * v));
+  if (lane == 0) atomicAdd(rgs + rid, w.gsr[i]);
+}
+
+__global__ void __launch_bounds__(kRowBlock) k_rel_apply_dense(TableView rel, float* __restrict__ rg,
+                                                                float* __restrict__ rgs, float lr) {
+  const long long r = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (r >= rel.num_rows) return;
+  const int lane = threadIdx.x & 31;
+  const float gs = rgs[r];
+  if (gs == 0.f) return;           // relation not touched by any rank this step
+  float* st = state_ptr(rel, r);
+  float s_new = 0.f;
+  if (lane == 0) { s_new = *st + gs; *st = s_new; rgs[r] = 0.f; }
+  s_new = __shfl_sync(0xffffffffu, s_new, 0);
+  const float stdv = sqrtf(s_new) + 1e-10f;
+  float* row = row_ptr(rel, r);
+  float* g = rg + r * (long long)rel.dim;
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int v = lane; v < (rel.dim >> 2); v += kWarp) {
+    float4 x = ld4(g + 4 * v), e = ld4(row + 4 * v);
+    st4(row + 4 * v, f4_add(e, make_float4((-lr * x.x) / stdv, (-lr * x.y) / stdv, (-lr * x.z) / stdv, (-lr * x.w) / stdv)));
+    st4(g + 4 * v, z);
+  }
+}
+
+void launch_rel_grad_dense(const LaunchCtx& c, const StepParams& p, const BatchView& b, const StepWs& w, float* rg,
+                           float* rgs) {
+  KGE_LAUNCH(c, k_rel_accumulate, ceil_div(p.B, kWarpsPerBlock), kRowBlock, 0, p, b, w, rg, rgs);
+}
+void launch_rel_apply_dense(const LaunchCtx& c, const TableView& rel, float* rg, float* rgs, float lr) {
+  KGE_LAUNCH(c, k_rel_apply_dense, ceil_div(rel.num_rows, kWarpsPerBlock), kRowBlock, 0, rel, rg, rgs, lr);
 }
 
 void launch_adagrad(const LaunchCtx& c, const TableView& t, const long long* idx, const float* grad, long long n,

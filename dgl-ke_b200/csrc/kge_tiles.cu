@@ -12,11 +12,6 @@
 
 namespace kge {
 
-#define KGE_LAUNCH(ctx, kernel, grid, block, smem, ...)                         \
-  do {                                                                          \
-    kernel<<<(grid), (block), (smem), (ctx).stream>>>(__VA_ARGS__);             \
-    if ((ctx).launch_counter) ++*(ctx).launch_counter;                          \
-  } while (0)
 
 enum { OP_DOT = 0, OP_L1 = 1, OP_ROT = 2 };
 constexpr int T = 64;      // tile edge

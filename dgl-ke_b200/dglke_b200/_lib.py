@@ -18,7 +18,9 @@ BUF_POS_SCORE, BUF_NEG_SCORE, BUF_NODE_GRAD, BUF_NEG_GRAD, BUF_REL_GRAD = range(
 EXPORTS = ["kge_abi_version", "kge_last_error", "kge_create", "kge_destroy", "kge_gather", "kge_score_pos",
            "kge_score_neg", "kge_loss_grad", "kge_adagrad", "kge_forward_backward", "kge_update",
            "kge_step_fused", "kge_step_fused_host", "kge_sync", "kge_debug_read", "kge_launch_count",
-           "kge_set_engine"]
+           "kge_set_engine", "kge_profile_enable", "kge_profile_read", "kge_set_relation_mode",
+           "kge_rel_grad_dense", "kge_rel_apply_dense", "kge_device_alloc", "kge_device_free", "kge_ipc_export",
+           "kge_ipc_open"]
 
 
 class KgeError(RuntimeError):
@@ -81,6 +83,15 @@ def load_library():
     lib.kge_launch_count.argtypes = [vp]
     lib.kge_launch_count.restype = i64
     lib.kge_set_engine.argtypes = [vp, C.c_int]
+    lib.kge_profile_enable.argtypes = [vp, C.c_int]
+    lib.kge_profile_read.argtypes = [vp, C.c_char_p, C.c_int, P(f32), C.c_int]
+    lib.kge_set_relation_mode.argtypes = [vp, C.c_int]
+    lib.kge_rel_grad_dense.argtypes = [vp, vp, vp, vp]
+    lib.kge_rel_apply_dense.argtypes = [vp, P(Table), vp, vp, f32, vp]
+    lib.kge_device_alloc.argtypes = [vp, i64, P(vp)]
+    lib.kge_device_free.argtypes = [vp, vp]
+    lib.kge_ipc_export.argtypes = [vp, vp, C.c_char_p, P(i64)]
+    lib.kge_ipc_open.argtypes = [vp, C.c_char_p, i64, P(vp)]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int and name not in ("kge_abi_version",):
@@ -133,6 +144,19 @@ class Handle:
 
     def set_engine(self, engine):
         check(self.lib.kge_set_engine(self._h, int(engine)))
+
+    def profile_enable(self, on=True):
+        check(self.lib.kge_profile_enable(self._h, 1 if on else 0))
+
+    def profile_read(self):
+        """[(kernel name, milliseconds)] of every launch since the last read (syncs the device)."""
+        names = C.create_string_buffer(8192)
+        ms = (C.c_float * 64)()
+        n = self.lib.kge_profile_read(self._h, names, 8192, ms, 64)
+        if n < 0:
+            check(n)
+        nm = names.value.decode().split(",") if n else []
+        return [(nm[i], float(ms[i])) for i in range(min(n, len(nm)))]
 
 
 _handles = {}

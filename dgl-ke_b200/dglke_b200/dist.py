@@ -1,0 +1,146 @@
+"""Single-box multi-GPU training: one process per GPU (torch.distributed, NCCL).
+
+Replaces the reference's multi-GPU data flow (--mix_cpu_gpu: entity table in host shared memory,
+H2D gather / D2H scatter per step, train.py:92-95, tensor_models.py:292-294,330-361) with:
+
+  * entity table + Adagrad state: contiguous row-range shards, one per GPU's HBM
+    (owner(id) = id // ceil(N_e / G)); every rank maps all peers' shards through CUDA IPC, so the
+    step kernels gather remote rows with peer loads and scatter updates with system-scope red.add over
+    NVLink / NVSwitch from inside the kernel -- no entity collective;
+  * edges: data parallel, each rank trains on its own edge stream (reference: RandomPartition,
+    dataloader/sampler.py:256-290), Hogwild across GPUs as the reference is across processes;
+  * relation table: replicated; per-relation gradient sums and mean(g^2) sums are all-reduced with
+    NCCL every step and every replica applies the identical Adagrad update (the only collective).
+"""
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from .engine import StepEngine, DeviceTable
+
+
+class _ExternalBuffer:
+    """Wraps a raw device pointer as a torch tensor through __cuda_array_interface__."""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
+
+def shard_rows(num_rows, world, rank):
+    per = (num_rows + world - 1) // world
+    lo = min(num_rows, rank * per)
+    hi = min(num_rows, (rank + 1) * per)
+    return per, lo, hi
+
+
+def owner_of(ids, num_rows, world):
+    per = (num_rows + world - 1) // world
+    return ids // per
+
+
+class ShardedTrainer:
+    """StepEngine-compatible driver (step / step_host / sync / h) over a sharded entity table."""
+
+    def __init__(self, hp, n_ent, n_rel, device, seed=0, group=None):
+        self.hp, self.device, self.group = hp, device, group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.h = _lib.get_handle(device.index)
+        lib = self.h.lib
+        De, Dr = hp.entity_dim, hp.relation_dim
+        per, lo, hi = shard_rows(n_ent, self.world, self.rank)
+        assert hi > lo, "more GPUs than entity rows"
+        self.n_ent, self.n_rel, self.rows_per_shard, self.row_lo, self.row_hi = n_ent, n_rel, per, lo, hi
+        # local shard: library-owned cudaMalloc (plain allocations are IPC-exportable)
+        n_local = hi - lo
+        p_emb, p_st = C.c_void_p(), C.c_void_p()
+        _lib.check(lib.kge_device_alloc(self.h.raw, n_local * De * 4, C.byref(p_emb)))
+        _lib.check(lib.kge_device_alloc(self.h.raw, max(n_local, 1) * 4, C.byref(p_st)))
+        self._owned = (p_emb, p_st)
+        self.ent_local = torch.as_tensor(_ExternalBuffer(p_emb.value, (n_local, De)), device=device)
+        self.ent_state_local = torch.as_tensor(_ExternalBuffer(p_st.value, (n_local,)), device=device)
+        g = torch.Generator(device=device).manual_seed(seed * 1000003 + self.rank)
+        self.ent_local.uniform_(-hp.emb_init, hp.emb_init, generator=g)
+        self.ent_state_local.zero_()
+        # exchange IPC handles
+        mine = torch.zeros(2, 72, dtype=torch.uint8)
+        for k, ptr in enumerate((p_emb, p_st)):
+            hbuf = C.create_string_buffer(64)
+            off = C.c_int64()
+            _lib.check(lib.kge_ipc_export(self.h.raw, ptr, hbuf, C.byref(off)))
+            mine[k, :64] = torch.frombuffer(bytearray(hbuf.raw), dtype=torch.uint8)
+            mine[k, 64:] = torch.frombuffer(bytearray(int(off.value).to_bytes(8, "little", signed=True)), dtype=torch.uint8)
+        allh = [None] * self.world
+        dist.all_gather_object(allh, mine.numpy().tobytes(), group=group)
+        emb_ptrs, st_ptrs = [], []
+        for r in range(self.world):
+            if r == self.rank:
+                emb_ptrs.append(p_emb.value)
+                st_ptrs.append(p_st.value)
+                continue
+            raw = allh[r]
+            ptrs = []
+            for k in range(2):
+                rec = raw[k * 72:(k + 1) * 72]
+                off = int.from_bytes(rec[64:72], "little", signed=True)
+                out = C.c_void_p()
+                _lib.check(lib.kge_ipc_open(self.h.raw, rec[:64], off, C.byref(out)))
+                ptrs.append(out.value)
+            emb_ptrs.append(ptrs[0])
+            st_ptrs.append(ptrs[1])
+        self.ent = DeviceTable(emb_ptrs, st_ptrs, n_ent, De, devices=list(range(self.world)))
+        # replicated relation table: identical init on every rank
+        gr = torch.Generator(device=device).manual_seed(seed * 1000003 + 777)
+        self.rel_emb = torch.empty((n_rel, Dr), dtype=torch.float32, device=device).uniform_(-hp.emb_init, hp.emb_init, generator=gr)
+        self.rel_state = torch.zeros(n_rel, dtype=torch.float32, device=device)
+        dist.broadcast(self.rel_emb, src=0, group=group)
+        self.rel = DeviceTable.from_tensors(self.rel_emb, self.rel_state)
+        # dense relation-gradient buffer [n_rel * Dr | n_rel], all-reduced as one message
+        self.rbuf = torch.zeros(n_rel * Dr + n_rel, dtype=torch.float32, device=device)
+        self.rg, self.rgs = self.rbuf[:n_rel * Dr], self.rbuf[n_rel * Dr:]
+        _lib.check(lib.kge_set_relation_mode(self.h.raw, 1))
+        self.eng = StepEngine(hp, self.ent, self.rel, device.index)
+        self.log4 = self.eng.log4
+        self._log_host = torch.zeros(4, dtype=torch.float32).pin_memory()
+        dist.barrier(group=group)
+
+    # -- one training step: forward/backward, entity Adagrad over NVLink, relation all-reduce + apply
+    def step(self, node_ids, head_local, tail_local, rel_ids, neg_ids, chunk_size, neg_sample_size, neg_head,
+             edge_weight=None, log4=None):
+        lib, h = self.h.lib, self.h
+        out = self.eng.forward_backward(node_ids, head_local, tail_local, rel_ids, neg_ids, chunk_size,
+                                        neg_sample_size, neg_head, edge_weight, log4)
+        _lib.check(lib.kge_rel_grad_dense(h.raw, self.rg.data_ptr(), self.rgs.data_ptr(), h.stream()))
+        self.eng.update()
+        dist.all_reduce(self.rbuf, op=dist.ReduceOp.SUM, group=self.group)
+        _lib.check(lib.kge_rel_apply_dense(h.raw, self.rel.ref(), self.rg.data_ptr(), self.rgs.data_ptr(),
+                                           float(self.hp.lr), h.stream()))
+        return out
+
+    def step_host(self, node_ids, head_local, tail_local, rel_ids, neg_ids, chunk_size, neg_sample_size, neg_head,
+                  edge_weight=None):
+        d = lambda t: t.to(self.device, non_blocking=True)
+        out = self.step(d(node_ids), d(head_local), d(tail_local), d(rel_ids), d(neg_ids), chunk_size,
+                        neg_sample_size, neg_head, None if edge_weight is None else d(edge_weight))
+        self._log_host.copy_(out, non_blocking=True)
+        return self._log_host
+
+    def sync(self):
+        torch.cuda.current_stream(self.device).synchronize()
+
+    def barrier(self):
+        """force_sync_interval analogue (train_pytorch.py:157-159): a cross-GPU barrier."""
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)
+
+    def gather_entity_table(self):
+        """Full [n_ent, D] table on this rank's device (for saving / evaluation)."""
+        parts = [torch.empty((shard_rows(self.n_ent, self.world, r)[2] - shard_rows(self.n_ent, self.world, r)[1],
+                              self.hp.entity_dim), dtype=torch.float32, device=self.device) for r in range(self.world)]
+        dist.all_gather(parts, self.ent_local.contiguous(), group=self.group) if len({p.shape for p in parts}) == 1 else \
+            [dist.broadcast(parts[r] if r != self.rank else self.ent_local, src=r, group=self.group) for r in range(self.world)]
+        parts[self.rank] = self.ent_local
+        return torch.cat(parts, 0)

@@ -197,9 +197,32 @@ KGE_API int kge_debug_read(kge_handle_t h, int which, float* out, int64_t n_floa
 
 /* Number of kernels the library has launched on this handle since creation. */
 KGE_API int64_t kge_launch_count(kge_handle_t h);
+/* Per-launch device timing: when enabled, every kernel the library launches on this handle is
+ * bracketed by CUDA events on the launching stream (<= 64 records; enable resets the record set).
+ * kge_profile_read synchronises the device, writes the kernel names (comma separated) and their
+ * durations in milliseconds, returns the record count and starts a new record set. */
+KGE_API int kge_profile_enable(kge_handle_t h, int on);
+KGE_API int kge_profile_read(kge_handle_t h, char* names, int names_len, float* ms, int max_records);
 /* Selects the contraction engine: 0 = fp32 CUDA-core tiles, 1 = tcgen05 3xTF32 tensor-core tiles
  * (bilinear models), -1 = library default. */
 KGE_API int kge_set_engine(kge_handle_t h, int engine);
+
+/* --- multi-GPU: row-range sharded entity table over peer-mapped HBM, replicated relation table ---
+ * Replaces --mix_cpu_gpu's host-pinned shared table (general_models.py:230-231, train.py:92-95):
+ * each rank allocates its shard, exports it with kge_ipc_export, opens every peer's shard with
+ * kge_ipc_open and passes all shards in kge_table_t; kernels then gather with peer loads and
+ * scatter with system-scope red.add over NVLink.
+ * Relation rows are replicated; in deferred mode the step leaves per-edge relation gradients in the
+ * workspace, kge_rel_grad_dense sums them per relation into rg [num_rel, D_r] / rgs [num_rel]
+ * (sum of mean(g^2)), the host all-reduces both with NCCL, and kge_rel_apply_dense applies the same
+ * Adagrad update on every replica and zeroes the buffers. */
+KGE_API int kge_set_relation_mode(kge_handle_t h, int deferred);
+KGE_API int kge_rel_grad_dense(kge_handle_t h, float* rg, float* rgs, void* stream);
+KGE_API int kge_rel_apply_dense(kge_handle_t h, const kge_table_t* rel, float* rg, float* rgs, float lr, void* stream);
+KGE_API int kge_device_alloc(kge_handle_t h, int64_t bytes, void** out);
+KGE_API int kge_device_free(kge_handle_t h, void* p);
+KGE_API int kge_ipc_export(kge_handle_t h, const void* dev_ptr, uint8_t handle_out[64], int64_t* offset_out);
+KGE_API int kge_ipc_open(kge_handle_t h, const uint8_t handle[64], int64_t offset, void** out);
 
 #ifdef __cplusplus
 }
