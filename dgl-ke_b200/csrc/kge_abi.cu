@@ -297,7 +297,7 @@ KGE_API int kge_profile_read(kge_handle_t h, char* names, int names_len, float* 
   names[0] = 0;
   for (int i = 0; i < n; ++i) {
     KGE_CUDA_OK(cudaEventElapsedTime(&ms[i], p.ev0[i], p.ev1[i]));
-    int w = snprintf(names + off, names_len - off, "%s%s", i ? "," : "", p.names[i]);
+    int w = snprintf(names + off, names_len - off, "%s%s", i ? "|" : "", p.names[i]);
     if (w < 0 || off + w >= names_len) break;
     off += w;
   }

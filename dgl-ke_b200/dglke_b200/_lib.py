@@ -155,7 +155,7 @@ class Handle:
         n = self.lib.kge_profile_read(self._h, names, 8192, ms, 64)
         if n < 0:
             check(n)
-        nm = names.value.decode().split(",") if n else []
+        nm = names.value.decode().split("|") if n else []
         return [(nm[i], float(ms[i])) for i in range(min(n, len(nm)))]
 
 

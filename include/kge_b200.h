@@ -199,7 +199,7 @@ KGE_API int kge_debug_read(kge_handle_t h, int which, float* out, int64_t n_floa
 KGE_API int64_t kge_launch_count(kge_handle_t h);
 /* Per-launch device timing: when enabled, every kernel the library launches on this handle is
  * bracketed by CUDA events on the launching stream (<= 64 records; enable resets the record set).
- * kge_profile_read synchronises the device, writes the kernel names (comma separated) and their
+ * kge_profile_read synchronises the device, writes the kernel names ('|' separated) and their
  * durations in milliseconds, returns the record count and starts a new record set. */
 KGE_API int kge_profile_enable(kge_handle_t h, int on);
 KGE_API int kge_profile_read(kge_handle_t h, char* names, int names_len, float* ms, int max_records);

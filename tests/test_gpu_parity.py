@@ -56,9 +56,11 @@ def _run_and_check(hp, tables, si, C, Cs, Ns, ref, tol=2e-5):
     for i, k in enumerate(("pos_loss", "neg_loss", "loss", "regularization")):
         if k in ref["log"]:
             np.testing.assert_allclose(log[i], ref["log"][k], rtol=2e-5, atol=1e-9, err_msg=k)
-    _close(gn, ref["nodes_grad"], tol, 2e-6, "nodes_grad")
-    _close(gg, ref["negs_grad"], tol, 2e-6, "negs_grad")
-    _close(gr, ref["rels_grad"], tol, 2e-6, "rels_grad")
+    # gradients are sums of up to chunk_size (or degree) terms of alternating sign: elements that cancel
+    # carry the fp32 reordering noise of the largest partial sums => absolute floor at 1e-5 of the tensor scale
+    _close(gn, ref["nodes_grad"], tol, 1e-5, "nodes_grad")
+    _close(gg, ref["negs_grad"], tol, 1e-5, "negs_grad")
+    _close(gr, ref["rels_grad"], tol, 1e-5, "rels_grad")
     _close(e.cpu().numpy(), ref["ent_emb"], tol, 1e-6, "entity table after update")
     _close(es.cpu().numpy(), ref["ent_state"], tol, 1e-6, "entity state_sum")
     _close(r.cpu().numpy(), ref["rel_emb"], tol, 1e-6, "relation table after update")
