@@ -57,6 +57,7 @@ def parse():
     ap.add_argument("--n-ent", type=int, default=0, help="override the entity count (capacity experiments)")
     ap.add_argument("--engine", type=int, default=-1, help="-1 library default, 0 fp32 tiles, 1 tcgen05")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA graphs (profiling)")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
     ap.add_argument("--cpu-procs", type=int, default=0, help="reference arm: worker processes (0 = all host threads)")
     ap.add_argument("--cpu-batch", type=int, default=1000, help="reference arm: batch per worker (dglke_train's 1000)")
@@ -255,7 +256,7 @@ def run_ours(args):
 
     # ---- CUDA graphs of the device-resident step (one per batch): no launch gaps inside a step ----
     graphs = None
-    if world == 1:
+    if world == 1 and not args.no_graph:
         try:
             graphs = []
             for k in range(NB):

@@ -118,3 +118,46 @@ class SyntheticSampler:
         k = self.step
         self.step += 1
         return self.batch(k)
+
+
+class TripleSampler(SyntheticSampler):
+    """Same iterator over a given triple list: positives are shuffled edges (one permutation per epoch),
+    negatives uniform entity ids with replacement (DGL EdgeSampler semantics as used by
+    TrainDataset.create_sampler, dataloader/sampler.py:376-419; exclude_positive=False)."""
+
+    def __init__(self, heads, rels, tails, n_entities, n_relations, batch_size, neg_sample_size, seed=0, rank=0,
+                 world=1):
+        super().__init__(n_entities, n_relations, batch_size, neg_sample_size, seed, rank)
+        idx = np.arange(len(heads))
+        if world > 1:   # RandomPartition (sampler.py:256-290): a fixed random split of the edges over the ranks
+            idx = np.random.default_rng(seed).permutation(len(heads))[rank::world]
+        self.h, self.r, self.t = np.asarray(heads)[idx], np.asarray(rels)[idx], np.asarray(tails)[idx]
+        self.n_edges = len(self.h)
+        if self.n_edges < batch_size:
+            raise ValueError("fewer edges (%d) than batch_size (%d)" % (self.n_edges, batch_size))
+        self._perm, self._epoch = None, -1
+
+    def batch(self, k):
+        per_epoch = self.n_edges // self.B          # the ragged last batch of an epoch is skipped
+        epoch, j = divmod(k, per_epoch)
+        if epoch != self._epoch:
+            self._perm = np.random.default_rng(self.seed + 7919 * epoch).permutation(self.n_edges)
+            self._epoch = epoch
+        e = self._perm[j * self.B:(j + 1) * self.B]
+        rng = np.random.default_rng(self.seed + 15485863 + k)
+        ng = rng.integers(0, self.n_ent, self.num_chunks * self.Ns)
+        pos_g = build_pos_graph(self.h[e], self.r[e], self.t[e])
+        neg_g = NegGraph(torch.from_numpy(ng.astype(np.int64)), self.num_chunks, self.chunk_size, self.Ns,
+                         neg_head=bool(k % 2))
+        return pos_g, neg_g
+
+
+def eval_batches(heads, rels, tails, n_entities, batch_size, neg_head, candidates=None):
+    """Yield (pos_g, neg_g) where every positive is ranked against `candidates` (default: all entities):
+    one chunk per batch, chunk_size = batch, neg_sample_size = #candidates (the reference views a
+    full-entity negative graph as one chunk, sampler.py:486-490)."""
+    cand = np.arange(n_entities) if candidates is None else np.asarray(candidates)
+    cand_t = torch.from_numpy(cand.astype(np.int64))
+    for s in range(0, len(heads), batch_size):
+        h, r, t = heads[s:s + batch_size], rels[s:s + batch_size], tails[s:s + batch_size]
+        yield build_pos_graph(h, r, t), NegGraph(cand_t, 1, len(h), len(cand), neg_head)

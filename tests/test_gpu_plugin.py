@@ -1,0 +1,130 @@
+"""GPU tests of the reference-facing plugin surface: KEModel's three-call step, the stand-alone
+score_func / ExternalEmbedding ops, forward_test ranking, and the dglke_train-compatible CLI."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch as th
+
+import kge_oracle as ko
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _args(**kw):
+    from dglke_b200.utils import ArgParser
+    a = ArgParser().parse_args(["--gpu", "0"])
+    a.eval_filter, a.strict_rel_part, a.soft_rel_part = False, False, False
+    for k, v in kw.items():
+        setattr(a, k, v)
+    return a
+
+
+@pytest.mark.parametrize("model,de", [("TransE_l2", False), ("ComplEx", False), ("RotatE", True)])
+def test_kemodel_three_call_step_matches_oracle(model, de):
+    from dglke_b200.general_models import KEModel
+    from dglke_b200.graph import SyntheticSampler
+    args = _args(lr=0.1, neg_adversarial_sampling=True, regularization_coef=1e-6, double_ent=de)
+    m = KEModel(args, model, 500, 9, 32, 12.0, double_entity_emb=de)
+    hp = ko.Hyper(model=model, hidden_dim=32, gamma=12.0, lr=0.1, reg_coef=1e-6, adversarial=True, double_ent=de)
+    ent, rel = m.entity_emb.emb.cpu().clone(), m.relation_emb.emb.cpu().clone()
+    es, rs = th.zeros(500), th.zeros(9)
+    s = SyntheticSampler(500, 9, 64, 16, seed=4)
+    for step in range(3):
+        pos_g, neg_g = next(s)
+        loss, log = m.forward(pos_g, neg_g, 0)          # train_pytorch.py:141
+        loss.backward()                                 # :145
+        m.update(0)                                     # :152
+        h, t = pos_g.all_edges()
+        fb = ko.train_step(hp, ent, es, rel, rs, pos_g.ndata["id"], h, t, pos_g.edata["id"], neg_g.ndata["id"],
+                           neg_g.num_chunks, neg_g.chunk_size, neg_g.neg_sample_size, neg_g.neg_head)
+        assert sorted(log.keys()) == sorted(fb["log"].keys())
+        for k in fb["log"]:
+            np.testing.assert_allclose(log[k], fb["log"][k], rtol=5e-5, atol=1e-9)
+        np.testing.assert_allclose(float(loss), fb["loss"], rtol=5e-5)
+    np.testing.assert_allclose(m.entity_emb.emb.cpu().numpy(), ent.numpy(), rtol=2e-4, atol=2e-6)
+    np.testing.assert_allclose(m.relation_emb.emb.cpu().numpy(), rel.numpy(), rtol=2e-4, atol=2e-6)
+    np.testing.assert_allclose(m.entity_emb.state_sum.cpu().numpy(), es.numpy(), rtol=2e-4, atol=1e-9)
+
+
+def test_plugin_consistency_create_neg_vs_edge_func():
+    """The reference's own unit-test invariant (tests/test_score.py:145-182): batched create_neg scores
+    equal per-edge edge_func scores, both corruption modes, rtol=atol=1e-5."""
+    from dglke_b200.general_models import KEModel
+    dev = th.device("cuda", 0)
+    for model, de in [("TransE_l1", False), ("TransE_l2", False), ("DistMult", False), ("ComplEx", False),
+                      ("RESCAL", False), ("RotatE", True)]:
+        m = KEModel(_args(), model, 100, 5, 20 if model != "RotatE" else 10, 12.0, double_entity_emb=de)
+        C, Cs, Ns = 2, 3, 4
+        rng = np.random.default_rng(0)
+        hid, tid, nid = (th.from_numpy(rng.integers(0, 100, n)).to(dev) for n in (C * Cs, C * Cs, C * Ns))
+        rid = th.from_numpy(rng.integers(0, 5, C * Cs)).to(dev)
+        h, t, n = m.entity_emb(hid, 0, False), m.entity_emb(tid, 0, False), m.entity_emb(nid, 0, False)
+        r = m.relation_emb(rid, 0, False)
+        for neg_head in (False, True):
+            fn = m.score_func.create_neg(neg_head)
+            got = fn(n, r, t, C, Cs, Ns) if neg_head else fn(h, r, n, C, Cs, Ns)
+            for c in range(C):
+                for i in range(Cs):
+                    e = c * Cs + i
+                    rows = n[c * Ns:(c + 1) * Ns]
+
+                    class Edges:
+                        src = {"emb": rows if neg_head else h[e:e + 1].expand(Ns, -1).contiguous()}
+                        dst = {"emb": t[e:e + 1].expand(Ns, -1).contiguous() if neg_head else rows}
+                        data = {"emb": r[e:e + 1].expand(Ns, -1).contiguous()}
+                    want = m.score_func.edge_func(Edges)["score"]
+                    if model == "RESCAL" and not neg_head:
+                        continue      # reference quirk: tail-mode create_neg scores h^T M^T t' 
+                    np.testing.assert_allclose(got[c, i].cpu().numpy(), want.cpu().numpy(), rtol=1e-5, atol=1e-5)
+
+
+def test_infer_all_pairs():
+    from dglke_b200.general_models import KEModel
+    m = KEModel(_args(), "DistMult", 50, 4, 16, 12.0)
+    dev = th.device("cuda", 0)
+    h, r, t = (m.entity_emb.emb[:3], m.relation_emb.emb[:2], m.entity_emb.emb[10:15])
+    got = m.score_func.infer(h, r, t).cpu()
+    want = th.einsum("ad,bd,cd->abc", h.cpu(), r.cpu(), t.cpu())
+    np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=1e-5, atol=1e-6)
+
+
+def test_forward_test_ranks_match_oracle():
+    from dglke_b200.general_models import KEModel
+    from dglke_b200.graph import eval_batches
+    m = KEModel(_args(), "TransE_l2", 200, 6, 24, 12.0)
+    hp = ko.Hyper(model="TransE_l2", hidden_dim=24, gamma=12.0)
+    ent, rel = m.entity_emb.emb.cpu(), m.relation_emb.emb.cpu()
+    rng = np.random.default_rng(1)
+    H, R, T = rng.integers(0, 200, 10), rng.integers(0, 6, 10), rng.integers(0, 200, 10)
+    for neg_head in (False, True):
+        logs = []
+        for pg, ng in eval_batches(H, R, T, 200, 4, neg_head):
+            m.forward_test(pg, ng, logs, 0)
+        h, r, t = ent[th.from_numpy(H)], rel[th.from_numpy(R)], ent[th.from_numpy(T)]
+        pos = ko.positive_score(hp, h, r, t)
+        neg = th.cat([ko.negative_score(hp, ent if neg_head else h[i:i + 1], r[i:i + 1], t[i:i + 1] if neg_head else ent,
+                                        1, 1, 200, neg_head).reshape(1, -1) for i in range(10)])
+        want = ko.rank_of_positive(pos, neg).tolist()
+        got = [int(l["MR"]) for l in logs]
+        # ties between the positive and its own copy among the candidates are decided by ~1e-6 noise
+        assert sum(abs(a - b) for a, b in zip(got, want)) <= 2, (got, want)
+
+
+def test_cli_trains_and_saves_reference_layout(tmp_path):
+    from dglke_b200 import train
+    fx = os.path.join(ROOT, "tests", "fixtures", "udd")
+    m = train.main(["--model_name", "DistMult", "--dataset", "tiny", "--format", "udd_hrt", "--data_path", fx,
+                    "--data_files", "entities.dict", "relations.dict", "train.txt", "valid.txt", "test.txt",
+                    "--batch_size", "16", "--neg_sample_size", "4", "--hidden_dim", "8", "--max_step", "20",
+                    "--log_interval", "10", "--gpu", "0", "--save_path", str(tmp_path), "-adv", "--test",
+                    "--batch_size_eval", "4", "--lr", "0.1"])
+    out = os.path.join(str(tmp_path), "DistMult_tiny_0")
+    ent = np.load(os.path.join(out, "tiny_DistMult_entity.npy"))
+    rel = np.load(os.path.join(out, "tiny_DistMult_relation.npy"))
+    assert ent.shape == (30, 8) and rel.shape == (4, 8) and ent.dtype == np.float32
+    cfg = json.load(open(os.path.join(out, "config.json")))
+    assert cfg["model_name"] == "DistMult" and cfg["hidden_dim"] == 8 and "emp_file" in cfg
+    np.testing.assert_array_equal(ent, m.entity_emb.emb.cpu().numpy())

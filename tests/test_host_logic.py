@@ -1,0 +1,91 @@
+"""CPU tests of the host-side mirror: flag surface vs the reference's own parser, batch/chunk
+bookkeeping, graph objects and samplers (no CUDA calls)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch as th
+
+from dglke_b200 import utils, graph
+
+REF = "/root/reference/python"
+
+
+def test_flag_surface_matches_reference_parser():
+    """Every option string, default and type of dglke_train's parser (utils.py:199-297, train.py:40-60)."""
+    if not os.path.isdir(os.path.join(REF, "dglke")):
+        pytest.skip("reference tree not present (GPU box)")
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import ref_harness as rh
+    rh.import_reference()
+    import importlib
+    ref_utils = importlib.import_module("dglke.utils")
+    ref_parser = ref_utils.CommonArgParser()
+    ours = utils.CommonArgParser()
+
+    def table(p):
+        return {tuple(a.option_strings): (a.default, a.type, a.nargs, tuple(a.choices) if a.choices else None,
+                                          type(a).__name__)
+                for a in p._actions if a.option_strings and a.dest != "help"}
+    assert table(ours) == table(ref_parser)
+    # train-only flags (train.py:44-60): read from the source since importing dglke.train needs more of DGL
+    src = open(os.path.join(REF, "dglke", "train.py")).read()
+    for flag in ("--gpu", "--mix_cpu_gpu", "--valid", "--rel_part", "--async_update", "--has_edge_importance"):
+        assert flag in src
+        assert any(flag in a.option_strings for a in utils.ArgParser()._actions)
+
+
+def test_defaults_worth_knowing():
+    a = utils.ArgParser().parse_args([])
+    assert (a.hidden_dim, a.batch_size, a.neg_sample_size, a.lr, a.gamma) == (400, 1024, 256, 0.01, 12.0)
+    assert (a.regularization_coef, a.regularization_norm, a.loss_genre, a.gpu) == (2e-6, 3, "Logsigmoid", [-1])
+
+
+def test_batch_size_rounding():
+    assert utils.get_compatible_batch_size(1000, 256) == 1024     # utils.py:27-33
+    assert utils.get_compatible_batch_size(1024, 256) == 1024
+    assert utils.get_compatible_batch_size(100, 256) == 100       # smaller than neg: untouched
+
+
+def test_chunk_layout_matches_reference_rules():
+    assert graph.chunk_layout(1000, 200) == (5, 200)
+    assert graph.chunk_layout(100, 256) == (1, 100)               # sampler.py:497-500
+    assert graph.chunk_layout(1001, 200) is None                  # ragged: skipped (sampler.py:503-504)
+
+
+def test_pos_graph_and_sampler():
+    pg = graph.build_pos_graph([5, 3, 5], [0, 1, 0], [3, 9, 9])
+    assert pg.ndata["id"].tolist() == [3, 5, 9]
+    h, t = pg.all_edges(order="eid")
+    assert pg.ndata["id"][h].tolist() == [5, 3, 5] and pg.ndata["id"][t].tolist() == [3, 9, 9]
+    assert pg.number_of_edges() == 3
+    s = graph.SyntheticSampler(100, 7, 12, 4, seed=1)
+    p1, n1 = next(s)
+    p2, n2 = next(s)
+    assert (n1.neg_head, n2.neg_head) == (False, True)           # tail first, then head (sampler.py:853-859)
+    assert (n1.num_chunks, n1.chunk_size, n1.neg_sample_size) == (3, 4, 4)
+    assert n1.ndata["id"][n1.tail_nid].shape[0] == 12
+    p1b, _ = graph.SyntheticSampler(100, 7, 12, 4, seed=1).batch(0)
+    assert th.equal(p1.ndata["id"], p1b.ndata["id"])             # seeded => reproducible
+
+
+def test_triple_sampler_epochs_and_partition():
+    rng = np.random.default_rng(0)
+    h, r, t = rng.integers(0, 50, 100), rng.integers(0, 3, 100), rng.integers(0, 50, 100)
+    s = graph.TripleSampler(h, r, t, 50, 3, 20, 5, seed=2)
+    seen = []
+    for k in range(5):                                            # one epoch = 5 batches of 20
+        pg, ng = s.batch(k)
+        hh, tt = pg.all_edges()
+        seen += list(zip(pg.ndata["id"][hh].tolist(), pg.edata["id"].tolist(), pg.ndata["id"][tt].tolist()))
+    assert sorted(seen) == sorted(zip(h.tolist(), r.tolist(), t.tolist()))
+    parts = [graph.TripleSampler(h, r, t, 50, 3, 10, 5, seed=2, rank=k, world=2).n_edges for k in range(2)]
+    assert sum(parts) == 100
+
+
+def test_eval_batches_one_chunk_all_entities():
+    b = list(graph.eval_batches(np.array([1, 2, 3]), np.array([0, 0, 1]), np.array([4, 5, 6]), 10, 2, True))
+    assert len(b) == 2
+    pg, ng = b[0]
+    assert (ng.num_chunks, ng.chunk_size, ng.neg_sample_size, ng.neg_head) == (1, 2, 10, True)
