@@ -14,6 +14,9 @@
 #include <cuda.h>
 #include "kge_common.cuh"
 
+namespace kge {
+bool umma_supported(const StepParams&);
+}
 using namespace kge;
 
 namespace {
@@ -161,6 +164,9 @@ int carve(kge_context* h, const StepParams& p, StepWs* w, cudaStream_t stream) {
   size_t ors = take(p.B), ocs = take(p.Nn), opl = take(p.B), onl = take(p.B);
   size_t oreg = take((size_t)p.B + p.Nn + U), owb = take(4), ogsr = take(p.B);
   size_t oMt = rescal ? take(BD) : 0;
+  const bool um = (h->engine == 1) && umma_supported(p);
+  size_t oAh = um ? take(BD) : 0, oAl = um ? take(BD) : 0, oBh = um ? take(ND) : 0, oBl = um ? take(ND) : 0;
+  size_t oVh = um ? take(BNs) : 0, oVl = um ? take(BNs) : 0;
   if (need > h->arena_bytes) {
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(stream, &cs);
@@ -181,6 +187,9 @@ int carve(kge_context* h, const StepParams& p, StepWs* w, cudaStream_t stream) {
   w->a2 = (float*)(a + oa2); w->b2 = (float*)(a + ob2); w->rowsum = (float*)(a + ors); w->colsum = (float*)(a + ocs);
   w->pl = (float*)(a + opl); w->nl = (float*)(a + onl); w->regp = (float*)(a + oreg); w->wbar = (float*)(a + owb); w->gsr = (float*)(a + ogsr);
   w->Mt = rescal ? (float*)(a + oMt) : nullptr;
+  w->Ahi = um ? (float*)(a + oAh) : nullptr; w->Alo = um ? (float*)(a + oAl) : nullptr;
+  w->Bhi = um ? (float*)(a + oBh) : nullptr; w->Blo = um ? (float*)(a + oBl) : nullptr;
+  w->Vhi = um ? (float*)(a + oVh) : nullptr; w->Vlo = um ? (float*)(a + oVl) : nullptr;
   return KGE_OK;
 }
 
@@ -327,7 +336,7 @@ KGE_API int kge_gather(kge_handle_t h, const kge_table_t* table, const int64_t* 
 }
 
 static bool use_umma(kge_context* h, const StepParams& p) {
-  if (h->engine == 0) return false;
+  if (h->engine != 1) return false;   // default: fp32 tiles until the tcgen05 engine is the validated default
   return umma_supported(p);
 }
 

@@ -73,6 +73,10 @@ struct StepWs {
   float* wbar;     // [1]      mean edge weight
   float* gsr;      // [B]      mean(GR_i^2) per edge (deferred relation update)
   float* Mt;       // [B, D]   RESCAL: M_r t  (tail mode needs it next to A = M_r h)
+  // tcgen05 engine: TF32 hi/lo splits of the contraction operands
+  float *Ahi, *Alo;   // [B, D]
+  float *Bhi, *Blo;   // [Nn, D]
+  float *Vhi, *Vlo;   // [B, Ns]
 };
 
 struct BatchView {

@@ -1,9 +1,437 @@
-// kge_umma.cu -- tcgen05 (5th-gen tensor core) engine for the bilinear contractions.
-// Placeholder until the 3xTF32 UMMA kernels land: reports "not supported" so the fp32 tile
-// engine (kge_tiles.cu) runs.
+// kge_umma.cu -- tcgen05 (5th-gen tensor core) engine for the three chunked contractions of the
+// bilinear / L2 models (TransE_l2, DistMult, ComplEx, RESCAL):
+//
+//   GEMM1  S[c]  = A[c]   . Bn[c]^T     (Cs x Ns, K = D)    both operands K-major
+//   GEMM2  GA[c] = V[c]   . Bn[c]       (Cs x D,  K = Ns)   A K-major, B MN-major
+//   GEMM3  GB[c] = V[c]^T . A[c]        (Ns x D,  K = Cs)   both operands MN-major
+//
+// fp32 fidelity on TF32 tensor cores: every operand is split x = hi + lo (both rounded to TF32) by
+// k_split_tf32 and each k-step issues hi*hi + hi*lo + lo*hi (3xTF32), accumulating in fp32 in TMEM.
+//
+// One CTA per 128 x Nt output tile (Nt <= 256): warp 0 = TMA producer (cp.async.bulk.tensor, 128B
+// swizzle, mbarrier pipeline), warp 1 = TMEM allocator + single-thread tcgen05.mma issuer,
+// warps 2-5 = epilogue (tcgen05.ld 32x32b: one accumulator row per thread).
+#include <cuda.h>
+#include <cstdio>
 #include "kge_common.cuh"
+
 namespace kge {
-bool umma_supported(const StepParams&) { return false; }
-int umma_score(const LaunchCtx&, const StepParams&, const StepWs&, char*, size_t) { return KGE_ERR_UNSUPPORTED; }
-int umma_grad(const LaunchCtx&, const StepParams&, const StepWs&, bool, char*, size_t) { return KGE_ERR_UNSUPPORTED; }
+
+namespace {
+
+constexpr int kBlockK = 32;                 // fp32 elements per k-block = one 128-byte swizzle span
+constexpr int kUmmaK = 8;                   // tf32: 32 bytes per MMA k-step
+constexpr int kTileM = 128;
+constexpr int kStages = 2;
+constexpr int kThreads = 192;
+constexpr int kTmemCols = 256;
+
+enum { G_SCORE = 0, G_GA = 1, G_GB = 2 };
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int y) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// shared-memory matrix descriptor, 128-byte swizzle (cute::UMMA::SmemDescriptor bit layout)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;            // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;            // SWIZZLE_128B
+  return d;
+}
+// instruction descriptor: D=f32, A=B=tf32, majors, N>>3, M>>4 (cute::UMMA::InstrDescriptor)
+__host__ __device__ inline uint32_t make_idesc(int M, int N, bool a_mn, bool b_mn) {
+  uint32_t d = 0;
+  d |= 1u << 4;                      // c_format = F32
+  d |= 2u << 7;                      // a_format = TF32
+  d |= 2u << 10;                     // b_format = TF32
+  d |= (a_mn ? 1u : 0u) << 15;
+  d |= (b_mn ? 1u : 0u) << 16;
+  d |= (uint32_t)(N >> 3) << 17;
+  d |= (uint32_t)(M >> 4) << 24;
+  return d;
+}
+
+struct GemmArgs {
+  int mode;              // G_SCORE / G_GA / G_GB
+  int C;                 // chunks
+  int rowsA_per_chunk;   // M-dimension rows per chunk (Cs for SCORE/GA, Ns for GB)
+  int rowsB_per_chunk;   // N-dimension rows per chunk when B is K-major (Ns for SCORE)
+  int krows_per_chunk;   // K extent (D for SCORE, Ns for GA, Cs for GB)
+  int b_box_rows;        // rows of the TMA box of a K-major B operand (tile N of the tensor map)
+  int model;
+  float gamma, reg_coef;
+  int reg_norm;
+  int Cs, Ns, D;
+  // epilogue pointers
+  float* out;            // SCORE: S [B,Ns] ; GA: GA [B,D] ; GB: Bn [Nn,D] (in place)
+  float* out2;           // SCORE: Vdist (TransE_l2)
+  const float* a2;       // SCORE l2
+  const float* b2;
+  const float* colsum;   // GB l2
+};
+
+// smem layout per stage: [A_hi | A_lo | B_hi | B_lo], each tile 1024-byte aligned
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kThreads, 1)
+k_umma_gemm(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
+            const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, GemmArgs g) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages], tmem_full_bar;
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.z;
+  const int m0 = blockIdx.y * kTileM;                 // row offset inside the chunk (M dimension)
+  const int n0 = blockIdx.x * 256;                    // column offset (N dimension)
+  const int Nleft = (g.mode == G_SCORE ? g.Ns : g.D) - n0;
+  const int Nt = Nleft >= 256 ? 256 : ((Nleft + 15) & ~15);      // UMMA N (multiple of 16)
+  const int nblk = (Nt + 31) >> 5;                                // 32-wide MN blocks of B (MN-major)
+  const int K = g.krows_per_chunk;
+  const int num_kb = (K + kBlockK - 1) / kBlockK;
+
+  constexpr uint32_t kABytes = kTileM * 128;                      // one A tile (hi or lo): 128 rows x 128 B
+  const uint32_t bBytes = B_MN ? (uint32_t)nblk * 4096u : (uint32_t)g.b_box_rows * 128u;
+  const uint32_t bBytesAligned = (bBytes + 1023u) & ~1023u;
+  const uint32_t stageBytes = 2 * kABytes + 2 * bBytesAligned;
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      // global coordinates
+      const int a_row0 = c * g.rowsA_per_chunk + m0;       // K-major A: row (M) coordinate
+      const int a_col0 = c * 0;                            // (unused)
+      (void)a_col0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % kStages;
+        const uint32_t ph = (kb / kStages) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* st = smem + (size_t)s * stageBytes;
+        uint8_t* sAh = st; uint8_t* sAl = st + kABytes;
+        uint8_t* sBh = st + 2 * kABytes; uint8_t* sBl = sBh + bBytesAligned;
+        const int k0 = kb * kBlockK;
+        uint32_t tx = 2 * kABytes + 2 * bBytes;
+        mbar_expect_tx(&full_bar[s], tx);
+        if (!A_MN) {
+          // A[rows = M][cols = K]: box {32 k, 128 rows}
+          tma_load_2d(sAh, &tmAh, &full_bar[s], k0, a_row0);
+          tma_load_2d(sAl, &tmAl, &full_bar[s], k0, a_row0);
+        } else {
+          // A stored [rows = K][cols = M] (V rows i = K, cols j = M): 4 boxes {32 m, 32 k}
+          const int krow0 = c * g.krows_per_chunk + k0;
+#pragma unroll
+          for (int b = 0; b < kTileM / 32; ++b) {
+            tma_load_2d(sAh + b * 4096, &tmAh, &full_bar[s], m0 + b * 32, krow0);
+            tma_load_2d(sAl + b * 4096, &tmAl, &full_bar[s], m0 + b * 32, krow0);
+          }
+        }
+        if (!B_MN) {
+          // B[rows = N][cols = K]: box {32 k, Nt rows}
+          const int b_row0 = c * g.rowsB_per_chunk + n0;
+          tma_load_2d(sBh, &tmBh, &full_bar[s], k0, b_row0);
+          tma_load_2d(sBl, &tmBl, &full_bar[s], k0, b_row0);
+        } else {
+          // B stored [rows = K][cols = N]: nblk boxes {32 n, 32 k}
+          const int krow0 = c * g.krows_per_chunk + k0;
+          for (int b = 0; b < nblk; ++b) {
+            tma_load_2d(sBh + b * 4096, &tmBh, &full_bar[s], n0 + b * 32, krow0);
+            tma_load_2d(sBl + b * 4096, &tmBl, &full_bar[s], n0 + b * 32, krow0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(kTileM, Nt, A_MN, B_MN);
+      uint32_t accumulate = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % kStages;
+        const uint32_t ph = (kb / kStages) & 1;
+        mbar_wait(&full_bar[s], ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t st = smem_u32(smem + (size_t)s * stageBytes);
+        const uint32_t sAh = st, sAl = st + kABytes, sBh = st + 2 * kABytes, sBl = sBh + bBytesAligned;
+        const int kleft = K - kb * kBlockK;
+        const int ksteps = kleft >= kBlockK ? kBlockK / kUmmaK : kleft / kUmmaK;   // K % 8 == 0 guaranteed
+        for (int ks = 0; ks < ksteps; ++ks) {
+          // K-major: +32 bytes per k-step inside the 128-byte swizzle span; SBO = 1024 (8-row groups)
+          // MN-major: one k-step = one 8-row atom (1024 bytes); LBO = 4096 between 32-wide MN blocks
+          const uint32_t aoff = A_MN ? ks * 1024u : ks * 32u;
+          const uint32_t boff = B_MN ? ks * 1024u : ks * 32u;
+          const uint64_t dAh = A_MN ? make_desc(sAh + aoff, 4096, 1024) : make_desc(sAh + aoff, 16, 1024);
+          const uint64_t dAl = A_MN ? make_desc(sAl + aoff, 4096, 1024) : make_desc(sAl + aoff, 16, 1024);
+          const uint64_t dBh = B_MN ? make_desc(sBh + boff, 4096, 1024) : make_desc(sBh + boff, 16, 1024);
+          const uint64_t dBl = B_MN ? make_desc(sBl + boff, 4096, 1024) : make_desc(sBl + boff, 16, 1024);
+          umma_tf32(tmem_base, dAh, dBh, idesc, accumulate);
+          umma_tf32(tmem_base, dAh, dBl, idesc, 1u);
+          umma_tf32(tmem_base, dAl, dBh, idesc, 1u);
+          accumulate = 1u;
+        }
+        umma_commit(&empty_bar[s]);          // frees the smem stage when these MMAs retire
+      }
+      umma_commit(&tmem_full_bar);           // accumulator complete
+    }
+  } else {
+    // ===================== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====================
+    mbar_wait(&tmem_full_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int q = warp & 3;
+    const int row_in_tile = q * 32 + lane;                 // accumulator row (M index) owned by this thread
+    const int m = m0 + row_in_tile;
+    const int Mrows = g.rowsA_per_chunk;
+    const bool row_ok = m < Mrows;
+    const uint32_t taddr_row = tmem_base + ((uint32_t)(q * 32) << 16);
+    if (g.mode == G_SCORE) {
+      const long long gi = (long long)c * g.Cs + m;
+      const float a2v = (row_ok && g.model == KGE_TRANSE_L2) ? g.a2[gi] : 0.f;
+      for (int col = 0; col < Nt; col += 8) {
+        float v[8];
+        tmem_ld8(taddr_row + col, v);
+        if (!row_ok) continue;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int j = n0 + col + e;
+          if (j >= g.Ns) continue;
+          float s;
+          if (g.model == KGE_TRANSE_L2) {
+            float sq = fmaf(-2.f, v[e], g.b2[(long long)c * g.Ns + j]) + a2v;
+            float d = sqrtf(fmaxf(sq, 1e-30f));
+            g.out2[gi * g.Ns + j] = d;
+            s = g.gamma - d;
+          } else {
+            s = v[e];
+          }
+          g.out[gi * g.Ns + j] = s;
+        }
+      }
+    } else if (g.mode == G_GA) {
+      float* row = g.out + ((long long)c * g.Cs + m) * g.D;
+      for (int col = 0; col < Nt; col += 8) {
+        float v[8];
+        tmem_ld8(taddr_row + col, v);
+        if (!row_ok) continue;
+        const int k = n0 + col;
+        if (k + 8 <= g.D) {
+          st4(row + k, make_float4(v[0], v[1], v[2], v[3]));
+          st4(row + k + 4, make_float4(v[4], v[5], v[6], v[7]));
+        } else {
+          for (int e = 0; e < 8; ++e) if (k + e < g.D) row[k + e] = v[e];
+        }
+      }
+    } else {  // G_GB: gradient of the negative rows, written over the gathered rows
+      float* row = g.out + ((long long)c * g.Ns + m) * g.D;
+      const float cs = (row_ok && g.model == KGE_TRANSE_L2) ? g.colsum[(long long)c * g.Ns + m] : 0.f;
+      for (int col = 0; col < Nt; col += 8) {
+        float v[8];
+        tmem_ld8(taddr_row + col, v);
+        if (!row_ok) continue;
+        const int k = n0 + col;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          if (k + e >= g.D) continue;
+          float b = row[k + e];
+          float gv = v[e];
+          if (g.model == KGE_TRANSE_L2) gv = fmaf(-cs, b, gv);
+          gv += reg_grad(b, g.reg_norm, g.reg_coef);
+          row[k + e] = gv;
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+  }
+}
+
+// x -> (hi, lo): hi = rna_tf32(x), lo = rna_tf32(x - hi)
+__global__ void k_split_tf32(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, long long n4) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n4; i += stride) {
+    float4 v = ld4(x + 4 * i), h, l;
+#define KGE_SPLIT(c_)                                                            \
+    { uint32_t hb; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v.c_));       \
+      h.c_ = __uint_as_float(hb); float r = v.c_ - h.c_; uint32_t lb;            \
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(r)); l.c_ = __uint_as_float(lb); }
+    KGE_SPLIT(x) KGE_SPLIT(y) KGE_SPLIT(z) KGE_SPLIT(w)
+#undef KGE_SPLIT
+    st4(hi + 4 * i, h);
+    st4(lo + 4 * i, l);
+  }
+}
+
+// ---- host side ----------------------------------------------------------------------------------
+typedef CUresult (*encode_fn_t)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+encode_fn_t get_encode() {
+  static encode_fn_t fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (encode_fn_t)p;
+  }
+  return fn;
+}
+
+// 2-D fp32 row-major matrix [rows, cols], box {32 cols, box_rows}, 128-byte swizzle, zero OOB fill
+bool make_map(CUtensorMap* m, const float* base, long long rows, long long cols, int box_rows, char* err, size_t errlen) {
+  encode_fn_t enc = get_encode();
+  if (!enc) { snprintf(err, errlen, "cuTensorMapEncodeTiled not available"); return false; }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 4};
+  cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { snprintf(err, errlen, "cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld box_rows=%d", (int)r, rows, cols, box_rows); return false; }
+  return true;
+}
+
+size_t smem_bytes_for(int Nt, bool b_mn) {
+  const int nblk = (Nt + 31) >> 5;
+  size_t b = b_mn ? (size_t)nblk * 4096 : (size_t)Nt * 128;
+  b = (b + 1023) & ~(size_t)1023;
+  return (size_t)kStages * (2 * kTileM * 128 + 2 * b) + 1024;
+}
+
+template <bool A_MN, bool B_MN>
+int launch_gemm(const LaunchCtx& c, const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh,
+                const CUtensorMap& bl, const GemmArgs& g, int ntiles_n, int Nt_max, char* err, size_t errlen) {
+  size_t smem = smem_bytes_for(Nt_max, B_MN);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_umma_gemm<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) { snprintf(err, errlen, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return KGE_ERR_CUDA; }
+    attr_set = true;
+  }
+  dim3 grid(ntiles_n, (g.rowsA_per_chunk + kTileM - 1) / kTileM, g.C);
+  KGE_LAUNCH(c, (k_umma_gemm<A_MN, B_MN>), grid, kThreads, smem, ah, al, bh, bl, g);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { snprintf(err, errlen, "umma launch: %s", cudaGetErrorString(e)); return KGE_ERR_CUDA; }
+  return KGE_OK;
+}
+
+void split(const LaunchCtx& c, const float* x, float* hi, float* lo, long long n) {
+  long long n4 = n / 4;
+  int grid = (int)((n4 + 255) / 256);
+  if (grid > c.num_sms * 16) grid = c.num_sms * 16;
+  if (grid < 1) grid = 1;
+  KGE_LAUNCH(c, k_split_tf32, grid, 256, 0, x, hi, lo, n4);
+}
+
+}  // namespace
+
+bool umma_supported(const StepParams& p) {
+  const bool model_ok = p.model == KGE_TRANSE_L2 || p.model == KGE_DISTMULT || p.model == KGE_COMPLEX || p.model == KGE_RESCAL;
+  return model_ok && (p.D % 8 == 0) && (p.Cs % 8 == 0) && (p.Ns % 8 == 0) && p.D >= 32 && p.Cs >= 8 && p.Ns >= 8;
+}
+
+// S = A . Bn^T  (+ TransE_l2 distance epilogue)
+int umma_score(const LaunchCtx& c, const StepParams& p, const StepWs& w, char* err, size_t errlen) {
+  split(c, w.A, w.Ahi, w.Alo, p.B * (long long)p.D);
+  split(c, w.Bn, w.Bhi, w.Blo, p.Nn * (long long)p.D);
+  const int Nt_max = p.Ns >= 256 ? 256 : ((p.Ns + 15) & ~15);
+  CUtensorMap ah, al, bh, bl;
+  if (!make_map(&ah, w.Ahi, p.B, p.D, kTileM, err, errlen) || !make_map(&al, w.Alo, p.B, p.D, kTileM, err, errlen) ||
+      !make_map(&bh, w.Bhi, p.Nn, p.D, Nt_max, err, errlen) || !make_map(&bl, w.Blo, p.Nn, p.D, Nt_max, err, errlen))
+    return KGE_ERR_CUDA;
+  GemmArgs g{};
+  g.mode = G_SCORE; g.C = p.C; g.rowsA_per_chunk = p.Cs; g.rowsB_per_chunk = p.Ns; g.krows_per_chunk = p.D;
+  g.b_box_rows = Nt_max;
+  g.model = p.model; g.gamma = p.gamma; g.reg_coef = p.reg_coef; g.reg_norm = p.reg_norm;
+  g.Cs = p.Cs; g.Ns = p.Ns; g.D = p.D;
+  g.out = w.S; g.out2 = w.V; g.a2 = w.a2; g.b2 = w.b2; g.colsum = nullptr;
+  return launch_gemm<false, false>(c, ah, al, bh, bl, g, (p.Ns + 255) / 256, Nt_max, err, errlen);
+}
+
+// side_b == false: GA = V . Bn ; side_b == true: G_neg = V^T . A (+ epilogue), in place over Bn
+int umma_grad(const LaunchCtx& c, const StepParams& p, const StepWs& w, bool side_b, char* err, size_t errlen) {
+  const int Nt_max = p.D >= 256 ? 256 : ((p.D + 15) & ~15);
+  CUtensorMap ah, al, bh, bl;
+  GemmArgs g{};
+  g.C = p.C; g.model = p.model; g.gamma = p.gamma; g.reg_coef = p.reg_coef; g.reg_norm = p.reg_norm;
+  g.Cs = p.Cs; g.Ns = p.Ns; g.D = p.D; g.colsum = w.colsum;
+  if (!side_b) {
+    split(c, w.V, w.Vhi, w.Vlo, p.B * (long long)p.Ns);
+    // A operand: V [B, Ns] K-major (K = j); B operand: Bn hi/lo [Nn, D] MN-major (rows = K = j, cols = N = k)
+    if (!make_map(&ah, w.Vhi, p.B, p.Ns, kTileM, err, errlen) || !make_map(&al, w.Vlo, p.B, p.Ns, kTileM, err, errlen) ||
+        !make_map(&bh, w.Bhi, p.Nn, p.D, 32, err, errlen) || !make_map(&bl, w.Blo, p.Nn, p.D, 32, err, errlen))
+      return KGE_ERR_CUDA;
+    g.mode = G_GA; g.rowsA_per_chunk = p.Cs; g.rowsB_per_chunk = 0; g.krows_per_chunk = p.Ns; g.out = w.GA;
+    return launch_gemm<false, true>(c, ah, al, bh, bl, g, (p.D + 255) / 256, Nt_max, err, errlen);
+  }
+  // A operand: V^T: stored V [B, Ns] = [rows = K = i][cols = M = j] MN-major; B operand: A hi/lo [B, D] MN-major
+  if (!make_map(&ah, w.Vhi, p.B, p.Ns, 32, err, errlen) || !make_map(&al, w.Vlo, p.B, p.Ns, 32, err, errlen) ||
+      !make_map(&bh, w.Ahi, p.B, p.D, 32, err, errlen) || !make_map(&bl, w.Alo, p.B, p.D, 32, err, errlen))
+    return KGE_ERR_CUDA;
+  g.mode = G_GB; g.rowsA_per_chunk = p.Ns; g.rowsB_per_chunk = 0; g.krows_per_chunk = p.Cs; g.out = w.Bn;
+  return launch_gemm<true, true>(c, ah, al, bh, bl, g, (p.D + 255) / 256, Nt_max, err, errlen);
+}
+
 }  // namespace kge
