@@ -164,7 +164,7 @@ int carve(kge_context* h, const StepParams& p, StepWs* w, cudaStream_t stream) {
   size_t ors = take(p.B), ocs = take(p.Nn), opl = take(p.B), onl = take(p.B);
   size_t oreg = take((size_t)p.B + p.Nn + U), owb = take(4), ogsr = take(p.B);
   size_t oMt = rescal ? take(BD) : 0;
-  const bool um = (h->engine == 1) && umma_supported(p);
+  const bool um = (h->engine != 0) && umma_supported(p);
   size_t oAh = um ? take(BD) : 0, oAl = um ? take(BD) : 0, oBh = um ? take(ND) : 0, oBl = um ? take(ND) : 0;
   size_t oVh = um ? take(BNs) : 0, oVl = um ? take(BNs) : 0;
   if (need > h->arena_bytes) {
@@ -336,7 +336,7 @@ KGE_API int kge_gather(kge_handle_t h, const kge_table_t* table, const int64_t* 
 }
 
 static bool use_umma(kge_context* h, const StepParams& p) {
-  if (h->engine != 1) return false;   // default: fp32 tiles until the tcgen05 engine is the validated default
+  if (h->engine == 0) return false;   // engine -1 (default) / 1: tcgen05 whenever the shape allows it
   return umma_supported(p);
 }
 

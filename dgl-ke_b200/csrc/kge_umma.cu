@@ -72,13 +72,15 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
 }
 
 // shared-memory matrix descriptor, 128-byte swizzle (cute::UMMA::SmemDescriptor bit layout)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// layout_type: 2 = SWIZZLE_128B (K-major operands), 1 = SWIZZLE_128B_BASE32B (the only layout the
+// tensor core accepts for MN-major tf32 operands; matches TMA's SWIZZLE_128B_ATOM_32B)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type = 2) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;            // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;            // SWIZZLE_128B
+  d |= (uint64_t)layout_type << 61;
   return d;
 }
 // instruction descriptor: D=f32, A=B=tf32, majors, N>>3, M>>4 (cute::UMMA::InstrDescriptor)
@@ -213,13 +215,14 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CU
         const int ksteps = kleft >= kBlockK ? kBlockK / kUmmaK : kleft / kUmmaK;   // K % 8 == 0 guaranteed
         for (int ks = 0; ks < ksteps; ++ks) {
           // K-major: +32 bytes per k-step inside the 128-byte swizzle span; SBO = 1024 (8-row groups)
-          // MN-major: one k-step = one 8-row atom (1024 bytes); LBO = 4096 between 32-wide MN blocks
+          // MN-major (128B swizzle, 32B atoms): k-atoms of 4 rows (512 B, SBO), one k-step = 2 atoms = 1024 B;
+          // LBO = 4096 between 32-wide MN blocks
           const uint32_t aoff = A_MN ? ks * 1024u : ks * 32u;
           const uint32_t boff = B_MN ? ks * 1024u : ks * 32u;
-          const uint64_t dAh = A_MN ? make_desc(sAh + aoff, 4096, 1024) : make_desc(sAh + aoff, 16, 1024);
-          const uint64_t dAl = A_MN ? make_desc(sAl + aoff, 4096, 1024) : make_desc(sAl + aoff, 16, 1024);
-          const uint64_t dBh = B_MN ? make_desc(sBh + boff, 4096, 1024) : make_desc(sBh + boff, 16, 1024);
-          const uint64_t dBl = B_MN ? make_desc(sBl + boff, 4096, 1024) : make_desc(sBl + boff, 16, 1024);
+          const uint64_t dAh = A_MN ? make_desc(sAh + aoff, 4096, 512, 1) : make_desc(sAh + aoff, 16, 1024);
+          const uint64_t dAl = A_MN ? make_desc(sAl + aoff, 4096, 512, 1) : make_desc(sAl + aoff, 16, 1024);
+          const uint64_t dBh = B_MN ? make_desc(sBh + boff, 4096, 512, 1) : make_desc(sBh + boff, 16, 1024);
+          const uint64_t dBl = B_MN ? make_desc(sBl + boff, 4096, 512, 1) : make_desc(sBl + boff, 16, 1024);
           umma_tf32(tmem_base, dAh, dBh, idesc, accumulate);
           umma_tf32(tmem_base, dAh, dBl, idesc, 1u);
           umma_tf32(tmem_base, dAl, dBh, idesc, 1u);
@@ -339,7 +342,8 @@ encode_fn_t get_encode() {
 }
 
 // 2-D fp32 row-major matrix [rows, cols], box {32 cols, box_rows}, 128-byte swizzle, zero OOB fill
-bool make_map(CUtensorMap* m, const float* base, long long rows, long long cols, int box_rows, char* err, size_t errlen) {
+bool make_map(CUtensorMap* m, const float* base, long long rows, long long cols, int box_rows, char* err, size_t errlen,
+              bool mn_major = false) {
   encode_fn_t enc = get_encode();
   if (!enc) { snprintf(err, errlen, "cuTensorMapEncodeTiled not available"); return false; }
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -347,7 +351,8 @@ bool make_map(CUtensorMap* m, const float* base, long long rows, long long cols,
   cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1u, 1u};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { snprintf(err, errlen, "cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld box_rows=%d", (int)r, rows, cols, box_rows); return false; }
   return true;
@@ -421,14 +426,14 @@ int umma_grad(const LaunchCtx& c, const StepParams& p, const StepWs& w, bool sid
     split(c, w.V, w.Vhi, w.Vlo, p.B * (long long)p.Ns);
     // A operand: V [B, Ns] K-major (K = j); B operand: Bn hi/lo [Nn, D] MN-major (rows = K = j, cols = N = k)
     if (!make_map(&ah, w.Vhi, p.B, p.Ns, kTileM, err, errlen) || !make_map(&al, w.Vlo, p.B, p.Ns, kTileM, err, errlen) ||
-        !make_map(&bh, w.Bhi, p.Nn, p.D, 32, err, errlen) || !make_map(&bl, w.Blo, p.Nn, p.D, 32, err, errlen))
+        !make_map(&bh, w.Bhi, p.Nn, p.D, 32, err, errlen, true) || !make_map(&bl, w.Blo, p.Nn, p.D, 32, err, errlen, true))
       return KGE_ERR_CUDA;
     g.mode = G_GA; g.rowsA_per_chunk = p.Cs; g.rowsB_per_chunk = 0; g.krows_per_chunk = p.Ns; g.out = w.GA;
     return launch_gemm<false, true>(c, ah, al, bh, bl, g, (p.D + 255) / 256, Nt_max, err, errlen);
   }
   // A operand: V^T: stored V [B, Ns] = [rows = K = i][cols = M = j] MN-major; B operand: A hi/lo [B, D] MN-major
-  if (!make_map(&ah, w.Vhi, p.B, p.Ns, 32, err, errlen) || !make_map(&al, w.Vlo, p.B, p.Ns, 32, err, errlen) ||
-      !make_map(&bh, w.Ahi, p.B, p.D, 32, err, errlen) || !make_map(&bl, w.Alo, p.B, p.D, 32, err, errlen))
+  if (!make_map(&ah, w.Vhi, p.B, p.Ns, 32, err, errlen, true) || !make_map(&al, w.Vlo, p.B, p.Ns, 32, err, errlen, true) ||
+      !make_map(&bh, w.Ahi, p.B, p.D, 32, err, errlen, true) || !make_map(&bl, w.Alo, p.B, p.D, 32, err, errlen, true))
     return KGE_ERR_CUDA;
   g.mode = G_GB; g.rowsA_per_chunk = p.Ns; g.rowsB_per_chunk = 0; g.krows_per_chunk = p.Cs; g.out = w.Bn;
   return launch_gemm<true, true>(c, ah, al, bh, bl, g, (p.D + 255) / 256, Nt_max, err, errlen);
