@@ -55,6 +55,7 @@ struct kge_context {
   // pinned + device staging for the *_host entry points
   char* pin = nullptr;
   char* dev_stage = nullptr;
+  float* red_partial = nullptr;      // k_reduce_log partials + ticket (persistent, zero-initialised once)
   size_t stage_bytes = 0;
   float* dev_log4 = nullptr;
   // last step (for kge_update / kge_debug_read)
@@ -186,6 +187,7 @@ int carve(kge_context* h, const StepParams& p, StepWs* w, cudaStream_t stream) {
   w->pos = (float*)(a + opos); w->gpos = (float*)(a + ogpos); w->pnorm = (float*)(a + opn);
   w->a2 = (float*)(a + oa2); w->b2 = (float*)(a + ob2); w->rowsum = (float*)(a + ors); w->colsum = (float*)(a + ocs);
   w->pl = (float*)(a + opl); w->nl = (float*)(a + onl); w->regp = (float*)(a + oreg); w->wbar = (float*)(a + owb); w->gsr = (float*)(a + ogsr);
+  w->red_partial = h->red_partial; w->red_ticket = (unsigned int*)(h->red_partial + 192);
   w->Mt = rescal ? (float*)(a + oMt) : nullptr;
   w->Ahi = um ? (float*)(a + oAh) : nullptr; w->Alo = um ? (float*)(a + oAl) : nullptr;
   w->Bhi = um ? (float*)(a + oBh) : nullptr; w->Blo = um ? (float*)(a + oBl) : nullptr;
@@ -261,6 +263,9 @@ KGE_API int kge_create(int device, kge_handle_t* out) {
   h->num_sms = prop.multiProcessorCount;
   DeviceGuard g(device);
   if (cudaMalloc(&h->dev_log4, 4 * sizeof(float)) != cudaSuccess) { delete h; return fail(KGE_ERR_NOMEM, "cudaMalloc failed"); }
+  if (cudaMalloc(&h->red_partial, 256 * sizeof(float)) != cudaSuccess || cudaMemset(h->red_partial, 0, 256 * sizeof(float)) != cudaSuccess) {
+    delete h; return fail(KGE_ERR_NOMEM, "cudaMalloc failed");
+  }
   *out = h;
   return KGE_OK;
 }
@@ -273,6 +278,7 @@ KGE_API int kge_destroy(kge_handle_t h) {
   if (h->dev_stage) cudaFree(h->dev_stage);
   if (h->pin) cudaFreeHost(h->pin);
   if (h->dev_log4) cudaFree(h->dev_log4);
+  if (h->red_partial) cudaFree(h->red_partial);
   if (h->prof.created)
     for (int i = 0; i < Profiler::kMax; ++i) { cudaEventDestroy(h->prof.ev0[i]); cudaEventDestroy(h->prof.ev1[i]); }
   delete h;

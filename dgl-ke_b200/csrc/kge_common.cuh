@@ -72,6 +72,8 @@ struct StepWs {
   float* regp;     // [B + Nn + U] partial sums of |x|^p
   float* wbar;     // [1]      mean edge weight
   float* gsr;      // [B]      mean(GR_i^2) per edge (deferred relation update)
+  float* red_partial;         // [64 * 3] partial sums of k_reduce_log
+  unsigned int* red_ticket;   // [1] completion ticket of k_reduce_log (zero between launches)
   float* Mt;       // [B, D]   RESCAL: M_r t  (tail mode needs it next to A = M_r h)
   // tcgen05 engine: TF32 hi/lo splits of the contraction operands
   float *Ahi, *Alo;   // [B, D]
@@ -147,6 +149,33 @@ __device__ __forceinline__ float f4_hsum(float4 a) { return (a.x + a.y) + (a.z +
 __device__ __forceinline__ float f4_dot(float4 a, float4 b) { return f4_hsum(f4_mul(a, b)); }
 __device__ __forceinline__ float sgnf(float x) { return (x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : 0.f); }
 
+// 3xTF32 operand split: x = hi + lo with hi = rna_tf32(x), lo = rna_tf32(x - hi)
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  uint32_t hb, lb;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(x));
+  hi = __uint_as_float(hb);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(x - hi));
+  lo = __uint_as_float(lb);
+}
+__device__ __forceinline__ void split_tf32_4(float4 v, float4& h, float4& l) {
+  split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+}
+// destination of an operand row: plain fp32 and/or its TF32 hi/lo split (tcgen05 engine)
+struct RowOut {
+  float* f32;
+  float* hi;
+  float* lo;
+};
+__device__ __forceinline__ void row_store4(const RowOut& o, int off, float4 v) {
+  if (o.f32) *reinterpret_cast<float4*>(o.f32 + off) = v;
+  if (o.hi) {
+    float4 h, l;
+    split_tf32_4(v, h, l);
+    *reinterpret_cast<float4*>(o.hi + off) = h;
+    *reinterpret_cast<float4*>(o.lo + off) = l;
+  }
+}
+
 // |x|^p  and  d/dx coef*|x|^p  (general_models.py:572-576: coef * norm(x, p)**p)
 __device__ __forceinline__ float abs_pow(float x, int p) {
   float ax = fabsf(x);
@@ -213,6 +242,14 @@ inline void prof_end(const LaunchCtx& c) {
   cudaEventRecord(p->ev1[p->n], c.stream);
   ++p->n;
 }
+
+#define KGE_LAUNCH_NAMED(ctx, name, kernel, grid, block, smem, ...)            \
+  do {                                                                          \
+    prof_begin((ctx), name);                                                    \
+    kernel<<<(grid), (block), (smem), (ctx).stream>>>(__VA_ARGS__);             \
+    prof_end((ctx));                                                            \
+    if ((ctx).launch_counter) ++*(ctx).launch_counter;                          \
+  } while (0)
 
 #define KGE_LAUNCH(ctx, kernel, grid, block, smem, ...)                         \
   do {                                                                          \

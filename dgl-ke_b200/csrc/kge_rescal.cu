@@ -58,7 +58,11 @@ __global__ void __launch_bounds__(kBlock) k_rescal_fwd(StepParams p, const float
   float pos = 0.f;
   for (int k = threadIdx.x; k < D; k += kBlock) {
     pos += sh[k] * sMt[k];
-    if (want_a) w.A[i * (long long)D + k] = p.neg_head ? sMt[k] : sMh[k];
+    if (want_a) {
+      const float av = p.neg_head ? sMt[k] : sMh[k];
+      if (w.Ahi) { float hh, ll; split_tf32(av, hh, ll); w.Ahi[i * (long long)D + k] = hh; w.Alo[i * (long long)D + k] = ll; }
+      else w.A[i * (long long)D + k] = av;
+    }
     if (!dense) w.Mt[i * (long long)D + k] = sMt[k];
   }
   pos = warp_sum(pos); reg = warp_sum(reg);

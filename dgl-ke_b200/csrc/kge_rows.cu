@@ -106,7 +106,7 @@ __device__ __forceinline__ void phase_cos_sin(float4 r, float inv_scale_den, flo
 template <int MODEL>
 __device__ __forceinline__ void edge_forward(const StepParams& p, const float* __restrict__ h,
                                              const float* __restrict__ r, const float* __restrict__ t,
-                                             float* __restrict__ a_out, int lane, float& pos_out, float& a2_out,
+                                             const RowOut& a_out, int lane, float& pos_out, float& a2_out,
                                              float& reg_out, float& nrm_out, bool want_a) {
   EdgeAcc acc{0.f, 0.f, 0.f};
   const bool reg_on = (p.reg_coef > 0.f && p.reg_norm > 0);
@@ -127,7 +127,7 @@ __device__ __forceinline__ void edge_forward(const StepParams& p, const float* _
       }
       float4 are, aim;
       edge_slice_cplx<MODEL>(hr, hi, tr, ti, cr, ci, p.neg_head, are, aim, acc);
-      if (want_a) { st4(a_out + 4 * v, are); st4(a_out + half + 4 * v, aim); }
+      if (want_a) { row_store4(a_out, 4 * v, are); row_store4(a_out, half + 4 * v, aim); }
     }
   } else {
     const int nv = p.D >> 2;
@@ -136,7 +136,7 @@ __device__ __forceinline__ void edge_forward(const StepParams& p, const float* _
       if (reg_on) acc.reg += abs_pow4_sum(r4, p.reg_norm);
       float4 a;
       edge_slice_real<MODEL>(h4, r4, t4, p.neg_head, a, acc);
-      if (want_a) st4(a_out + 4 * v, a);
+      if (want_a) row_store4(a_out, 4 * v, a);
     }
   }
   float s = warp_sum(acc.pos);
@@ -160,7 +160,10 @@ __global__ void __launch_bounds__(kRowBlock) k_prep(StepParams p, TableView ent,
     const float* t = row_ptr(ent, b.node_ids[b.tail_local[job]]);
     const float* r = row_ptr(rel, b.rel_ids[job]);
     float pos, a2, reg, nrm;
-    edge_forward<MODEL>(p, h, r, t, w.A + job * (long long)p.D, lane, pos, a2, reg, nrm, true);
+    const long long ro = job * (long long)p.D;
+    // tcgen05 engine: A is only consumed as hi/lo operands; fp32 tiles: plain fp32
+    const RowOut ao{w.Ahi ? nullptr : w.A + ro, w.Ahi ? w.Ahi + ro : nullptr, w.Ahi ? w.Alo + ro : nullptr};
+    edge_forward<MODEL>(p, h, r, t, ao, lane, pos, a2, reg, nrm, true);
     if (lane == 0) {
       w.pos[job] = pos;
       if (MODEL == KGE_TRANSE_L2) { w.a2[job] = a2; w.pnorm[job] = nrm; }
@@ -171,11 +174,12 @@ __global__ void __launch_bounds__(kRowBlock) k_prep(StepParams p, TableView ent,
   job -= p.B;
   if (job < p.Nn) {
     const float* src = row_ptr(ent, b.neg_ids[job]);
-    float* dst = w.Bn + job * (long long)p.D;
+    const long long ro = job * (long long)p.D;
+    const RowOut bo{w.Bn + ro, w.Bhi ? w.Bhi + ro : nullptr, w.Bhi ? w.Blo + ro : nullptr};
     float b2 = 0.f, reg = 0.f;
     for (int v = lane; v < (p.D >> 2); v += kWarp) {
       float4 x = ld4_stream(src + 4 * v);
-      st4(dst + 4 * v, x);
+      row_store4(bo, 4 * v, x);
       if (MODEL == KGE_TRANSE_L2) b2 += f4_dot(x, x);
       if (reg_on) reg += abs_pow4_sum(x, p.reg_norm);
     }
@@ -211,8 +215,10 @@ __global__ void __launch_bounds__(kRowBlock) k_prep_dense(StepParams p, const fl
     const float* trow = tail + job * (long long)p.D;
     // kge_score_neg passes the negatives in place of the corrupted side: only the kept side is read
     if (!want_pos) { if (p.neg_head) hrow = trow; else trow = hrow; }
-    edge_forward<MODEL>(p, hrow, relr + job * (long long)p.Dr, trow,
-                        want_a ? w.A + job * (long long)p.D : nullptr, lane, pos, a2, reg, nrm, want_a);
+    const long long ro = job * (long long)p.D;
+    const RowOut ao{(want_a && !w.Ahi) ? w.A + ro : nullptr, (want_a && w.Ahi) ? w.Ahi + ro : nullptr,
+                    (want_a && w.Ahi) ? w.Alo + ro : nullptr};
+    edge_forward<MODEL>(p, hrow, relr + job * (long long)p.Dr, trow, ao, lane, pos, a2, reg, nrm, want_a);
     if (lane == 0) {
       if (want_pos) w.pos[job] = pos;
       if (want_a && MODEL == KGE_TRANSE_L2) w.a2[job] = a2;
@@ -220,12 +226,18 @@ __global__ void __launch_bounds__(kRowBlock) k_prep_dense(StepParams p, const fl
     return;
   }
   job -= p.B;
-  if (job < p.Nn && negrows != nullptr && MODEL == KGE_TRANSE_L2) {
+  if (job < p.Nn && negrows != nullptr) {
     const float* src = negrows + job * (long long)p.D;
+    const long long ro = job * (long long)p.D;
+    const RowOut bo{nullptr, w.Bhi ? w.Bhi + ro : nullptr, w.Bhi ? w.Blo + ro : nullptr};
     float b2 = 0.f;
-    for (int v = lane; v < (p.D >> 2); v += kWarp) { float4 x = ld4(src + 4 * v); b2 += f4_dot(x, x); }
+    for (int v = lane; v < (p.D >> 2); v += kWarp) {
+      float4 x = ld4(src + 4 * v);
+      b2 += f4_dot(x, x);
+      row_store4(bo, 4 * v, x);
+    }
     b2 = warp_sum(b2);
-    if (lane == 0) w.b2[job] = b2;
+    if (lane == 0 && MODEL == KGE_TRANSE_L2) w.b2[job] = b2;
   }
 }
 
@@ -256,7 +268,7 @@ void launch_prep_nonedge(const LaunchCtx& c, const StepParams& p, const TableVie
 
 void launch_prep_dense(const LaunchCtx& c, const StepParams& p, const float* head, const float* relr,
                        const float* tail, const float* negrows, const StepWs& w, bool want_pos, bool want_a) {
-  long long jobs = p.B + ((negrows && p.model == KGE_TRANSE_L2) ? p.Nn : 0);
+  long long jobs = p.B + ((negrows && (p.model == KGE_TRANSE_L2 || w.Bhi)) ? p.Nn : 0);
   KGE_DISPATCH_MODEL(p.model, KGE_LAUNCH(c, k_prep_dense<M>, ceil_div(jobs, kWarpsPerBlock), kRowBlock, 0, p, head,
                                          relr, tail, negrows, w, want_pos, want_a));
 }
@@ -269,7 +281,8 @@ __global__ void __launch_bounds__(kRowBlock) k_loss(StepParams p, const float* _
                                                      const float* __restrict__ S, const float* __restrict__ wt,
                                                      const float* __restrict__ wbar, float* __restrict__ V,
                                                      float* __restrict__ gpos, float* __restrict__ rowsum,
-                                                     float* __restrict__ pl, float* __restrict__ nl) {
+                                                     float* __restrict__ pl, float* __restrict__ nl,
+                                                     float* __restrict__ Vhi, float* __restrict__ Vlo) {
   long long i = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   if (i >= p.B) return;
   const int lane = threadIdx.x & 31;
@@ -295,6 +308,7 @@ __global__ void __launch_bounds__(kRowBlock) k_loss(StepParams p, const float* _
     float coef = g;
     if (p.model == KGE_TRANSE_L2) { float dist = v[j]; coef = g / dist; rs += coef; }   // v[j] = |a-b| from k_score
     v[j] = coef;
+    if (Vhi) { float hh, ll; split_tf32(coef, hh, ll); Vhi[i * (long long)p.Ns + j] = hh; Vlo[i * (long long)p.Ns + j] = ll; }
   }
   nls = warp_sum(nls);
   rs = warp_sum(rs);
@@ -308,14 +322,24 @@ __global__ void __launch_bounds__(kRowBlock) k_loss(StepParams p, const float* _
   }
 }
 
-__global__ void k_colsum(StepParams p, const float* __restrict__ V, float* __restrict__ colsum) {
-  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= p.Nn) return;
-  long long c = t / p.Ns; int j = (int)(t - c * p.Ns);
-  const float* v = V + (c * p.Cs) * (long long)p.Ns + j;
+// colsum[c, j] = sum_i V[c, i, j]: one CTA per (chunk, 32 columns); 8 warps split the rows, fixed-order
+// shared-memory reduction (deterministic).
+__global__ void __launch_bounds__(256) k_colsum(StepParams p, const float* __restrict__ V, float* __restrict__ colsum) {
+  __shared__ float part[8][33];
+  const int c = blockIdx.y, j = blockIdx.x * 32 + (threadIdx.x & 31), w = threadIdx.x >> 5;
   float s = 0.f;
-  for (int i = 0; i < p.Cs; ++i) s += v[(long long)i * p.Ns];
-  colsum[t] = s;
+  if (j < p.Ns) {
+    const float* v = V + ((long long)c * p.Cs) * p.Ns + j;
+    for (int i = w; i < p.Cs; i += 8) s += v[(long long)i * p.Ns];
+  }
+  part[w][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (w == 0 && j < p.Ns) {
+    float t = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) t += part[q][threadIdx.x];
+    colsum[(long long)c * p.Ns + j] = t;
+  }
 }
 
 __device__ __forceinline__ float block_sum(float v, float* sh) {
@@ -337,23 +361,42 @@ __global__ void __launch_bounds__(1024) k_mean(const float* __restrict__ x, long
   if (threadIdx.x == 0) *out = s / (float)n;
 }
 
-// log4 = {pos_loss, neg_loss, loss (no reg), reg}
-__global__ void __launch_bounds__(1024) k_reduce_log(StepParams p, const float* __restrict__ pl,
-                                                      const float* __restrict__ nl, const float* __restrict__ regp,
-                                                      long long nreg, const float* __restrict__ wbar,
-                                                      float* __restrict__ log4) {
+// log4 = {pos_loss, neg_loss, loss (no reg), reg}.  kRedBlocks CTAs reduce fixed slices into partials;
+// the CTA that finishes last (ticket counter) adds the partials in index order => deterministic.
+constexpr int kRedBlocks = 64;
+__global__ void __launch_bounds__(256) k_reduce_log(StepParams p, const float* __restrict__ pl,
+                                                     const float* __restrict__ nl, const float* __restrict__ regp,
+                                                     long long nreg, const float* __restrict__ wbar,
+                                                     float* __restrict__ partial, unsigned int* __restrict__ ticket,
+                                                     float* __restrict__ log4) {
   __shared__ float sh[32];
+  __shared__ bool last;
   float a = 0.f, b = 0.f, r = 0.f;
-  for (long long i = threadIdx.x; i < p.B; i += blockDim.x) { a += pl[i]; b += nl[i]; }
-  for (long long i = threadIdx.x; i < nreg; i += blockDim.x) r += regp[i];
+  const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = t0; i < p.B; i += stride) { a += pl[i]; b += nl[i]; }
+  for (long long i = t0; i < nreg; i += stride) r += regp[i];
   a = block_sum(a, sh);
   b = block_sum(b, sh);
   r = block_sum(r, sh);
   if (threadIdx.x == 0) {
-    float pos_loss = a / (float)p.B * (wbar ? *wbar : 1.f);
-    float neg_loss = b / (float)p.B;
+    partial[blockIdx.x * 3 + 0] = a; partial[blockIdx.x * 3 + 1] = b; partial[blockIdx.x * 3 + 2] = r;
+    __threadfence();
+    unsigned int t = atomicAdd(ticket, 1u);
+    last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    float sa = 0.f, sb = 0.f, sr = 0.f;
+    for (int q = 0; q < (int)gridDim.x; ++q) {
+      sa += ((volatile float*)partial)[q * 3 + 0]; sb += ((volatile float*)partial)[q * 3 + 1];
+      sr += ((volatile float*)partial)[q * 3 + 2];
+    }
+    float pos_loss = sa / (float)p.B * (wbar ? *wbar : 1.f);
+    float neg_loss = sb / (float)p.B;
     log4[0] = pos_loss; log4[1] = neg_loss; log4[2] = (neg_loss + pos_loss) / 2.f;
-    log4[3] = p.reg_coef * r;
+    log4[3] = p.reg_coef * sr;
+    *ticket = 0u;      // ready for the next step
   }
 }
 
@@ -361,12 +404,12 @@ void launch_loss(const LaunchCtx& c, const StepParams& p, const float* pos, cons
                  const StepWs& w, float* log4, bool want_reg) {
   if (wt) KGE_LAUNCH(c, k_mean, 1, 1024, 0, wt, p.B, w.wbar);
   KGE_LAUNCH(c, k_loss, ceil_div(p.B, kWarpsPerBlock), kRowBlock, 0, p, pos, S, wt, w.wbar, w.V, w.gpos, w.rowsum,
-             w.pl, w.nl);
-  if (p.model == KGE_TRANSE_L2) KGE_LAUNCH(c, k_colsum, ceil_div(p.Nn, 256), 256, 0, p, w.V, w.colsum);
+             w.pl, w.nl, w.Vhi, w.Vlo);
+  if (p.model == KGE_TRANSE_L2) KGE_LAUNCH(c, k_colsum, dim3(ceil_div(p.Ns, 32), p.C), 256, 0, p, w.V, w.colsum);
   const bool reg_on = want_reg && (p.reg_coef > 0.f && p.reg_norm > 0);
   if (log4)
-    KGE_LAUNCH(c, k_reduce_log, 1, 1024, 0, p, w.pl, w.nl, w.regp, reg_on ? (p.B + p.Nn + p.U) : 0,
-               wt ? w.wbar : nullptr, log4);
+    KGE_LAUNCH(c, k_reduce_log, kRedBlocks, 256, 0, p, w.pl, w.nl, w.regp, reg_on ? (p.B + p.Nn + p.U) : 0,
+               wt ? w.wbar : nullptr, w.red_partial, w.red_ticket, log4);
 }
 
 // ------------------------------------------------------------------------------------------ a9

@@ -71,6 +71,17 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                 "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // shared-memory matrix descriptor, 128-byte swizzle (cute::UMMA::SmemDescriptor bit layout)
 // layout_type: 2 = SWIZZLE_128B (K-major operands), 1 = SWIZZLE_128B_BASE32B (the only layout the
 // tensor core accepts for MN-major tf32 operands; matches TMA's SWIZZLE_128B_ATOM_32B)
@@ -242,59 +253,79 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CU
     const int Mrows = g.rowsA_per_chunk;
     const bool row_ok = m < Mrows;
     const uint32_t taddr_row = tmem_base + ((uint32_t)(q * 32) << 16);
+    // Nt is a multiple of 16; Ns, D are multiples of 8: every 8-column group is entirely valid or entirely padding
     if (g.mode == G_SCORE) {
       const long long gi = (long long)c * g.Cs + m;
-      const float a2v = (row_ok && g.model == KGE_TRANSE_L2) ? g.a2[gi] : 0.f;
-      for (int col = 0; col < Nt; col += 8) {
-        float v[8];
-        tmem_ld8(taddr_row + col, v);
+      const bool l2 = g.model == KGE_TRANSE_L2;
+      const float a2v = (row_ok && l2) ? g.a2[gi] : 0.f;
+      const float* b2c = g.b2 + (long long)c * g.Ns;
+      for (int col = 0; col < Nt; col += 16) {
+        float v[16];
+        tmem_ld16(taddr_row + col, v);
         if (!row_ok) continue;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int j = n0 + col + e;
+        for (int h8 = 0; h8 < 2; ++h8) {
+          const int j = n0 + col + h8 * 8;
           if (j >= g.Ns) continue;
-          float s;
-          if (g.model == KGE_TRANSE_L2) {
-            float sq = fmaf(-2.f, v[e], g.b2[(long long)c * g.Ns + j]) + a2v;
-            float d = sqrtf(fmaxf(sq, 1e-30f));
-            g.out2[gi * g.Ns + j] = d;
-            s = g.gamma - d;
+          float sc[8];
+          if (l2) {
+            // batched_l2_dist (score_fun.py:26-34): (|b|^2 - 2 a.b) + |a|^2, clamp, sqrt
+            float4 bq0 = ld4(b2c + j), bq1 = ld4(b2c + j + 4);
+            const float bb[8] = {bq0.x, bq0.y, bq0.z, bq0.w, bq1.x, bq1.y, bq1.z, bq1.w};
+            float d[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              float sq = fmaf(-2.f, v[h8 * 8 + e], bb[e]) + a2v;
+              d[e] = sqrtf(fmaxf(sq, 1e-30f));
+              sc[e] = g.gamma - d[e];
+            }
+            st4(g.out2 + gi * g.Ns + j, make_float4(d[0], d[1], d[2], d[3]));
+            st4(g.out2 + gi * g.Ns + j + 4, make_float4(d[4], d[5], d[6], d[7]));
           } else {
-            s = v[e];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) sc[e] = v[h8 * 8 + e];
           }
-          g.out[gi * g.Ns + j] = s;
+          st4(g.out + gi * g.Ns + j, make_float4(sc[0], sc[1], sc[2], sc[3]));
+          st4(g.out + gi * g.Ns + j + 4, make_float4(sc[4], sc[5], sc[6], sc[7]));
         }
       }
     } else if (g.mode == G_GA) {
       float* row = g.out + ((long long)c * g.Cs + m) * g.D;
-      for (int col = 0; col < Nt; col += 8) {
-        float v[8];
-        tmem_ld8(taddr_row + col, v);
+      for (int col = 0; col < Nt; col += 16) {
+        float v[16];
+        tmem_ld16(taddr_row + col, v);
         if (!row_ok) continue;
-        const int k = n0 + col;
-        if (k + 8 <= g.D) {
-          st4(row + k, make_float4(v[0], v[1], v[2], v[3]));
-          st4(row + k + 4, make_float4(v[4], v[5], v[6], v[7]));
-        } else {
-          for (int e = 0; e < 8; ++e) if (k + e < g.D) row[k + e] = v[e];
+#pragma unroll
+        for (int h8 = 0; h8 < 2; ++h8) {
+          const int k = n0 + col + h8 * 8;
+          if (k >= g.D) continue;
+          st4(row + k, make_float4(v[h8 * 8 + 0], v[h8 * 8 + 1], v[h8 * 8 + 2], v[h8 * 8 + 3]));
+          st4(row + k + 4, make_float4(v[h8 * 8 + 4], v[h8 * 8 + 5], v[h8 * 8 + 6], v[h8 * 8 + 7]));
         }
       }
     } else {  // G_GB: gradient of the negative rows, written over the gathered rows
       float* row = g.out + ((long long)c * g.Ns + m) * g.D;
-      const float cs = (row_ok && g.model == KGE_TRANSE_L2) ? g.colsum[(long long)c * g.Ns + m] : 0.f;
-      for (int col = 0; col < Nt; col += 8) {
-        float v[8];
-        tmem_ld8(taddr_row + col, v);
+      const bool l2 = g.model == KGE_TRANSE_L2;
+      const float cs = (row_ok && l2) ? g.colsum[(long long)c * g.Ns + m] : 0.f;
+      for (int col = 0; col < Nt; col += 16) {
+        float v[16];
+        tmem_ld16(taddr_row + col, v);
         if (!row_ok) continue;
-        const int k = n0 + col;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          if (k + e >= g.D) continue;
-          float b = row[k + e];
-          float gv = v[e];
-          if (g.model == KGE_TRANSE_L2) gv = fmaf(-cs, b, gv);
-          gv += reg_grad(b, g.reg_norm, g.reg_coef);
-          row[k + e] = gv;
+        for (int h8 = 0; h8 < 2; ++h8) {
+          const int k = n0 + col + h8 * 8;
+          if (k >= g.D) continue;
+          float4 b0 = ld4(row + k), b1 = ld4(row + k + 4);
+          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+          float o[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float gv = v[h8 * 8 + e];
+            if (l2) gv = fmaf(-cs, bb[e], gv);                 // sum_i V_ij a_i - (sum_i V_ij) b_j
+            o[e] = gv + reg_grad(bb[e], g.reg_norm, g.reg_coef);
+          }
+          st4(row + k, make_float4(o[0], o[1], o[2], o[3]));
+          st4(row + k + 4, make_float4(o[4], o[5], o[6], o[7]));
         }
       }
     }
@@ -341,9 +372,40 @@ encode_fn_t get_encode() {
   return fn;
 }
 
-// 2-D fp32 row-major matrix [rows, cols], box {32 cols, box_rows}, 128-byte swizzle, zero OOB fill
+// cuTensorMapEncodeTiled costs ~0.1 ms per call on this driver; the workspace matrices keep their
+// addresses between steps, so the encoded maps are cached (per host thread).
+struct MapKey { const void* base; long long rows, cols; int box_rows; bool mn; };
+struct MapCache {
+  static constexpr int kN = 32;
+  MapKey keys[kN];
+  CUtensorMap maps[kN];
+  int n = 0, next = 0;
+};
+thread_local MapCache g_maps;
+
+bool make_map_uncached(CUtensorMap* m, const float* base, long long rows, long long cols, int box_rows, char* err,
+                       size_t errlen, bool mn_major);
+
 bool make_map(CUtensorMap* m, const float* base, long long rows, long long cols, int box_rows, char* err, size_t errlen,
               bool mn_major = false) {
+  MapCache& mc = g_maps;
+  for (int i = 0; i < mc.n; ++i) {
+    const MapKey& k = mc.keys[i];
+    if (k.base == base && k.rows == rows && k.cols == cols && k.box_rows == box_rows && k.mn == mn_major) {
+      *m = mc.maps[i];
+      return true;
+    }
+  }
+  if (!make_map_uncached(m, base, rows, cols, box_rows, err, errlen, mn_major)) return false;
+  int slot = mc.n < MapCache::kN ? mc.n++ : (mc.next++ % MapCache::kN);
+  mc.keys[slot] = MapKey{base, rows, cols, box_rows, mn_major};
+  mc.maps[slot] = *m;
+  return true;
+}
+
+// 2-D fp32 row-major matrix [rows, cols], box {32 cols, box_rows}, 128-byte swizzle, zero OOB fill
+bool make_map_uncached(CUtensorMap* m, const float* base, long long rows, long long cols, int box_rows, char* err,
+                       size_t errlen, bool mn_major) {
   encode_fn_t enc = get_encode();
   if (!enc) { snprintf(err, errlen, "cuTensorMapEncodeTiled not available"); return false; }
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -376,7 +438,8 @@ int launch_gemm(const LaunchCtx& c, const CUtensorMap& ah, const CUtensorMap& al
     attr_set = true;
   }
   dim3 grid(ntiles_n, (g.rowsA_per_chunk + kTileM - 1) / kTileM, g.C);
-  KGE_LAUNCH(c, (k_umma_gemm<A_MN, B_MN>), grid, kThreads, smem, ah, al, bh, bl, g);
+  const char* nm = g.mode == G_SCORE ? "k_umma_gemm<score S=A.Bn^T>" : (g.mode == G_GA ? "k_umma_gemm<grad_a GA=V.Bn>" : "k_umma_gemm<grad_b GB=V^T.A>");
+  KGE_LAUNCH_NAMED(c, nm, (k_umma_gemm<A_MN, B_MN>), grid, kThreads, smem, ah, al, bh, bl, g);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { snprintf(err, errlen, "umma launch: %s", cudaGetErrorString(e)); return KGE_ERR_CUDA; }
   return KGE_OK;
@@ -399,8 +462,7 @@ bool umma_supported(const StepParams& p) {
 
 // S = A . Bn^T  (+ TransE_l2 distance epilogue)
 int umma_score(const LaunchCtx& c, const StepParams& p, const StepWs& w, char* err, size_t errlen) {
-  split(c, w.A, w.Ahi, w.Alo, p.B * (long long)p.D);
-  split(c, w.Bn, w.Bhi, w.Blo, p.Nn * (long long)p.D);
+  // operands arrive already split: k_prep writes A / Bn as TF32 hi/lo, k_loss writes V hi/lo
   const int Nt_max = p.Ns >= 256 ? 256 : ((p.Ns + 15) & ~15);
   CUtensorMap ah, al, bh, bl;
   if (!make_map(&ah, w.Ahi, p.B, p.D, kTileM, err, errlen) || !make_map(&al, w.Alo, p.B, p.D, kTileM, err, errlen) ||
@@ -423,7 +485,6 @@ int umma_grad(const LaunchCtx& c, const StepParams& p, const StepWs& w, bool sid
   g.C = p.C; g.model = p.model; g.gamma = p.gamma; g.reg_coef = p.reg_coef; g.reg_norm = p.reg_norm;
   g.Cs = p.Cs; g.Ns = p.Ns; g.D = p.D; g.colsum = w.colsum;
   if (!side_b) {
-    split(c, w.V, w.Vhi, w.Vlo, p.B * (long long)p.Ns);
     // A operand: V [B, Ns] K-major (K = j); B operand: Bn hi/lo [Nn, D] MN-major (rows = K = j, cols = N = k)
     if (!make_map(&ah, w.Vhi, p.B, p.Ns, kTileM, err, errlen) || !make_map(&al, w.Vlo, p.B, p.Ns, kTileM, err, errlen) ||
         !make_map(&bh, w.Bhi, p.Nn, p.D, 32, err, errlen, true) || !make_map(&bl, w.Blo, p.Nn, p.D, 32, err, errlen, true))

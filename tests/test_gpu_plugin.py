@@ -56,7 +56,7 @@ def test_plugin_consistency_create_neg_vs_edge_func():
     dev = th.device("cuda", 0)
     for model, de in [("TransE_l1", False), ("TransE_l2", False), ("DistMult", False), ("ComplEx", False),
                       ("RESCAL", False), ("RotatE", True)]:
-        m = KEModel(_args(), model, 100, 5, 20 if model != "RotatE" else 10, 12.0, double_entity_emb=de)
+        m = KEModel(_args(), model, 100, 5, 24 if model != "RotatE" else 12, 12.0, double_entity_emb=de)
         C, Cs, Ns = 2, 3, 4
         rng = np.random.default_rng(0)
         hid, tid, nid = (th.from_numpy(rng.integers(0, 100, n)).to(dev) for n in (C * Cs, C * Cs, C * Ns))
