@@ -27,15 +27,16 @@ for _p in (ROOT, os.path.join(ROOT, "dgl-ke_b200")):
 
 WORKLOADS = {
     # name: (model, n_ent, n_rel, hidden, gamma, lr, rc, neg, double_ent, default batch, description)
-    "fb15k_transe_l2": ("TransE_l2", 14951, 1345, 400, 19.9, 0.25, 1e-9, 200, False, 4000,
+    # default batch 14800 = 74 chunks of 200: the contraction GEMMs then launch 148 / 296 CTAs = whole waves of the 148 SMs
+    "fb15k_transe_l2": ("TransE_l2", 14951, 1345, 400, 19.9, 0.25, 1e-9, 200, False, 14800,
                         "TransE_l2 FB15k-shape d=400 neg=200 -adv (BASELINE configs[1])"),
     "wikikg2_rotate": ("RotatE", 2500604, 535, 200, 12.0, 0.01, 1e-9, 256, True, 4096,
                        "RotatE wikikg2-shape d=200 -de neg=256 -adv (BASELINE configs[2])"),
-    "freebase_complex": ("ComplEx", 86054151, 14824, 400, 143.0, 0.1, 2e-6, 200, False, 4000,
+    "freebase_complex": ("ComplEx", 86054151, 14824, 400, 143.0, 0.1, 2e-6, 200, False, 14800,
                          "ComplEx Freebase-shape 86M entities d=400 neg=200 -adv (BASELINE configs[3])"),
     "synth_distmult": ("DistMult", 100000000, 10000, 512, 143.0, 0.08, 2e-6, 1024, False, 4096,
                        "DistMult synthetic 100M entities d=512 neg=1024 -adv (BASELINE configs[4])"),
-    "big_transe_l2": ("TransE_l2", 20000000, 1345, 400, 19.9, 0.25, 1e-9, 200, False, 4000,
+    "big_transe_l2": ("TransE_l2", 20000000, 1345, 400, 19.9, 0.25, 1e-9, 200, False, 14800,
                       "TransE_l2 d=400 neg=200 -adv on a 20M-entity (32 GB) table: HBM-resident variant of configs[1]"),
 }
 METRIC = "edges/sec TransE_l2 d=400 neg=200 at 1/2/4/8 B200 vs ref CPU; HBM GB/s %peak"
