@@ -158,7 +158,9 @@ int carve(kge_context* h, const StepParams& p, StepWs* w, cudaStream_t stream) {
   const bool rescal = p.model == KGE_RESCAL;
   size_t need = 0;
   auto take = [&](size_t floats) { size_t off = need; need += align_up(floats * f); return off; };
-  size_t oNG = take(U * p.D);                 // first: stays at a fixed offset so the zero state survives
+  // NG first, sized for the largest possible node count (2B): rows >= U are never written, rows < U are
+  // re-zeroed by k_upd_nodes, so one fill keeps the whole region zero across steps with varying U
+  size_t oNG = take((U ? (size_t)2 * p.B : 0) * p.D);
   size_t oA = take(BD), oBn = take(ND), oGA = take(BD), oGR = take((size_t)p.B * p.Dr);
   size_t oS = take(BNs), oV = take(BNs);
   size_t opos = take(p.B), ogpos = take(p.B), opn = take(p.B), oa2 = take(p.B), ob2 = take(p.Nn);
@@ -200,7 +202,7 @@ LaunchCtx lctx(kge_context* h, void* stream) { return LaunchCtx{(cudaStream_t)st
 // NG (node-gradient accumulator) has to be zero when k_chain starts.  k_upd_nodes re-zeroes the
 // rows it consumes, so only a fresh / enlarged region needs an explicit fill.
 void ensure_ng_zero(kge_context* h, const StepParams& p, const StepWs& w, const LaunchCtx& c, bool force) {
-  size_t n = (size_t)p.U * p.D;
+  size_t n = (size_t)2 * p.B * p.D;
   if (force || h->ng_dirty || h->ng_ptr != w.NG || h->ng_floats < n) {
     launch_fill_zero(c, w.NG, (long long)n);
     h->ng_ptr = w.NG;
@@ -234,7 +236,8 @@ void launch_rescal_chain(const LaunchCtx&, const StepParams&, const TableView& e
                          const BatchView&, const StepWs&);
 // tcgen05 engine (kge_umma.cu): returns false when the shape is not handled (caller falls back to engine 0)
 bool umma_supported(const StepParams&);
-int umma_score(const LaunchCtx&, const StepParams&, const StepWs&, char* err, size_t errlen);
+int umma_score(const LaunchCtx&, const StepParams&, const StepWs&, bool fuse_loss, const float* edge_w, char* err,
+               size_t errlen);
 int umma_grad(const LaunchCtx&, const StepParams&, const StepWs&, bool side_b, char* err, size_t errlen);
 }  // namespace kge
 
@@ -348,7 +351,7 @@ static bool use_umma(kge_context* h, const StepParams& p) {
 
 static int run_score(kge_context* h, const LaunchCtx& c, const StepParams& p, const StepWs& w) {
   if (use_umma(h, p)) {
-    int rc = umma_score(c, p, w, g_err, sizeof(g_err));
+    int rc = umma_score(c, p, w, false, nullptr, g_err, sizeof(g_err));
     if (rc) return rc;
   } else {
     launch_score(c, p, w);
@@ -464,8 +467,15 @@ KGE_API int kge_forward_backward(kge_handle_t h, const kge_step_cfg_t* cfg, cons
   ensure_ng_zero(h, p, w, c, false);
   if (p.model == KGE_RESCAL) launch_rescal_prep(c, p, ve, vr, b, w);
   else launch_prep(c, p, ve, vr, b, w);
-  if ((rc = run_score(h, c, p, w))) return rc;
-  launch_loss(c, p, w.pos, w.S, b.edge_weight, w, log4 ? log4 : h->dev_log4, true);
+  if (use_umma(h, p) && p.Ns <= 256) {
+    // score GEMM with the loss fused into its epilogue (one accumulator row = one positive's negatives)
+    launch_wbar(c, p, b.edge_weight, w);
+    if ((rc = umma_score(c, p, w, true, b.edge_weight, g_err, sizeof(g_err)))) return rc;
+    launch_reduce_log(c, p, b.edge_weight, w, log4 ? log4 : h->dev_log4, true);
+  } else {
+    if ((rc = run_score(h, c, p, w))) return rc;
+    launch_loss(c, p, w.pos, w.S, b.edge_weight, w, log4 ? log4 : h->dev_log4, true);
+  }
   if (use_umma(h, p)) {
     if ((rc = umma_grad(c, p, w, false, g_err, sizeof(g_err)))) return rc;
     if ((rc = umma_grad(c, p, w, true, g_err, sizeof(g_err)))) return rc;

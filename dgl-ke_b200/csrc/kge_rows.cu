@@ -385,31 +385,47 @@ __global__ void __launch_bounds__(256) k_reduce_log(StepParams p, const float* _
     last = (t == gridDim.x - 1);
   }
   __syncthreads();
-  if (last && threadIdx.x == 0) {
+  if (last) {
     __threadfence();
+    // fixed-order tree over the kRedBlocks partials (one per thread of warp 0..1), deterministic
     float sa = 0.f, sb = 0.f, sr = 0.f;
-    for (int q = 0; q < (int)gridDim.x; ++q) {
-      sa += ((volatile float*)partial)[q * 3 + 0]; sb += ((volatile float*)partial)[q * 3 + 1];
-      sr += ((volatile float*)partial)[q * 3 + 2];
+    if (threadIdx.x < gridDim.x) {
+      sa = ((volatile float*)partial)[threadIdx.x * 3 + 0];
+      sb = ((volatile float*)partial)[threadIdx.x * 3 + 1];
+      sr = ((volatile float*)partial)[threadIdx.x * 3 + 2];
     }
-    float pos_loss = sa / (float)p.B * (wbar ? *wbar : 1.f);
-    float neg_loss = sb / (float)p.B;
-    log4[0] = pos_loss; log4[1] = neg_loss; log4[2] = (neg_loss + pos_loss) / 2.f;
-    log4[3] = p.reg_coef * sr;
-    *ticket = 0u;      // ready for the next step
+    sa = block_sum(sa, sh);
+    sb = block_sum(sb, sh);
+    sr = block_sum(sr, sh);
+    if (threadIdx.x == 0) {
+      float pos_loss = sa / (float)p.B * (wbar ? *wbar : 1.f);
+      float neg_loss = sb / (float)p.B;
+      log4[0] = pos_loss; log4[1] = neg_loss; log4[2] = (neg_loss + pos_loss) / 2.f;
+      log4[3] = p.reg_coef * sr;
+      *ticket = 0u;      // ready for the next step
+    }
   }
 }
 
-void launch_loss(const LaunchCtx& c, const StepParams& p, const float* pos, const float* S, const float* wt,
-                 const StepWs& w, float* log4, bool want_reg) {
+void launch_wbar(const LaunchCtx& c, const StepParams& p, const float* wt, const StepWs& w) {
   if (wt) KGE_LAUNCH(c, k_mean, 1, 1024, 0, wt, p.B, w.wbar);
-  KGE_LAUNCH(c, k_loss, ceil_div(p.B, kWarpsPerBlock), kRowBlock, 0, p, pos, S, wt, w.wbar, w.V, w.gpos, w.rowsum,
-             w.pl, w.nl, w.Vhi, w.Vlo);
-  if (p.model == KGE_TRANSE_L2) KGE_LAUNCH(c, k_colsum, dim3(ceil_div(p.Ns, 32), p.C), 256, 0, p, w.V, w.colsum);
+}
+
+void launch_reduce_log(const LaunchCtx& c, const StepParams& p, const float* wt, const StepWs& w, float* log4,
+                       bool want_reg) {
   const bool reg_on = want_reg && (p.reg_coef > 0.f && p.reg_norm > 0);
   if (log4)
     KGE_LAUNCH(c, k_reduce_log, kRedBlocks, 256, 0, p, w.pl, w.nl, w.regp, reg_on ? (p.B + p.Nn + p.U) : 0,
                wt ? w.wbar : nullptr, w.red_partial, w.red_ticket, log4);
+}
+
+void launch_loss(const LaunchCtx& c, const StepParams& p, const float* pos, const float* S, const float* wt,
+                 const StepWs& w, float* log4, bool want_reg) {
+  launch_wbar(c, p, wt, w);
+  KGE_LAUNCH(c, k_loss, ceil_div(p.B, kWarpsPerBlock), kRowBlock, 0, p, pos, S, wt, w.wbar, w.V, w.gpos, w.rowsum,
+             w.pl, w.nl, w.Vhi, w.Vlo);
+  if (p.model == KGE_TRANSE_L2) KGE_LAUNCH(c, k_colsum, dim3(ceil_div(p.Ns, 32), p.C), 256, 0, p, w.V, w.colsum);
+  launch_reduce_log(c, p, wt, w, log4, want_reg);
 }
 
 // ------------------------------------------------------------------------------------------ a9

@@ -124,6 +124,15 @@ struct GemmArgs {
   const float* a2;       // SCORE l2
   const float* b2;
   const float* colsum;   // GB l2
+  // fused loss epilogue of the score GEMM (k_loss semantics, loss.py:69-98)
+  int fuse_loss, adversarial;
+  float adv_temperature, inv2B;
+  const float* pos;      // [B] positive scores
+  const float* wt;       // [B] edge weights or null
+  const float* wbar;     // [1] mean edge weight (with wt)
+  float *Vhi, *Vlo;      // [B, Ns] backward coefficients, TF32 split
+  float *rowsum, *gpos, *pl, *nl;   // [B]
+  float* colsum_acc;     // [Nn] zeroed by the host; TransE_l2 only
 };
 
 // smem layout per stage: [A_hi | A_lo | B_hi | B_lo], each tile 1024-byte aligned
@@ -254,7 +263,110 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CU
     const bool row_ok = m < Mrows;
     const uint32_t taddr_row = tmem_base + ((uint32_t)(q * 32) << 16);
     // Nt is a multiple of 16; Ns, D are multiples of 8: every 8-column group is entirely valid or entirely padding
-    if (g.mode == G_SCORE) {
+    if (g.mode == G_SCORE && g.fuse_loss) {
+      // ---- score + loss fused: this thread owns row i of the chunk's [Cs x Ns] score tile (single N tile)
+      const long long gi = (long long)c * g.Cs + (row_ok ? m : 0);
+      const bool l2 = g.model == KGE_TRANSE_L2;
+      const float a2v = l2 ? g.a2[gi] : 0.f;
+      const float* b2c = g.b2 + (long long)c * g.Ns;
+      const float w_i = (g.wt && row_ok) ? g.wt[gi] : 1.f;
+      const float T = g.adv_temperature;
+      // score (and distance) of 8 columns starting at j from 8 accumulator values
+      auto scores8 = [&](const float* acc, int j, float* sc, float* d) {
+        if (l2) {
+          float4 bq0 = ld4(b2c + j), bq1 = ld4(b2c + j + 4);
+          const float bb[8] = {bq0.x, bq0.y, bq0.z, bq0.w, bq1.x, bq1.y, bq1.z, bq1.w};
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float sq = fmaf(-2.f, acc[e], bb[e]) + a2v;
+            d[e] = sqrtf(fmaxf(sq, 1e-30f));
+            sc[e] = g.gamma - d[e];
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) { sc[e] = acc[e]; d[e] = 1.f; }
+        }
+      };
+      float mx = -INFINITY, den = 1.f;
+      if (g.adversarial) {
+        for (int col = 0; col < Nt; col += 16) {
+          float v[16];
+          tmem_ld16(taddr_row + col, v);
+#pragma unroll
+          for (int h8 = 0; h8 < 2; ++h8) {
+            const int j = col + h8 * 8;
+            if (j >= g.Ns) continue;
+            float sc[8], d[8];
+            scores8(v + h8 * 8, j, sc, d);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) mx = fmaxf(mx, sc[e] * T);
+          }
+        }
+        float dsum = 0.f;
+        for (int col = 0; col < Nt; col += 16) {
+          float v[16];
+          tmem_ld16(taddr_row + col, v);
+#pragma unroll
+          for (int h8 = 0; h8 < 2; ++h8) {
+            const int j = col + h8 * 8;
+            if (j >= g.Ns) continue;
+            float sc[8], d[8];
+            scores8(v + h8 * 8, j, sc, d);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) dsum += expf(sc[e] * T - mx);
+          }
+        }
+        den = dsum;
+      }
+      const float uni = 1.f / (float)g.Ns;
+      float nls = 0.f, rs = 0.f;
+      for (int col = 0; col < Nt; col += 16) {
+        float v[16];
+        tmem_ld16(taddr_row + col, v);
+#pragma unroll
+        for (int h8 = 0; h8 < 2; ++h8) {
+          const int j = col + h8 * 8;
+          if (j >= g.Ns) continue;                     // uniform across the warp
+          float sc[8], d[8], cf[8];
+          scores8(v + h8 * 8, j, sc, d);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float pij = g.adversarial ? expf(sc[e] * T - mx) / den : uni;
+            nls += pij * (softplusf(sc[e]) * w_i);
+            float gg = pij * sigmoidf(sc[e]) * w_i * g.inv2B;
+            cf[e] = l2 ? gg / d[e] : gg;
+            if (!row_ok) cf[e] = 0.f;
+            rs += cf[e];
+          }
+          if (row_ok) {
+            float4 h0, l0, h1, l1;
+            split_tf32_4(make_float4(cf[0], cf[1], cf[2], cf[3]), h0, l0);
+            split_tf32_4(make_float4(cf[4], cf[5], cf[6], cf[7]), h1, l1);
+            const long long o = gi * g.Ns + j;
+            st4(g.Vhi + o, h0); st4(g.Vhi + o + 4, h1);
+            st4(g.Vlo + o, l0); st4(g.Vlo + o + 4, l1);
+            st4(g.out + o, make_float4(sc[0], sc[1], sc[2], sc[3]));
+            st4(g.out + o + 4, make_float4(sc[4], sc[5], sc[6], sc[7]));
+          }
+          if (l2) {
+            // colsum[c, j] += sum over the 32 rows of this warp (then one atomic per column and warp)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              float t = warp_sum(cf[e]);
+              if (lane == e) atomicAdd(g.colsum_acc + (long long)c * g.Ns + j + e, t);
+            }
+          }
+        }
+      }
+      if (row_ok) {
+        const float ps = g.pos[gi];
+        const float wb = g.wt ? *g.wbar : 1.f;
+        g.pl[gi] = softplusf(-ps);
+        g.nl[gi] = nls;
+        g.gpos[gi] = -sigmoidf(-ps) * wb * g.inv2B;
+        if (l2) g.rowsum[gi] = rs;
+      }
+    } else if (g.mode == G_SCORE) {
       const long long gi = (long long)c * g.Cs + m;
       const bool l2 = g.model == KGE_TRANSE_L2;
       const float a2v = (row_ok && l2) ? g.a2[gi] : 0.f;
@@ -461,7 +573,8 @@ bool umma_supported(const StepParams& p) {
 }
 
 // S = A . Bn^T  (+ TransE_l2 distance epilogue)
-int umma_score(const LaunchCtx& c, const StepParams& p, const StepWs& w, char* err, size_t errlen) {
+int umma_score(const LaunchCtx& c, const StepParams& p, const StepWs& w, bool fuse_loss, const float* edge_w, char* err,
+               size_t errlen) {
   // operands arrive already split: k_prep writes A / Bn as TF32 hi/lo, k_loss writes V hi/lo
   const int Nt_max = p.Ns >= 256 ? 256 : ((p.Ns + 15) & ~15);
   CUtensorMap ah, al, bh, bl;
@@ -474,6 +587,16 @@ int umma_score(const LaunchCtx& c, const StepParams& p, const StepWs& w, char* e
   g.model = p.model; g.gamma = p.gamma; g.reg_coef = p.reg_coef; g.reg_norm = p.reg_norm;
   g.Cs = p.Cs; g.Ns = p.Ns; g.D = p.D;
   g.out = w.S; g.out2 = w.V; g.a2 = w.a2; g.b2 = w.b2; g.colsum = nullptr;
+  g.fuse_loss = (fuse_loss && p.Ns <= 256) ? 1 : 0;
+  if (g.fuse_loss) {
+    g.adversarial = p.adversarial; g.adv_temperature = p.adv_temperature; g.inv2B = 0.5f / (float)p.B;
+    g.pos = w.pos; g.wt = edge_w; g.wbar = w.wbar; g.Vhi = w.Vhi; g.Vlo = w.Vlo;
+    g.rowsum = w.rowsum; g.gpos = w.gpos; g.pl = w.pl; g.nl = w.nl; g.colsum_acc = w.colsum;
+    if (p.model == KGE_TRANSE_L2) {
+      cudaError_t e = cudaMemsetAsync(w.colsum, 0, (size_t)p.Nn * sizeof(float), c.stream);
+      if (e != cudaSuccess) { snprintf(err, errlen, "cudaMemsetAsync(colsum): %s", cudaGetErrorString(e)); return KGE_ERR_CUDA; }
+    }
+  }
   return launch_gemm<false, false>(c, ah, al, bh, bl, g, (p.Ns + 255) / 256, Nt_max, err, errlen);
 }
 
