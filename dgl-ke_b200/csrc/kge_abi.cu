@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdarg>
 #include <cstring>
+#include <cstdlib>
 #include <new>
 #include <cuda.h>
 #include "kge_common.cuh"
@@ -45,6 +46,7 @@ struct kge_context {
   long long launches = 0;
   int engine = -1;
   int rel_deferred = 0;
+  int fuse_loss = 0;       // score epilogue computes the loss (KGE_B200_FUSE_LOSS=1): slower with 4 epilogue warps, kept for study
   // device arena (grown on demand, never inside a graph capture)
   char* arena = nullptr;
   size_t arena_bytes = 0;
@@ -168,8 +170,11 @@ int carve(kge_context* h, const StepParams& p, StepWs* w, cudaStream_t stream) {
   size_t oreg = take((size_t)p.B + p.Nn + U), owb = take(4), ogsr = take(p.B);
   size_t oMt = rescal ? take(BD) : 0;
   const bool um = (h->engine != 0) && umma_supported(p);
-  size_t oAh = um ? take(BD) : 0, oAl = um ? take(BD) : 0, oBh = um ? take(ND) : 0, oBl = um ? take(ND) : 0;
-  size_t oVh = um ? take(BNs) : 0, oVl = um ? take(BNs) : 0;
+  // slab layout pads the blocked dimension to a multiple of 32 (+ one slab of slack for box overruns)
+  const size_t sA = (size_t)p.B * slab_blocks(p.D) * 32 + 8192, sB = (size_t)p.Nn * slab_blocks(p.D) * 32 + 8192;
+  const size_t sV = (size_t)p.B * slab_blocks(p.Ns) * 32 + 8192;
+  size_t oAh = um ? take(sA) : 0, oAl = um ? take(sA) : 0, oBh = um ? take(sB) : 0, oBl = um ? take(sB) : 0;
+  size_t oVh = um ? take(sV) : 0, oVl = um ? take(sV) : 0;
   if (need > h->arena_bytes) {
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(stream, &cs);
@@ -264,6 +269,7 @@ KGE_API int kge_create(int device, kge_handle_t* out) {
   if (!h) return fail(KGE_ERR_NOMEM, "out of host memory");
   h->device = device;
   h->num_sms = prop.multiProcessorCount;
+  { const char* e = getenv("KGE_B200_FUSE_LOSS"); h->fuse_loss = (e && e[0] == '1') ? 1 : 0; }
   DeviceGuard g(device);
   if (cudaMalloc(&h->dev_log4, 4 * sizeof(float)) != cudaSuccess) { delete h; return fail(KGE_ERR_NOMEM, "cudaMalloc failed"); }
   if (cudaMalloc(&h->red_partial, 256 * sizeof(float)) != cudaSuccess || cudaMemset(h->red_partial, 0, 256 * sizeof(float)) != cudaSuccess) {
@@ -467,7 +473,7 @@ KGE_API int kge_forward_backward(kge_handle_t h, const kge_step_cfg_t* cfg, cons
   ensure_ng_zero(h, p, w, c, false);
   if (p.model == KGE_RESCAL) launch_rescal_prep(c, p, ve, vr, b, w);
   else launch_prep(c, p, ve, vr, b, w);
-  if (use_umma(h, p) && p.Ns <= 256) {
+  if (h->fuse_loss && use_umma(h, p) && p.Ns <= 256) {
     // score GEMM with the loss fused into its epilogue (one accumulator row = one positive's negatives)
     launch_wbar(c, p, b.edge_weight, w);
     if ((rc = umma_score(c, p, w, true, b.edge_weight, g_err, sizeof(g_err)))) return rc;

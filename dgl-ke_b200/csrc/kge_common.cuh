@@ -76,9 +76,9 @@ struct StepWs {
   unsigned int* red_ticket;   // [1] completion ticket of k_reduce_log (zero between launches)
   float* Mt;       // [B, D]   RESCAL: M_r t  (tail mode needs it next to A = M_r h)
   // tcgen05 engine: TF32 hi/lo splits of the contraction operands
-  float *Ahi, *Alo;   // [B, D]
-  float *Bhi, *Blo;   // [Nn, D]
-  float *Vhi, *Vlo;   // [B, Ns]
+  float *Ahi, *Alo;   // [C][D/32][Cs][32]   (slab layout, see slab_off)
+  float *Bhi, *Blo;   // [C][D/32][Ns][32]
+  float *Vhi, *Vlo;   // [C][Ns/32][Cs][32]
 };
 
 struct BatchView {
@@ -160,17 +160,28 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
 __device__ __forceinline__ void split_tf32_4(float4 v, float4& h, float4& l) {
   split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
 }
-// destination of an operand row: plain fp32 and/or its TF32 hi/lo split (tcgen05 engine)
+// tcgen05 operand layout ("k-blocked slabs"): a per-chunk matrix X[c][row][col] (row < R, col < Ncol) is stored as
+//   X[c][col / 32][row][col % 32]
+// so that every TMA box the GEMMs load -- {32 cols, n rows} of one (chunk, 32-column block) -- is ONE contiguous
+// n*128-byte region of HBM (the row-major layout made each box 128..208 scattered 128-byte lines).
+__host__ __device__ inline int slab_blocks(int ncol) { return (ncol + 31) >> 5; }
+__device__ __forceinline__ long long slab_off(long long chunk, int nblk, int R, int row, int col) {
+  return ((chunk * nblk + (col >> 5)) * (long long)R + row) * 32 + (col & 31);
+}
+// destination of an operand row: plain fp32 row-major and/or its TF32 hi/lo split in slab layout
 struct RowOut {
-  float* f32;
-  float* hi;
+  float* f32;        // row-major row pointer or null
+  float* hi;         // slab-layout base pointers or null
   float* lo;
+  long long chunk;
+  int nblk, R, row;
 };
-__device__ __forceinline__ void row_store4(const RowOut& o, int off, float4 v) {
-  if (o.f32) *reinterpret_cast<float4*>(o.f32 + off) = v;
+__device__ __forceinline__ void row_store4(const RowOut& o, int col, float4 v) {
+  if (o.f32) *reinterpret_cast<float4*>(o.f32 + col) = v;
   if (o.hi) {
     float4 h, l;
     split_tf32_4(v, h, l);
+    const long long off = slab_off(o.chunk, o.nblk, o.R, o.row, col);
     *reinterpret_cast<float4*>(o.hi + off) = h;
     *reinterpret_cast<float4*>(o.lo + off) = l;
   }

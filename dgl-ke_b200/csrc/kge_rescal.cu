@@ -60,7 +60,12 @@ __global__ void __launch_bounds__(kBlock) k_rescal_fwd(StepParams p, const float
     pos += sh[k] * sMt[k];
     if (want_a) {
       const float av = p.neg_head ? sMt[k] : sMh[k];
-      if (w.Ahi) { float hh, ll; split_tf32(av, hh, ll); w.Ahi[i * (long long)D + k] = hh; w.Alo[i * (long long)D + k] = ll; }
+      if (w.Ahi) {
+        float hh, ll;
+        split_tf32(av, hh, ll);
+        const long long o = slab_off(i / p.Cs, slab_blocks(D), p.Cs, (int)(i % p.Cs), k);
+        w.Ahi[o] = hh; w.Alo[o] = ll;
+      }
       else w.A[i * (long long)D + k] = av;
     }
     if (!dense) w.Mt[i * (long long)D + k] = sMt[k];

@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(kRowBlock) k_prep(StepParams p, TableView ent,
     float pos, a2, reg, nrm;
     const long long ro = job * (long long)p.D;
     // tcgen05 engine: A is only consumed as hi/lo operands; fp32 tiles: plain fp32
-    const RowOut ao{w.Ahi ? nullptr : w.A + ro, w.Ahi ? w.Ahi + ro : nullptr, w.Ahi ? w.Alo + ro : nullptr};
+    const RowOut ao{w.Ahi ? nullptr : w.A + ro, w.Ahi, w.Alo, job / p.Cs, slab_blocks(p.D), p.Cs, (int)(job % p.Cs)};
     edge_forward<MODEL>(p, h, r, t, ao, lane, pos, a2, reg, nrm, true);
     if (lane == 0) {
       w.pos[job] = pos;
@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(kRowBlock) k_prep(StepParams p, TableView ent,
   if (job < p.Nn) {
     const float* src = row_ptr(ent, b.neg_ids[job]);
     const long long ro = job * (long long)p.D;
-    const RowOut bo{w.Bn + ro, w.Bhi ? w.Bhi + ro : nullptr, w.Bhi ? w.Blo + ro : nullptr};
+    const RowOut bo{w.Bn + ro, w.Bhi, w.Blo, job / p.Ns, slab_blocks(p.D), p.Ns, (int)(job % p.Ns)};
     float b2 = 0.f, reg = 0.f;
     for (int v = lane; v < (p.D >> 2); v += kWarp) {
       float4 x = ld4_stream(src + 4 * v);
@@ -216,8 +216,8 @@ __global__ void __launch_bounds__(kRowBlock) k_prep_dense(StepParams p, const fl
     // kge_score_neg passes the negatives in place of the corrupted side: only the kept side is read
     if (!want_pos) { if (p.neg_head) hrow = trow; else trow = hrow; }
     const long long ro = job * (long long)p.D;
-    const RowOut ao{(want_a && !w.Ahi) ? w.A + ro : nullptr, (want_a && w.Ahi) ? w.Ahi + ro : nullptr,
-                    (want_a && w.Ahi) ? w.Alo + ro : nullptr};
+    const RowOut ao{(want_a && !w.Ahi) ? w.A + ro : nullptr, want_a ? w.Ahi : nullptr, want_a ? w.Alo : nullptr,
+                    job / p.Cs, slab_blocks(p.D), p.Cs, (int)(job % p.Cs)};
     edge_forward<MODEL>(p, hrow, relr + job * (long long)p.Dr, trow, ao, lane, pos, a2, reg, nrm, want_a);
     if (lane == 0) {
       if (want_pos) w.pos[job] = pos;
@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(kRowBlock) k_prep_dense(StepParams p, const fl
   if (job < p.Nn && negrows != nullptr) {
     const float* src = negrows + job * (long long)p.D;
     const long long ro = job * (long long)p.D;
-    const RowOut bo{nullptr, w.Bhi ? w.Bhi + ro : nullptr, w.Bhi ? w.Blo + ro : nullptr};
+    const RowOut bo{nullptr, w.Bhi, w.Blo, job / p.Ns, slab_blocks(p.D), p.Ns, (int)(job % p.Ns)};
     float b2 = 0.f;
     for (int v = lane; v < (p.D >> 2); v += kWarp) {
       float4 x = ld4(src + 4 * v);
@@ -308,7 +308,12 @@ __global__ void __launch_bounds__(kRowBlock) k_loss(StepParams p, const float* _
     float coef = g;
     if (p.model == KGE_TRANSE_L2) { float dist = v[j]; coef = g / dist; rs += coef; }   // v[j] = |a-b| from k_score
     v[j] = coef;
-    if (Vhi) { float hh, ll; split_tf32(coef, hh, ll); Vhi[i * (long long)p.Ns + j] = hh; Vlo[i * (long long)p.Ns + j] = ll; }
+    if (Vhi) {
+      float hh, ll;
+      split_tf32(coef, hh, ll);
+      const long long o = slab_off(i / p.Cs, slab_blocks(p.Ns), p.Cs, (int)(i % p.Cs), j);
+      Vhi[o] = hh; Vlo[o] = ll;
+    }
   }
   nls = warp_sum(nls);
   rs = warp_sum(rs);

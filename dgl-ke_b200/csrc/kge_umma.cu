@@ -114,6 +114,8 @@ struct GemmArgs {
   int rowsB_per_chunk;   // N-dimension rows per chunk when B is K-major (Ns for SCORE)
   int krows_per_chunk;   // K extent (D for SCORE, Ns for GA, Cs for GB)
   int b_box_rows;        // rows of the TMA box of a K-major B operand (tile N of the tensor map)
+  int a_nblk, a_R;       // slab geometry of the A operand matrix: 32-column blocks per chunk, rows per chunk
+  int b_nblk, b_R;       // same for the B operand matrix
   int model;
   float gamma, reg_coef;
   int reg_norm;
@@ -136,7 +138,7 @@ struct GemmArgs {
 };
 
 // smem layout per stage: [A_hi | A_lo | B_hi | B_lo], each tile 1024-byte aligned
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, int MODE, bool FUSE>
 __global__ void __launch_bounds__(kThreads, 1)
 k_umma_gemm(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
             const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, GemmArgs g) {
@@ -148,7 +150,7 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CU
   const int c = blockIdx.z;
   const int m0 = blockIdx.y * kTileM;                 // row offset inside the chunk (M dimension)
   const int n0 = blockIdx.x * 256;                    // column offset (N dimension)
-  const int Nleft = (g.mode == G_SCORE ? g.Ns : g.D) - n0;
+  const int Nleft = (MODE == G_SCORE ? g.Ns : g.D) - n0;
   const int Nt = Nleft >= 256 ? 256 : ((Nleft + 15) & ~15);      // UMMA N (multiple of 16)
   const int nblk = (Nt + 31) >> 5;                                // 32-wide MN blocks of B (MN-major)
   const int K = g.krows_per_chunk;
@@ -177,10 +179,6 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CU
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      // global coordinates
-      const int a_row0 = c * g.rowsA_per_chunk + m0;       // K-major A: row (M) coordinate
-      const int a_col0 = c * 0;                            // (unused)
-      (void)a_col0;
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % kStages;
         const uint32_t ph = (kb / kStages) & 1;
@@ -191,30 +189,30 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CU
         const int k0 = kb * kBlockK;
         uint32_t tx = 2 * kABytes + 2 * bBytes;
         mbar_expect_tx(&full_bar[s], tx);
+        // slab layout: row coordinate of (chunk c, 32-column block blk, row r) = (c * nblk + blk) * R + r; x = 0
         if (!A_MN) {
-          // A[rows = M][cols = K]: box {32 k, 128 rows}
-          tma_load_2d(sAh, &tmAh, &full_bar[s], k0, a_row0);
-          tma_load_2d(sAl, &tmAl, &full_bar[s], k0, a_row0);
+          // A K-major: column block = k-block kb, rows = M: one contiguous 16 KB box {32, 128 rows}
+          const int ya = (c * g.a_nblk + kb) * g.a_R + m0;
+          tma_load_2d(sAh, &tmAh, &full_bar[s], 0, ya);
+          tma_load_2d(sAl, &tmAl, &full_bar[s], 0, ya);
         } else {
-          // A stored [rows = K][cols = M] (V rows i = K, cols j = M): 4 boxes {32 m, 32 k}
-          const int krow0 = c * g.krows_per_chunk + k0;
+          // A MN-major (stored [K rows][M cols]): column block = M block, rows = K: 4 contiguous boxes {32, 32 rows}
 #pragma unroll
           for (int b = 0; b < kTileM / 32; ++b) {
-            tma_load_2d(sAh + b * 4096, &tmAh, &full_bar[s], m0 + b * 32, krow0);
-            tma_load_2d(sAl + b * 4096, &tmAl, &full_bar[s], m0 + b * 32, krow0);
+            const int ya = (c * g.a_nblk + (m0 >> 5) + b) * g.a_R + k0;
+            tma_load_2d(sAh + b * 4096, &tmAh, &full_bar[s], 0, ya);
+            tma_load_2d(sAl + b * 4096, &tmAl, &full_bar[s], 0, ya);
           }
         }
         if (!B_MN) {
-          // B[rows = N][cols = K]: box {32 k, Nt rows}
-          const int b_row0 = c * g.rowsB_per_chunk + n0;
-          tma_load_2d(sBh, &tmBh, &full_bar[s], k0, b_row0);
-          tma_load_2d(sBl, &tmBl, &full_bar[s], k0, b_row0);
+          const int yb = (c * g.b_nblk + kb) * g.b_R + n0;
+          tma_load_2d(sBh, &tmBh, &full_bar[s], 0, yb);
+          tma_load_2d(sBl, &tmBl, &full_bar[s], 0, yb);
         } else {
-          // B stored [rows = K][cols = N]: nblk boxes {32 n, 32 k}
-          const int krow0 = c * g.krows_per_chunk + k0;
           for (int b = 0; b < nblk; ++b) {
-            tma_load_2d(sBh + b * 4096, &tmBh, &full_bar[s], n0 + b * 32, krow0);
-            tma_load_2d(sBl + b * 4096, &tmBl, &full_bar[s], n0 + b * 32, krow0);
+            const int yb = (c * g.b_nblk + (n0 >> 5) + b) * g.b_R + k0;
+            tma_load_2d(sBh + b * 4096, &tmBh, &full_bar[s], 0, yb);
+            tma_load_2d(sBl + b * 4096, &tmBl, &full_bar[s], 0, yb);
           }
         }
       }
@@ -263,7 +261,7 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CU
     const bool row_ok = m < Mrows;
     const uint32_t taddr_row = tmem_base + ((uint32_t)(q * 32) << 16);
     // Nt is a multiple of 16; Ns, D are multiples of 8: every 8-column group is entirely valid or entirely padding
-    if (g.mode == G_SCORE && g.fuse_loss) {
+    if (MODE == G_SCORE && FUSE) {
       // ---- score + loss fused: this thread owns row i of the chunk's [Cs x Ns] score tile (single N tile)
       const long long gi = (long long)c * g.Cs + (row_ok ? m : 0);
       const bool l2 = g.model == KGE_TRANSE_L2;
@@ -343,8 +341,9 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CU
             split_tf32_4(make_float4(cf[0], cf[1], cf[2], cf[3]), h0, l0);
             split_tf32_4(make_float4(cf[4], cf[5], cf[6], cf[7]), h1, l1);
             const long long o = gi * g.Ns + j;
-            st4(g.Vhi + o, h0); st4(g.Vhi + o + 4, h1);
-            st4(g.Vlo + o, l0); st4(g.Vlo + o + 4, l1);
+            const long long ov = slab_off(c, slab_blocks(g.Ns), g.Cs, m, j);
+            st4(g.Vhi + ov, h0); st4(g.Vhi + ov + 4, h1);
+            st4(g.Vlo + ov, l0); st4(g.Vlo + ov + 4, l1);
             st4(g.out + o, make_float4(sc[0], sc[1], sc[2], sc[3]));
             st4(g.out + o + 4, make_float4(sc[4], sc[5], sc[6], sc[7]));
           }
@@ -366,7 +365,7 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CU
         g.gpos[gi] = -sigmoidf(-ps) * wb * g.inv2B;
         if (l2) g.rowsum[gi] = rs;
       }
-    } else if (g.mode == G_SCORE) {
+    } else if (MODE == G_SCORE) {
       const long long gi = (long long)c * g.Cs + m;
       const bool l2 = g.model == KGE_TRANSE_L2;
       const float a2v = (row_ok && l2) ? g.a2[gi] : 0.f;
@@ -401,7 +400,7 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CU
           st4(g.out + gi * g.Ns + j + 4, make_float4(sc[4], sc[5], sc[6], sc[7]));
         }
       }
-    } else if (g.mode == G_GA) {
+    } else if (MODE == G_GA) {
       float* row = g.out + ((long long)c * g.Cs + m) * g.D;
       for (int col = 0; col < Nt; col += 16) {
         float v[16];
@@ -539,19 +538,20 @@ size_t smem_bytes_for(int Nt, bool b_mn) {
   return (size_t)kStages * (2 * kTileM * 128 + 2 * b) + 1024;
 }
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, int MODE, bool FUSE>
 int launch_gemm(const LaunchCtx& c, const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh,
                 const CUtensorMap& bl, const GemmArgs& g, int ntiles_n, int Nt_max, char* err, size_t errlen) {
   size_t smem = smem_bytes_for(Nt_max, B_MN);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_umma_gemm<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(k_umma_gemm<A_MN, B_MN, MODE, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) { snprintf(err, errlen, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return KGE_ERR_CUDA; }
     attr_set = true;
   }
   dim3 grid(ntiles_n, (g.rowsA_per_chunk + kTileM - 1) / kTileM, g.C);
-  const char* nm = g.mode == G_SCORE ? "k_umma_gemm<score S=A.Bn^T>" : (g.mode == G_GA ? "k_umma_gemm<grad_a GA=V.Bn>" : "k_umma_gemm<grad_b GB=V^T.A>");
-  KGE_LAUNCH_NAMED(c, nm, (k_umma_gemm<A_MN, B_MN>), grid, kThreads, smem, ah, al, bh, bl, g);
+  const char* nm = MODE == G_SCORE ? (FUSE ? "k_umma_gemm<score+loss S=A.Bn^T>" : "k_umma_gemm<score S=A.Bn^T>")
+                                   : (MODE == G_GA ? "k_umma_gemm<grad_a GA=V.Bn>" : "k_umma_gemm<grad_b GB=V^T.A>");
+  KGE_LAUNCH_NAMED(c, nm, (k_umma_gemm<A_MN, B_MN, MODE, FUSE>), grid, kThreads, smem, ah, al, bh, bl, g);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { snprintf(err, errlen, "umma launch: %s", cudaGetErrorString(e)); return KGE_ERR_CUDA; }
   return KGE_OK;
@@ -578,12 +578,14 @@ int umma_score(const LaunchCtx& c, const StepParams& p, const StepWs& w, bool fu
   // operands arrive already split: k_prep writes A / Bn as TF32 hi/lo, k_loss writes V hi/lo
   const int Nt_max = p.Ns >= 256 ? 256 : ((p.Ns + 15) & ~15);
   CUtensorMap ah, al, bh, bl;
-  if (!make_map(&ah, w.Ahi, p.B, p.D, kTileM, err, errlen) || !make_map(&al, w.Alo, p.B, p.D, kTileM, err, errlen) ||
-      !make_map(&bh, w.Bhi, p.Nn, p.D, Nt_max, err, errlen) || !make_map(&bl, w.Blo, p.Nn, p.D, Nt_max, err, errlen))
+  const long long rowsA = p.B * (long long)slab_blocks(p.D), rowsB = p.Nn * (long long)slab_blocks(p.D);
+  if (!make_map(&ah, w.Ahi, rowsA, 32, kTileM, err, errlen) || !make_map(&al, w.Alo, rowsA, 32, kTileM, err, errlen) ||
+      !make_map(&bh, w.Bhi, rowsB, 32, Nt_max, err, errlen) || !make_map(&bl, w.Blo, rowsB, 32, Nt_max, err, errlen))
     return KGE_ERR_CUDA;
   GemmArgs g{};
   g.mode = G_SCORE; g.C = p.C; g.rowsA_per_chunk = p.Cs; g.rowsB_per_chunk = p.Ns; g.krows_per_chunk = p.D;
   g.b_box_rows = Nt_max;
+  g.a_nblk = slab_blocks(p.D); g.a_R = p.Cs; g.b_nblk = slab_blocks(p.D); g.b_R = p.Ns;
   g.model = p.model; g.gamma = p.gamma; g.reg_coef = p.reg_coef; g.reg_norm = p.reg_norm;
   g.Cs = p.Cs; g.Ns = p.Ns; g.D = p.D;
   g.out = w.S; g.out2 = w.V; g.a2 = w.a2; g.b2 = w.b2; g.colsum = nullptr;
@@ -597,7 +599,8 @@ int umma_score(const LaunchCtx& c, const StepParams& p, const StepWs& w, bool fu
       if (e != cudaSuccess) { snprintf(err, errlen, "cudaMemsetAsync(colsum): %s", cudaGetErrorString(e)); return KGE_ERR_CUDA; }
     }
   }
-  return launch_gemm<false, false>(c, ah, al, bh, bl, g, (p.Ns + 255) / 256, Nt_max, err, errlen);
+  if (g.fuse_loss) return launch_gemm<false, false, G_SCORE, true>(c, ah, al, bh, bl, g, (p.Ns + 255) / 256, Nt_max, err, errlen);
+  return launch_gemm<false, false, G_SCORE, false>(c, ah, al, bh, bl, g, (p.Ns + 255) / 256, Nt_max, err, errlen);
 }
 
 // side_b == false: GA = V . Bn ; side_b == true: G_neg = V^T . A (+ epilogue), in place over Bn
@@ -609,18 +612,22 @@ int umma_grad(const LaunchCtx& c, const StepParams& p, const StepWs& w, bool sid
   g.Cs = p.Cs; g.Ns = p.Ns; g.D = p.D; g.colsum = w.colsum;
   if (!side_b) {
     // A operand: V [B, Ns] K-major (K = j); B operand: Bn hi/lo [Nn, D] MN-major (rows = K = j, cols = N = k)
-    if (!make_map(&ah, w.Vhi, p.B, p.Ns, kTileM, err, errlen) || !make_map(&al, w.Vlo, p.B, p.Ns, kTileM, err, errlen) ||
-        !make_map(&bh, w.Bhi, p.Nn, p.D, 32, err, errlen, true) || !make_map(&bl, w.Blo, p.Nn, p.D, 32, err, errlen, true))
+    const long long rowsV = p.B * (long long)slab_blocks(p.Ns), rowsB = p.Nn * (long long)slab_blocks(p.D);
+    if (!make_map(&ah, w.Vhi, rowsV, 32, kTileM, err, errlen) || !make_map(&al, w.Vlo, rowsV, 32, kTileM, err, errlen) ||
+        !make_map(&bh, w.Bhi, rowsB, 32, 32, err, errlen, true) || !make_map(&bl, w.Blo, rowsB, 32, 32, err, errlen, true))
       return KGE_ERR_CUDA;
+    g.a_nblk = slab_blocks(p.Ns); g.a_R = p.Cs; g.b_nblk = slab_blocks(p.D); g.b_R = p.Ns;
     g.mode = G_GA; g.rowsA_per_chunk = p.Cs; g.rowsB_per_chunk = 0; g.krows_per_chunk = p.Ns; g.out = w.GA;
-    return launch_gemm<false, true>(c, ah, al, bh, bl, g, (p.D + 255) / 256, Nt_max, err, errlen);
+    return launch_gemm<false, true, G_GA, false>(c, ah, al, bh, bl, g, (p.D + 255) / 256, Nt_max, err, errlen);
   }
   // A operand: V^T: stored V [B, Ns] = [rows = K = i][cols = M = j] MN-major; B operand: A hi/lo [B, D] MN-major
-  if (!make_map(&ah, w.Vhi, p.B, p.Ns, 32, err, errlen, true) || !make_map(&al, w.Vlo, p.B, p.Ns, 32, err, errlen, true) ||
-      !make_map(&bh, w.Ahi, p.B, p.D, 32, err, errlen, true) || !make_map(&bl, w.Alo, p.B, p.D, 32, err, errlen, true))
+  const long long rowsV = p.B * (long long)slab_blocks(p.Ns), rowsA = p.B * (long long)slab_blocks(p.D);
+  if (!make_map(&ah, w.Vhi, rowsV, 32, 32, err, errlen, true) || !make_map(&al, w.Vlo, rowsV, 32, 32, err, errlen, true) ||
+      !make_map(&bh, w.Ahi, rowsA, 32, 32, err, errlen, true) || !make_map(&bl, w.Alo, rowsA, 32, 32, err, errlen, true))
     return KGE_ERR_CUDA;
+  g.a_nblk = slab_blocks(p.Ns); g.a_R = p.Cs; g.b_nblk = slab_blocks(p.D); g.b_R = p.Cs;
   g.mode = G_GB; g.rowsA_per_chunk = p.Ns; g.rowsB_per_chunk = 0; g.krows_per_chunk = p.Cs; g.out = w.Bn;
-  return launch_gemm<true, true>(c, ah, al, bh, bl, g, (p.D + 255) / 256, Nt_max, err, errlen);
+  return launch_gemm<true, true, G_GB, false>(c, ah, al, bh, bl, g, (p.D + 255) / 256, Nt_max, err, errlen);
 }
 
 }  // namespace kge
