@@ -13,6 +13,7 @@
 // warps 2-5 = epilogue (tcgen05.ld 32x32b: one accumulator row per thread).
 #include <cuda.h>
 #include <cstdio>
+#include <cstdlib>
 #include "kge_common.cuh"
 
 namespace kge {
@@ -23,11 +24,16 @@ constexpr int kBlockK = 32;                 // fp32 elements per k-block = one 1
 constexpr int kUmmaK = 8;                   // tf32: 32 bytes per MMA k-step
 constexpr int kTileM = 128;
 constexpr int kStages = 2;
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;                // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
 constexpr int kTmemCols = 256;
 
 enum { G_SCORE = 0, G_GA = 1, G_GB = 2 };
 
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -135,6 +141,7 @@ struct GemmArgs {
   float *Vhi, *Vlo;      // [B, Ns] backward coefficients, TF32 split
   float *rowsum, *gpos, *pl, *nl;   // [B]
   float* colsum_acc;     // [Nn] zeroed by the host; TransE_l2 only
+  unsigned long long* dbg;   // optional per-CTA timestamps (KGE_B200_UMMA_TIMING=1): start, first full, mainloop end, end
 };
 
 // smem layout per stage: [A_hi | A_lo | B_hi | B_lo], each tile 1024-byte aligned
@@ -145,7 +152,9 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CU
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages], tmem_full_bar;
   __shared__ uint32_t tmem_base_slot;
+  __shared__ __align__(16) float b2s[256];     // |b_j|^2 of this tile's negatives (score epilogue)
 
+  const unsigned long long t_entry = gtime();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c = blockIdx.z;
   const int m0 = blockIdx.y * kTileM;                 // row offset inside the chunk (M dimension)
@@ -175,6 +184,8 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CU
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_slot;
+  const int cta_lin = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  if (g.dbg && threadIdx.x == 0) { g.dbg[cta_lin * 6 + 4] = t_entry; g.dbg[cta_lin * 6 + 0] = gtime(); }
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -226,6 +237,7 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CU
         const int s = kb % kStages;
         const uint32_t ph = (kb / kStages) & 1;
         mbar_wait(&full_bar[s], ph);
+        if (g.dbg && kb == 0) g.dbg[cta_lin * 6 + 1] = gtime();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t st = smem_u32(smem + (size_t)s * stageBytes);
         const uint32_t sAh = st, sAl = st + kABytes, sBh = st + 2 * kABytes, sBl = sBh + bBytesAligned;
@@ -252,9 +264,22 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CU
     }
   } else {
     // ===================== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====================
+    if (MODE == G_SCORE && g.model == KGE_TRANSE_L2) {
+      // stage the tile's |b_j|^2 once (every row of the tile needs all of them) while the mainloop runs
+      const int et = threadIdx.x - 64;                 // 0..255
+      if (et < 256) b2s[et] = (n0 + et < g.Ns) ? g.b2[(long long)c * g.Ns + n0 + et] : 0.f;
+      asm volatile("bar.sync 1, 256;" ::: "memory");   // the 8 epilogue warps only
+    }
     mbar_wait(&tmem_full_bar, 0);
+    if (g.dbg && threadIdx.x == 64) g.dbg[cta_lin * 6 + 2] = gtime();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int q = warp & 3;
+    // two warps share a TMEM lane quarter and split the tile's columns (the fused-loss variant needs whole rows:
+    // there only the first warp of each quarter works)
+    const int ehalf = (warp - 2) >> 2;
+    const int Nt_half = FUSE ? Nt : (((Nt >> 1) + 15) & ~15);
+    const int col_begin = ehalf ? Nt_half : 0;
+    const int col_end = FUSE ? (ehalf ? 0 : Nt) : (ehalf ? Nt : Nt_half);
     const int row_in_tile = q * 32 + lane;                 // accumulator row (M index) owned by this thread
     const int m = m0 + row_in_tile;
     const int Mrows = g.rowsA_per_chunk;
@@ -262,17 +287,17 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CU
     const uint32_t taddr_row = tmem_base + ((uint32_t)(q * 32) << 16);
     // Nt is a multiple of 16; Ns, D are multiples of 8: every 8-column group is entirely valid or entirely padding
     if (MODE == G_SCORE && FUSE) {
+      if (ehalf == 0) {
       // ---- score + loss fused: this thread owns row i of the chunk's [Cs x Ns] score tile (single N tile)
       const long long gi = (long long)c * g.Cs + (row_ok ? m : 0);
       const bool l2 = g.model == KGE_TRANSE_L2;
       const float a2v = l2 ? g.a2[gi] : 0.f;
-      const float* b2c = g.b2 + (long long)c * g.Ns;
       const float w_i = (g.wt && row_ok) ? g.wt[gi] : 1.f;
       const float T = g.adv_temperature;
       // score (and distance) of 8 columns starting at j from 8 accumulator values
       auto scores8 = [&](const float* acc, int j, float* sc, float* d) {
         if (l2) {
-          float4 bq0 = ld4(b2c + j), bq1 = ld4(b2c + j + 4);
+          float4 bq0 = *reinterpret_cast<const float4*>(&b2s[j]), bq1 = *reinterpret_cast<const float4*>(&b2s[j + 4]);
           const float bb[8] = {bq0.x, bq0.y, bq0.z, bq0.w, bq1.x, bq1.y, bq1.z, bq1.w};
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
@@ -365,12 +390,12 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CU
         g.gpos[gi] = -sigmoidf(-ps) * wb * g.inv2B;
         if (l2) g.rowsum[gi] = rs;
       }
+      }
     } else if (MODE == G_SCORE) {
       const long long gi = (long long)c * g.Cs + m;
       const bool l2 = g.model == KGE_TRANSE_L2;
       const float a2v = (row_ok && l2) ? g.a2[gi] : 0.f;
-      const float* b2c = g.b2 + (long long)c * g.Ns;
-      for (int col = 0; col < Nt; col += 16) {
+      for (int col = col_begin; col < col_end; col += 16) {
         float v[16];
         tmem_ld16(taddr_row + col, v);
         if (!row_ok) continue;
@@ -381,7 +406,7 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CU
           float sc[8];
           if (l2) {
             // batched_l2_dist (score_fun.py:26-34): (|b|^2 - 2 a.b) + |a|^2, clamp, sqrt
-            float4 bq0 = ld4(b2c + j), bq1 = ld4(b2c + j + 4);
+            float4 bq0 = *reinterpret_cast<const float4*>(&b2s[j - n0]), bq1 = *reinterpret_cast<const float4*>(&b2s[j - n0 + 4]);
             const float bb[8] = {bq0.x, bq0.y, bq0.z, bq0.w, bq1.x, bq1.y, bq1.z, bq1.w};
             float d[8];
 #pragma unroll
@@ -402,7 +427,7 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CU
       }
     } else if (MODE == G_GA) {
       float* row = g.out + ((long long)c * g.Cs + m) * g.D;
-      for (int col = 0; col < Nt; col += 16) {
+      for (int col = col_begin; col < col_end; col += 16) {
         float v[16];
         tmem_ld16(taddr_row + col, v);
         if (!row_ok) continue;
@@ -418,34 +443,51 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CU
       float* row = g.out + ((long long)c * g.Ns + m) * g.D;
       const bool l2 = g.model == KGE_TRANSE_L2;
       const float cs = (row_ok && l2) ? g.colsum[(long long)c * g.Ns + m] : 0.f;
-      for (int col = 0; col < Nt; col += 16) {
+      // the row's own values b (for -colsum*b and the regulariser) are prefetched one 16-column chunk ahead so
+      // that their global-memory latency overlaps the TMEM load + math + stores of the current chunk
+      float4 bcur[4], bnxt[4];
+      auto load_b = [&](int col, float4* dst) {
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const int k = n0 + col + q4 * 4;
+          dst[q4] = (row_ok && col < col_end && k < g.D) ? ld4(row + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      };
+      load_b(col_begin, bcur);
+      for (int col = col_begin; col < col_end; col += 16) {
+        load_b(col + 16, bnxt);
         float v[16];
         tmem_ld16(taddr_row + col, v);
-        if (!row_ok) continue;
+        if (row_ok) {
 #pragma unroll
-        for (int h8 = 0; h8 < 2; ++h8) {
-          const int k = n0 + col + h8 * 8;
-          if (k >= g.D) continue;
-          float4 b0 = ld4(row + k), b1 = ld4(row + k + 4);
-          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-          float o[8];
+          for (int h8 = 0; h8 < 2; ++h8) {
+            const int k = n0 + col + h8 * 8;
+            if (k >= g.D) continue;
+            const float4 b0 = bcur[h8 * 2], b1 = bcur[h8 * 2 + 1];
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            float o[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            float gv = v[h8 * 8 + e];
-            if (l2) gv = fmaf(-cs, bb[e], gv);                 // sum_i V_ij a_i - (sum_i V_ij) b_j
-            o[e] = gv + reg_grad(bb[e], g.reg_norm, g.reg_coef);
+            for (int e = 0; e < 8; ++e) {
+              float gv = v[h8 * 8 + e];
+              if (l2) gv = fmaf(-cs, bb[e], gv);                 // sum_i V_ij a_i - (sum_i V_ij) b_j
+              o[e] = gv + reg_grad(bb[e], g.reg_norm, g.reg_coef);
+            }
+            st4(row + k, make_float4(o[0], o[1], o[2], o[3]));
+            st4(row + k + 4, make_float4(o[4], o[5], o[6], o[7]));
           }
-          st4(row + k, make_float4(o[0], o[1], o[2], o[3]));
-          st4(row + k + 4, make_float4(o[4], o[5], o[6], o[7]));
         }
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) bcur[q4] = bnxt[q4];
       }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
   __syncthreads();
+  if (g.dbg && threadIdx.x == 0) g.dbg[cta_lin * 6 + 3] = gtime();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+    if (g.dbg && lane == 0) g.dbg[cta_lin * 6 + 5] = gtime();
   }
 }
 
@@ -551,7 +593,31 @@ int launch_gemm(const LaunchCtx& c, const CUtensorMap& ah, const CUtensorMap& al
   dim3 grid(ntiles_n, (g.rowsA_per_chunk + kTileM - 1) / kTileM, g.C);
   const char* nm = MODE == G_SCORE ? (FUSE ? "k_umma_gemm<score+loss S=A.Bn^T>" : "k_umma_gemm<score S=A.Bn^T>")
                                    : (MODE == G_GA ? "k_umma_gemm<grad_a GA=V.Bn>" : "k_umma_gemm<grad_b GB=V^T.A>");
-  KGE_LAUNCH_NAMED(c, nm, (k_umma_gemm<A_MN, B_MN, MODE, FUSE>), grid, kThreads, smem, ah, al, bh, bl, g);
+  static const bool timing = getenv("KGE_B200_UMMA_TIMING") != nullptr;
+  GemmArgs ga = g;
+  unsigned long long* dbg = nullptr;
+  const size_t nct = (size_t)grid.x * grid.y * grid.z;
+  if (timing) { cudaMalloc(&dbg, nct * 6 * sizeof(unsigned long long)); ga.dbg = dbg; }
+  KGE_LAUNCH_NAMED(c, nm, (k_umma_gemm<A_MN, B_MN, MODE, FUSE>), grid, kThreads, smem, ah, al, bh, bl, ga);
+  if (timing) {
+    cudaStreamSynchronize(c.stream);
+    unsigned long long* hbuf = (unsigned long long*)malloc(nct * 6 * sizeof(unsigned long long));
+    cudaMemcpy(hbuf, dbg, nct * 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    double t1 = 0, t2 = 0, t3 = 0, ta = 0, td = 0; unsigned long long mn = ~0ull, mx = 0, mne = ~0ull, mxd = 0;
+    for (size_t i = 0; i < nct; ++i) {
+      const unsigned long long* r = hbuf + i * 6;
+      t1 += (double)(r[1] - r[0]); t2 += (double)(r[2] - r[0]); t3 += (double)(r[3] - r[0]);
+      ta += (double)(r[0] - r[4]); td += (double)(r[5] - r[3]);
+      if (r[0] < mn) mn = r[0];
+      if (r[3] > mx) mx = r[3];
+      if (r[4] < mne) mne = r[4];
+      if (r[5] > mxd) mxd = r[5];
+    }
+    fprintf(stderr, "[umma timing] %s ctas=%zu alloc=%.2fus first_full=%.2fus mainloop_end=%.2fus cta_end=%.2fus dealloc=%.2fus "
+            "span(after alloc..before dealloc)=%.2fus span(entry..after dealloc)=%.2fus\n", nm, nct, ta / nct / 1e3, t1 / nct / 1e3,
+            t2 / nct / 1e3, t3 / nct / 1e3, td / nct / 1e3, (double)(mx - mn) / 1e3, (double)(mxd - mne) / 1e3);
+    free(hbuf); cudaFree(dbg);
+  }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { snprintf(err, errlen, "umma launch: %s", cudaGetErrorString(e)); return KGE_ERR_CUDA; }
   return KGE_OK;
