@@ -257,7 +257,7 @@ def run_ours(args):
 
     # ---- CUDA graphs of the device-resident step (one per batch): no launch gaps inside a step ----
     graphs = None
-    if world == 1 and not args.no_graph:
+    if not args.no_graph:
         try:
             graphs = []
             for k in range(NB):
@@ -269,6 +269,11 @@ def run_ours(args):
             sys.stderr.write("graph capture failed (%r); timing eager launches\n" % (e,))
             graphs = None
             torch.cuda.synchronize()
+    if world > 1:   # every rank must take the same path (a captured NCCL collective needs all ranks)
+        ok = torch.tensor([1 if graphs is not None else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            graphs = None
 
     def timed(run_step, after=None):
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]

@@ -110,33 +110,62 @@ __device__ __forceinline__ void edge_forward(const StepParams& p, const float* _
                                              float& reg_out, float& nrm_out, bool want_a) {
   EdgeAcc acc{0.f, 0.f, 0.f};
   const bool reg_on = (p.reg_coef > 0.f && p.reg_norm > 0);
+  // All loads of the (up to kIt) slices a lane owns are issued before any arithmetic: 9-12 independent 16-byte
+  // loads in flight per lane hide HBM latency, and the ~2 us NVLink latency when the rows live on a peer GPU.
+  constexpr int kIt = 4;                                  // register-resident fast path: D <= 512
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
   if (MODEL == KGE_COMPLEX || MODEL == KGE_ROTATE) {
     const int half = p.D >> 1, nvh = half >> 2;
     const float den = p.emb_init / 3.14159265358979323846f;
-    for (int v = lane; v < nvh; v += kWarp) {
-      float4 hr = ld4(h + 4 * v), hi = ld4(h + half + 4 * v);
-      float4 tr = ld4(t + 4 * v), ti = ld4(t + half + 4 * v);
-      float4 cr, ci;
-      if (MODEL == KGE_COMPLEX) {
-        cr = ld4(r + 4 * v); ci = ld4(r + half + 4 * v);
-        if (reg_on) acc.reg += abs_pow4_sum(cr, p.reg_norm) + abs_pow4_sum(ci, p.reg_norm);
-      } else {
-        float4 ph = ld4(r + 4 * v);
-        if (reg_on) acc.reg += abs_pow4_sum(ph, p.reg_norm);
-        phase_cos_sin(ph, den, cr, ci);
+    for (int v0 = 0; v0 < nvh; v0 += kWarp * (kIt / 2)) {
+      float4 hr[kIt / 2], hi[kIt / 2], tr[kIt / 2], ti[kIt / 2], r0[kIt / 2], r1[kIt / 2];
+#pragma unroll
+      for (int it = 0; it < kIt / 2; ++it) {
+        const int v = v0 + lane + kWarp * it;
+        const bool ok = v < nvh;
+        hr[it] = ok ? ld4(h + 4 * v) : z4; hi[it] = ok ? ld4(h + half + 4 * v) : z4;
+        tr[it] = ok ? ld4(t + 4 * v) : z4; ti[it] = ok ? ld4(t + half + 4 * v) : z4;
+        r0[it] = ok ? ld4(r + 4 * v) : z4;
+        r1[it] = (ok && MODEL == KGE_COMPLEX) ? ld4(r + half + 4 * v) : z4;
       }
-      float4 are, aim;
-      edge_slice_cplx<MODEL>(hr, hi, tr, ti, cr, ci, p.neg_head, are, aim, acc);
-      if (want_a) { row_store4(a_out, 4 * v, are); row_store4(a_out, half + 4 * v, aim); }
+#pragma unroll
+      for (int it = 0; it < kIt / 2; ++it) {
+        const int v = v0 + lane + kWarp * it;
+        if (v >= nvh) continue;
+        float4 cr, ci;
+        if (MODEL == KGE_COMPLEX) {
+          cr = r0[it]; ci = r1[it];
+          if (reg_on) acc.reg += abs_pow4_sum(cr, p.reg_norm) + abs_pow4_sum(ci, p.reg_norm);
+        } else {
+          if (reg_on) acc.reg += abs_pow4_sum(r0[it], p.reg_norm);
+          phase_cos_sin(r0[it], den, cr, ci);
+        }
+        float4 are, aim;
+        edge_slice_cplx<MODEL>(hr[it], hi[it], tr[it], ti[it], cr, ci, p.neg_head, are, aim, acc);
+        if (want_a) { row_store4(a_out, 4 * v, are); row_store4(a_out, half + 4 * v, aim); }
+      }
     }
   } else {
     const int nv = p.D >> 2;
-    for (int v = lane; v < nv; v += kWarp) {
-      float4 h4 = ld4(h + 4 * v), r4 = ld4(r + 4 * v), t4 = ld4(t + 4 * v);
-      if (reg_on) acc.reg += abs_pow4_sum(r4, p.reg_norm);
-      float4 a;
-      edge_slice_real<MODEL>(h4, r4, t4, p.neg_head, a, acc);
-      if (want_a) row_store4(a_out, 4 * v, a);
+    for (int v0 = 0; v0 < nv; v0 += kWarp * kIt) {
+      float4 h4[kIt], r4[kIt], t4[kIt];
+#pragma unroll
+      for (int it = 0; it < kIt; ++it) {
+        const int v = v0 + lane + kWarp * it;
+        const bool ok = v < nv;
+        h4[it] = ok ? ld4(h + 4 * v) : z4;
+        r4[it] = ok ? ld4(r + 4 * v) : z4;
+        t4[it] = ok ? ld4(t + 4 * v) : z4;
+      }
+#pragma unroll
+      for (int it = 0; it < kIt; ++it) {
+        const int v = v0 + lane + kWarp * it;
+        if (v >= nv) continue;
+        if (reg_on) acc.reg += abs_pow4_sum(r4[it], p.reg_norm);
+        float4 a;
+        edge_slice_real<MODEL>(h4[it], r4[it], t4[it], p.neg_head, a, acc);
+        if (want_a) row_store4(a_out, 4 * v, a);
+      }
     }
   }
   float s = warp_sum(acc.pos);
@@ -177,11 +206,22 @@ __global__ void __launch_bounds__(kRowBlock) k_prep(StepParams p, TableView ent,
     const long long ro = job * (long long)p.D;
     const RowOut bo{w.Bn + ro, w.Bhi, w.Blo, job / p.Ns, slab_blocks(p.D), p.Ns, (int)(job % p.Ns)};
     float b2 = 0.f, reg = 0.f;
-    for (int v = lane; v < (p.D >> 2); v += kWarp) {
-      float4 x = ld4_stream(src + 4 * v);
-      row_store4(bo, 4 * v, x);
-      if (MODEL == KGE_TRANSE_L2) b2 += f4_dot(x, x);
-      if (reg_on) reg += abs_pow4_sum(x, p.reg_norm);
+    const int nv = p.D >> 2;
+    for (int v0 = 0; v0 < nv; v0 += kWarp * 4) {
+      float4 x[4];
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int v = v0 + lane + kWarp * it;
+        x[it] = (v < nv) ? ld4_stream(src + 4 * v) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int v = v0 + lane + kWarp * it;
+        if (v >= nv) continue;
+        row_store4(bo, 4 * v, x[it]);
+        if (MODEL == KGE_TRANSE_L2) b2 += f4_dot(x[it], x[it]);
+        if (reg_on) reg += abs_pow4_sum(x[it], p.reg_norm);
+      }
     }
     b2 = warp_sum(b2); reg = warp_sum(reg);
     if (lane == 0) {
@@ -525,30 +565,45 @@ __global__ void __launch_bounds__(kRowBlock) k_chain(StepParams p, TableView ent
       nrm_scale = (n > 0.f) ? (-gp / n) : 0.f;
       rsum = w.rowsum[i];
     }
-    for (int v = lane; v < nv; v += kWarp) {
-      float4 h4 = ld4(h + 4 * v), r4 = ld4(r + 4 * v), t4 = ld4(t + 4 * v), g4 = ld4(ga + 4 * v);
-      float4 dh, dt, dr;
-      if (MODEL == KGE_TRANSE_L1 || MODEL == KGE_TRANSE_L2) {
-        float4 e = f4_sub(f4_add(h4, r4), t4);
-        float4 u;   // gpos * dpos/dh
-        if (MODEL == KGE_TRANSE_L2) u = f4_scale(e, nrm_scale);
-        else u = make_float4(-gp * sgnf(e.x), -gp * sgnf(e.y), -gp * sgnf(e.z), -gp * sgnf(e.w));
-        float4 a = p.neg_head ? f4_sub(t4, r4) : f4_add(h4, r4);
-        float4 gA = (MODEL == KGE_TRANSE_L2) ? f4_fma(a, -rsum, g4) : g4;   // GA - rowsum * a
-        if (p.neg_head) { dt = f4_sub(gA, u); dr = f4_sub(u, gA); dh = u; }
-        else            { dh = f4_add(u, gA); dr = dh; dt = f4_neg(u); }
-      } else {  // DistMult
-        dh = f4_scale(f4_mul(r4, t4), gp);
-        dr = f4_scale(f4_mul(h4, t4), gp);
-        dt = f4_scale(f4_mul(h4, r4), gp);
-        if (p.neg_head) { dt = f4_add(dt, f4_mul(g4, r4)); dr = f4_add(dr, f4_mul(g4, t4)); }
-        else            { dh = f4_add(dh, f4_mul(g4, r4)); dr = f4_add(dr, f4_mul(g4, h4)); }
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int v0 = 0; v0 < nv; v0 += kWarp * 4) {
+      // 16 independent 16-byte loads per lane before any arithmetic (HBM / NVLink latency hiding)
+      float4 hq[4], rq[4], tq[4], gq[4];
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int v = v0 + lane + kWarp * it;
+        const bool ok = v < nv;
+        hq[it] = ok ? ld4(h + 4 * v) : z4; rq[it] = ok ? ld4(r + 4 * v) : z4;
+        tq[it] = ok ? ld4(t + 4 * v) : z4; gq[it] = ok ? ld4(ga + 4 * v) : z4;
       }
-      red_add4(ngh + 4 * v, dh);
-      red_add4(ngt + 4 * v, dt);
-      dr = f4_add(dr, reg_grad4(r4, p.reg_norm, p.reg_coef));
-      st4(gr + 4 * v, dr);
-      gs += f4_dot(dr, dr);
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int v = v0 + lane + kWarp * it;
+        if (v >= nv) continue;
+        const float4 h4 = hq[it], r4 = rq[it], t4 = tq[it], g4 = gq[it];
+        float4 dh, dt, dr;
+        if (MODEL == KGE_TRANSE_L1 || MODEL == KGE_TRANSE_L2) {
+          float4 e = f4_sub(f4_add(h4, r4), t4);
+          float4 u;   // gpos * dpos/dh
+          if (MODEL == KGE_TRANSE_L2) u = f4_scale(e, nrm_scale);
+          else u = make_float4(-gp * sgnf(e.x), -gp * sgnf(e.y), -gp * sgnf(e.z), -gp * sgnf(e.w));
+          float4 a = p.neg_head ? f4_sub(t4, r4) : f4_add(h4, r4);
+          float4 gA = (MODEL == KGE_TRANSE_L2) ? f4_fma(a, -rsum, g4) : g4;   // GA - rowsum * a
+          if (p.neg_head) { dt = f4_sub(gA, u); dr = f4_sub(u, gA); dh = u; }
+          else            { dh = f4_add(u, gA); dr = dh; dt = f4_neg(u); }
+        } else {  // DistMult
+          dh = f4_scale(f4_mul(r4, t4), gp);
+          dr = f4_scale(f4_mul(h4, t4), gp);
+          dt = f4_scale(f4_mul(h4, r4), gp);
+          if (p.neg_head) { dt = f4_add(dt, f4_mul(g4, r4)); dr = f4_add(dr, f4_mul(g4, t4)); }
+          else            { dh = f4_add(dh, f4_mul(g4, r4)); dr = f4_add(dr, f4_mul(g4, h4)); }
+        }
+        red_add4(ngh + 4 * v, dh);
+        red_add4(ngt + 4 * v, dt);
+        dr = f4_add(dr, reg_grad4(r4, p.reg_norm, p.reg_coef));
+        st4(gr + 4 * v, dr);
+        gs += f4_dot(dr, dr);
+      }
     }
   }
   gs = warp_sum(gs);
@@ -574,18 +629,50 @@ __global__ void __launch_bounds__(kRowBlock) k_upd_nodes(StepParams p, TableView
   float* row = row_ptr(ent, id);
   float* ng = w.NG + u * (long long)p.D;
   const int nv = p.D >> 2;
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  float* st = state_ptr(ent, id);
+  if (nv <= 4 * kWarp) {
+    // D <= 512: the row and its gradient stay in registers -- one read and one write of the (possibly peer-GPU) row
+    float4 x[4], g[4];
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int v = lane + kWarp * it;
+      const bool ok = v < nv;
+      x[it] = ok ? ld4(row + 4 * v) : z;
+      g[it] = ok ? ld4(ng + 4 * v) : z;
+    }
+    float gs = 0.f;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      g[it] = f4_add(g[it], reg_grad4(x[it], p.reg_norm, p.reg_coef));
+      gs += f4_dot(g[it], g[it]);
+    }
+    gs = warp_sum(gs) / (float)p.D;
+    float s_new = 0.f;
+    if (lane == 0) { s_new = *st + gs; *st = s_new; }
+    s_new = __shfl_sync(0xffffffffu, s_new, 0);
+    const float stdv = sqrtf(s_new) + 1e-10f;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int v = lane + kWarp * it;
+      if (v >= nv) continue;
+      float4 tmp = make_float4((-p.lr * g[it].x) / stdv, (-p.lr * g[it].y) / stdv, (-p.lr * g[it].z) / stdv,
+                               (-p.lr * g[it].w) / stdv);
+      st4(row + 4 * v, f4_add(x[it], tmp));
+      st4(ng + 4 * v, z);
+    }
+    return;
+  }
   float gs = 0.f;
   for (int v = lane; v < nv; v += kWarp) {
     float4 g = f4_add(ld4(ng + 4 * v), reg_grad4(ld4(row + 4 * v), p.reg_norm, p.reg_coef));
     gs += f4_dot(g, g);
   }
   gs = warp_sum(gs) / (float)p.D;
-  float* st = state_ptr(ent, id);
   float s_new = 0.f;
   if (lane == 0) { s_new = *st + gs; *st = s_new; }
   s_new = __shfl_sync(0xffffffffu, s_new, 0);
   const float stdv = sqrtf(s_new) + 1e-10f;
-  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int v = lane; v < nv; v += kWarp) {
     float4 x = ld4(row + 4 * v);
     float4 g = f4_add(ld4(ng + 4 * v), reg_grad4(x, p.reg_norm, p.reg_coef));
