@@ -103,7 +103,7 @@ __device__ __forceinline__ void phase_cos_sin(float4 r, float inv_scale_den, flo
 }
 
 // One warp = one edge.  h/r/t are row pointers (table rows or dense rows).
-template <int MODEL>
+template <int MODEL, int KIT>
 __device__ __forceinline__ void edge_forward(const StepParams& p, const float* __restrict__ h,
                                              const float* __restrict__ r, const float* __restrict__ t,
                                              const RowOut& a_out, int lane, float& pos_out, float& a2_out,
@@ -112,15 +112,16 @@ __device__ __forceinline__ void edge_forward(const StepParams& p, const float* _
   const bool reg_on = (p.reg_coef > 0.f && p.reg_norm > 0);
   // All loads of the (up to kIt) slices a lane owns are issued before any arithmetic: 9-12 independent 16-byte
   // loads in flight per lane hide HBM latency, and the ~2 us NVLink latency when the rows live on a peer GPU.
-  constexpr int kIt = 4;                                  // register-resident fast path: D <= 512
+  constexpr int kIt = KIT;                                // slices per lane loaded ahead (1: local HBM, 4: sharded)
+  constexpr int kItC = KIT > 1 ? KIT / 2 : 1;             // complex models load two half-rows per slice
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
   if (MODEL == KGE_COMPLEX || MODEL == KGE_ROTATE) {
     const int half = p.D >> 1, nvh = half >> 2;
     const float den = p.emb_init / 3.14159265358979323846f;
-    for (int v0 = 0; v0 < nvh; v0 += kWarp * (kIt / 2)) {
-      float4 hr[kIt / 2], hi[kIt / 2], tr[kIt / 2], ti[kIt / 2], r0[kIt / 2], r1[kIt / 2];
+    for (int v0 = 0; v0 < nvh; v0 += kWarp * kItC) {
+      float4 hr[kItC], hi[kItC], tr[kItC], ti[kItC], r0[kItC], r1[kItC];
 #pragma unroll
-      for (int it = 0; it < kIt / 2; ++it) {
+      for (int it = 0; it < kItC; ++it) {
         const int v = v0 + lane + kWarp * it;
         const bool ok = v < nvh;
         hr[it] = ok ? ld4(h + 4 * v) : z4; hi[it] = ok ? ld4(h + half + 4 * v) : z4;
@@ -129,7 +130,7 @@ __device__ __forceinline__ void edge_forward(const StepParams& p, const float* _
         r1[it] = (ok && MODEL == KGE_COMPLEX) ? ld4(r + half + 4 * v) : z4;
       }
 #pragma unroll
-      for (int it = 0; it < kIt / 2; ++it) {
+      for (int it = 0; it < kItC; ++it) {
         const int v = v0 + lane + kWarp * it;
         if (v >= nvh) continue;
         float4 cr, ci;
@@ -178,7 +179,7 @@ __device__ __forceinline__ void edge_forward(const StepParams& p, const float* _
 }
 
 // Job space of k_prep: [0,B) edges | [B, B+Nn) negatives | [B+Nn, B+Nn+U) unique nodes (reg only)
-template <int MODEL>
+template <int MODEL, int KIT>
 __global__ void __launch_bounds__(kRowBlock) k_prep(StepParams p, TableView ent, TableView rel, BatchView b, StepWs w,
                                                      long long job0) {
   long long job = job0 + (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
@@ -192,7 +193,7 @@ __global__ void __launch_bounds__(kRowBlock) k_prep(StepParams p, TableView ent,
     const long long ro = job * (long long)p.D;
     // tcgen05 engine: A is only consumed as hi/lo operands; fp32 tiles: plain fp32
     const RowOut ao{w.Ahi ? nullptr : w.A + ro, w.Ahi, w.Alo, job / p.Cs, slab_blocks(p.D), p.Cs, (int)(job % p.Cs)};
-    edge_forward<MODEL>(p, h, r, t, ao, lane, pos, a2, reg, nrm, true);
+    edge_forward<MODEL, KIT>(p, h, r, t, ao, lane, pos, a2, reg, nrm, true);
     if (lane == 0) {
       w.pos[job] = pos;
       if (MODEL == KGE_TRANSE_L2) { w.a2[job] = a2; w.pnorm[job] = nrm; }
@@ -207,15 +208,15 @@ __global__ void __launch_bounds__(kRowBlock) k_prep(StepParams p, TableView ent,
     const RowOut bo{w.Bn + ro, w.Bhi, w.Blo, job / p.Ns, slab_blocks(p.D), p.Ns, (int)(job % p.Ns)};
     float b2 = 0.f, reg = 0.f;
     const int nv = p.D >> 2;
-    for (int v0 = 0; v0 < nv; v0 += kWarp * 4) {
-      float4 x[4];
+    for (int v0 = 0; v0 < nv; v0 += kWarp * KIT) {
+      float4 x[KIT];
 #pragma unroll
-      for (int it = 0; it < 4; ++it) {
+      for (int it = 0; it < KIT; ++it) {
         const int v = v0 + lane + kWarp * it;
         x[it] = (v < nv) ? ld4_stream(src + 4 * v) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
-      for (int it = 0; it < 4; ++it) {
+      for (int it = 0; it < KIT; ++it) {
         const int v = v0 + lane + kWarp * it;
         if (v >= nv) continue;
         row_store4(bo, 4 * v, x[it]);
@@ -258,7 +259,7 @@ __global__ void __launch_bounds__(kRowBlock) k_prep_dense(StepParams p, const fl
     const long long ro = job * (long long)p.D;
     const RowOut ao{(want_a && !w.Ahi) ? w.A + ro : nullptr, want_a ? w.Ahi : nullptr, want_a ? w.Alo : nullptr,
                     job / p.Cs, slab_blocks(p.D), p.Cs, (int)(job % p.Cs)};
-    edge_forward<MODEL>(p, hrow, relr + job * (long long)p.Dr, trow, ao, lane, pos, a2, reg, nrm, want_a);
+    edge_forward<MODEL, 1>(p, hrow, relr + job * (long long)p.Dr, trow, ao, lane, pos, a2, reg, nrm, want_a);
     if (lane == 0) {
       if (want_pos) w.pos[job] = pos;
       if (want_a && MODEL == KGE_TRANSE_L2) w.a2[job] = a2;
@@ -295,7 +296,12 @@ void launch_prep(const LaunchCtx& c, const StepParams& p, const TableView& ent, 
                  const BatchView& b, const StepWs& w) {
   const bool reg_on = (p.reg_coef > 0.f && p.reg_norm > 0);
   long long jobs = p.B + p.Nn + (reg_on ? p.U : 0);
-  KGE_DISPATCH_MODEL(p.model, KGE_LAUNCH(c, k_prep<M>, ceil_div(jobs, kWarpsPerBlock), kRowBlock, 0, p, ent, rel, b, w, 0LL));
+  // sharded tables: deeper per-lane load batches hide the ~2 us NVLink latency; local HBM prefers occupancy
+  if (ent.n_shards > 1) {
+    KGE_DISPATCH_MODEL(p.model, KGE_LAUNCH(c, (k_prep<M, 4>), ceil_div(jobs, kWarpsPerBlock), kRowBlock, 0, p, ent, rel, b, w, 0LL));
+  } else {
+    KGE_DISPATCH_MODEL(p.model, KGE_LAUNCH(c, (k_prep<M, 1>), ceil_div(jobs, kWarpsPerBlock), kRowBlock, 0, p, ent, rel, b, w, 0LL));
+  }
 }
 
 // negatives + unique-node jobs only (RESCAL runs its own per-edge kernel)
@@ -303,7 +309,7 @@ void launch_prep_nonedge(const LaunchCtx& c, const StepParams& p, const TableVie
                          const BatchView& b, const StepWs& w) {
   const bool reg_on = (p.reg_coef > 0.f && p.reg_norm > 0);
   long long jobs = p.Nn + (reg_on ? p.U : 0);
-  KGE_LAUNCH(c, k_prep<KGE_DISTMULT>, ceil_div(jobs, kWarpsPerBlock), kRowBlock, 0, p, ent, rel, b, w, p.B);
+  KGE_LAUNCH(c, (k_prep<KGE_DISTMULT, 1>), ceil_div(jobs, kWarpsPerBlock), kRowBlock, 0, p, ent, rel, b, w, p.B);
 }
 
 void launch_prep_dense(const LaunchCtx& c, const StepParams& p, const float* head, const float* relr,
@@ -478,7 +484,7 @@ void launch_loss(const LaunchCtx& c, const StepParams& p, const float* pos, cons
 // contraction kernels) and gpos = dL/dpos.  Emits
 //   NG[head_local] += dL/dh,  NG[tail_local] += dL/dt          (red.add, L2-resident workspace)
 //   GR[i] = dL/dr_i + reg'(r_i),  rel.state_sum[rel_id] += mean(GR[i]^2)   (Adagrad phase 1, a10)
-template <int MODEL>
+template <int MODEL, int KIT>
 __global__ void __launch_bounds__(kRowBlock) k_chain(StepParams p, TableView ent, TableView rel, BatchView b, StepWs w) {
   const long long i = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   if (i >= p.B) return;
@@ -566,18 +572,18 @@ __global__ void __launch_bounds__(kRowBlock) k_chain(StepParams p, TableView ent
       rsum = w.rowsum[i];
     }
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int v0 = 0; v0 < nv; v0 += kWarp * 4) {
-      // 16 independent 16-byte loads per lane before any arithmetic (HBM / NVLink latency hiding)
-      float4 hq[4], rq[4], tq[4], gq[4];
+    for (int v0 = 0; v0 < nv; v0 += kWarp * KIT) {
+      // 4*KIT independent 16-byte loads per lane before any arithmetic (HBM / NVLink latency hiding)
+      float4 hq[KIT], rq[KIT], tq[KIT], gq[KIT];
 #pragma unroll
-      for (int it = 0; it < 4; ++it) {
+      for (int it = 0; it < KIT; ++it) {
         const int v = v0 + lane + kWarp * it;
         const bool ok = v < nv;
         hq[it] = ok ? ld4(h + 4 * v) : z4; rq[it] = ok ? ld4(r + 4 * v) : z4;
         tq[it] = ok ? ld4(t + 4 * v) : z4; gq[it] = ok ? ld4(ga + 4 * v) : z4;
       }
 #pragma unroll
-      for (int it = 0; it < 4; ++it) {
+      for (int it = 0; it < KIT; ++it) {
         const int v = v0 + lane + kWarp * it;
         if (v >= nv) continue;
         const float4 h4 = hq[it], r4 = rq[it], t4 = tq[it], g4 = gq[it];
@@ -615,7 +621,11 @@ __global__ void __launch_bounds__(kRowBlock) k_chain(StepParams p, TableView ent
 
 void launch_chain(const LaunchCtx& c, const StepParams& p, const TableView& ent, const TableView& rel,
                   const BatchView& b, const StepWs& w) {
-  KGE_DISPATCH_MODEL(p.model, KGE_LAUNCH(c, k_chain<M>, ceil_div(p.B, kWarpsPerBlock), kRowBlock, 0, p, ent, rel, b, w));
+  if (ent.n_shards > 1) {
+    KGE_DISPATCH_MODEL(p.model, KGE_LAUNCH(c, (k_chain<M, 4>), ceil_div(p.B, kWarpsPerBlock), kRowBlock, 0, p, ent, rel, b, w));
+  } else {
+    KGE_DISPATCH_MODEL(p.model, KGE_LAUNCH(c, (k_chain<M, 1>), ceil_div(p.B, kWarpsPerBlock), kRowBlock, 0, p, ent, rel, b, w));
+  }
 }
 
 // ------------------------------------------------------------------------------------------ a10
@@ -722,12 +732,37 @@ void launch_update_entities(const LaunchCtx& c, const StepParams& p, const Table
   KGE_LAUNCH(c, k_apply, ceil_div(p.Nn, kWarpsPerBlock), kRowBlock, 0, ent, b.neg_ids, w.Bn, p.Nn, p.D, p.lr);
 }
 
+// negatives (entity entry 2, phase 2) and relation rows in ONE launch: job space [0,Nn) | [Nn, Nn+B)
+__global__ void __launch_bounds__(kRowBlock) k_apply2(TableView ent, const long long* __restrict__ neg_ids,
+                                                       const float* __restrict__ gneg, long long Nn, int D,
+                                                       TableView rel, const long long* __restrict__ rel_ids,
+                                                       const float* __restrict__ grel, long long B, int Dr, float lr) {
+  long long j = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const bool is_rel = j >= Nn;
+  if (is_rel) j -= Nn;
+  if (is_rel && j >= B) return;
+  const TableView& t = is_rel ? rel : ent;
+  const int dim = is_rel ? Dr : D;
+  const long long id = is_rel ? rel_ids[j] : neg_ids[j];
+  const float stdv = sqrtf(*state_ptr(t, id)) + 1e-10f;
+  const float* g = (is_rel ? grel : gneg) + j * (long long)dim;
+  float* row = row_ptr(t, id);
+  for (int v = lane; v < (dim >> 2); v += kWarp) {
+    float4 x = ld4(g + 4 * v);
+    table_red_add4(t, row + 4 * v, make_float4((-lr * x.x) / stdv, (-lr * x.y) / stdv, (-lr * x.z) / stdv, (-lr * x.w) / stdv));
+  }
+}
+
 void launch_update(const LaunchCtx& c, const StepParams& p, const TableView& ent, const TableView& rel,
                    const BatchView& b, const StepWs& w) {
-  launch_update_entities(c, p, ent, b, w);
-  // relation entry: state was accumulated by k_chain
-  if (!p.rel_deferred)
-    KGE_LAUNCH(c, k_apply, ceil_div(p.B, kWarpsPerBlock), kRowBlock, 0, rel, b.rel_ids, w.GR, p.B, p.Dr, p.lr);
+  if (p.rel_deferred) { launch_update_entities(c, p, ent, b, w); return; }
+  // entity entry 1 (unique positive nodes) -- must finish before entry 2 touches state_sum
+  KGE_LAUNCH(c, k_upd_nodes, ceil_div(p.U, kWarpsPerBlock), kRowBlock, 0, p, ent, b, w);
+  KGE_LAUNCH(c, k_state_add, ceil_div(p.Nn, kWarpsPerBlock), kRowBlock, 0, ent, b.neg_ids, w.Bn, p.Nn, p.D);
+  // entry 2 rows + relation rows (their state was accumulated by k_chain)
+  KGE_LAUNCH(c, k_apply2, ceil_div(p.Nn + p.B, kWarpsPerBlock), kRowBlock, 0, ent, b.neg_ids, w.Bn, p.Nn, p.D, rel,
+             b.rel_ids, w.GR, p.B, p.Dr, p.lr);
 }
 
 // ---- multi-GPU relation path: per-edge gradients -> dense per-relation sums (all-reduced by the host
