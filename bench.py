@@ -331,10 +331,12 @@ def run_ours(args):
 
     if world > 1:
         dist.barrier()
+        torch.cuda.synchronize()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        # leave without tearing down NCCL / captured graphs / IPC mappings: destroying a process group whose
+        # collectives live inside CUDA graphs has been seen to hang at exit
+        sys.stdout.flush()
+        os._exit(0)
 
     peaks = {}
     try:
@@ -378,7 +380,8 @@ def run_ours(args):
     }
     print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":
