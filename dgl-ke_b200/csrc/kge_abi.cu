@@ -163,6 +163,7 @@ int carve(kge_context* h, const StepParams& p, StepWs* w, cudaStream_t stream) {
   // NG first, sized for the largest possible node count (2B): rows >= U are never written, rows < U are
   // re-zeroed by k_upd_nodes, so one fill keeps the whole region zero across steps with varying U
   size_t oNG = take((U ? (size_t)2 * p.B : 0) * p.D);
+  size_t oNC = take(U * p.D);
   size_t oA = take(BD), oBn = take(ND), oGA = take(BD), oGR = take((size_t)p.B * p.Dr);
   size_t oS = take(BNs), oV = take(BNs);
   size_t opos = take(p.B), ogpos = take(p.B), opn = take(p.B), oa2 = take(p.B), ob2 = take(p.Nn);
@@ -189,7 +190,7 @@ int carve(kge_context* h, const StepParams& p, StepWs* w, cudaStream_t stream) {
     h->arena_bytes = bytes;
   }
   char* a = h->arena;
-  w->NG = (float*)(a + oNG); w->A = (float*)(a + oA); w->Bn = (float*)(a + oBn); w->GA = (float*)(a + oGA);
+  w->NG = (float*)(a + oNG); w->NC = (float*)(a + oNC); w->A = (float*)(a + oA); w->Bn = (float*)(a + oBn); w->GA = (float*)(a + oGA);
   w->GR = (float*)(a + oGR); w->S = (float*)(a + oS); w->V = (float*)(a + oV);
   w->pos = (float*)(a + opos); w->gpos = (float*)(a + ogpos); w->pnorm = (float*)(a + opn);
   w->a2 = (float*)(a + oa2); w->b2 = (float*)(a + ob2); w->rowsum = (float*)(a + ors); w->colsum = (float*)(a + ocs);
@@ -471,6 +472,7 @@ KGE_API int kge_forward_backward(kge_handle_t h, const kge_step_cfg_t* cfg, cons
   LaunchCtx c = lctx(h, stream);
   BatchView b = bview(batch);
   ensure_ng_zero(h, p, w, c, false);
+  launch_gather_nodes(c, p, ve, b, w);      // pos_g.ndata['emb'] = entity_emb(pos_g.ndata['id'])  (general_models.py:548)
   if (p.model == KGE_RESCAL) launch_rescal_prep(c, p, ve, vr, b, w);
   else launch_prep(c, p, ve, vr, b, w);
   if (h->fuse_loss && use_umma(h, p) && p.Ns <= 256) {

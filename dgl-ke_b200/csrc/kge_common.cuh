@@ -58,6 +58,8 @@ struct StepWs {
   float* GA;       // [B, D]   d loss / d a
   float* GR;       // [B, Dr]  d loss / d relation rows (per edge)
   float* NG;       // [U, D]   d loss / d unique positive nodes (without reg), zero between steps
+  float* NC;       // [U, D]   gathered rows of the unique positive nodes (= pos_g.ndata['emb'], general_models.py:548):
+                   //          every later read of a head/tail row is local, even when the table is sharded over GPUs
   float* S;        // [B, Ns]  negative scores
   float* V;        // [B, Ns]  backward coefficients
   float* pos;      // [B]
@@ -271,6 +273,7 @@ inline void prof_end(const LaunchCtx& c) {
   } while (0)
 
 void launch_gather(const LaunchCtx&, const TableView& t, const long long* idx, long long n, float* out);
+void launch_gather_nodes(const LaunchCtx&, const StepParams&, const TableView& ent, const BatchView&, const StepWs&);
 void launch_prep(const LaunchCtx&, const StepParams&, const TableView& ent, const TableView& rel,
                  const BatchView&, const StepWs&);
 // dense-row variant used by kge_score_pos / kge_score_neg (rows already gathered)

@@ -178,7 +178,7 @@ __device__ __forceinline__ void edge_forward(const StepParams& p, const float* _
   else pos_out = s;
 }
 
-// Job space of k_prep: [0,B) edges | [B, B+Nn) negatives | [B+Nn, B+Nn+U) unique nodes (reg only)
+// Job space of k_prep: [0,B) edges | [B, B+Nn) negatives
 template <int MODEL, int KIT>
 __global__ void __launch_bounds__(kRowBlock) k_prep(StepParams p, TableView ent, TableView rel, BatchView b, StepWs w,
                                                      long long job0) {
@@ -186,8 +186,8 @@ __global__ void __launch_bounds__(kRowBlock) k_prep(StepParams p, TableView ent,
   const int lane = threadIdx.x & 31;
   const bool reg_on = (p.reg_coef > 0.f && p.reg_norm > 0);
   if (job < p.B) {
-    const float* h = row_ptr(ent, b.node_ids[b.head_local[job]]);
-    const float* t = row_ptr(ent, b.node_ids[b.tail_local[job]]);
+    const float* h = w.NC + b.head_local[job] * (long long)p.D;     // local copies made by k_gather_nodes
+    const float* t = w.NC + b.tail_local[job] * (long long)p.D;
     const float* r = row_ptr(rel, b.rel_ids[job]);
     float pos, a2, reg, nrm;
     const long long ro = job * (long long)p.D;
@@ -231,14 +231,44 @@ __global__ void __launch_bounds__(kRowBlock) k_prep(StepParams p, TableView ent,
     }
     return;
   }
-  job -= p.Nn;
-  if (job < p.U && reg_on) {
-    const float* src = row_ptr(ent, b.node_ids[job]);
-    float reg = 0.f;
-    for (int v = lane; v < (p.D >> 2); v += kWarp) reg += abs_pow4_sum(ld4(src + 4 * v), p.reg_norm);
-    reg = warp_sum(reg);
-    if (lane == 0) w.regp[p.B + p.Nn + job] = reg;
+}
+
+// ExternalEmbedding.__call__ on pos_g.ndata['id'] (general_models.py:548): NC[u,:] = ent[node_ids[u],:], one warp per
+// unique node, plus the node's share of the regulariser.  The only kernel (besides the negatives' gather in k_prep)
+// that reads entity rows from the table -- over NVLink when the owner is a peer GPU.
+template <int KIT>
+__global__ void __launch_bounds__(kRowBlock) k_gather_nodes(StepParams p, TableView ent, BatchView b, StepWs w) {
+  const long long u = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (u >= p.U) return;
+  const int lane = threadIdx.x & 31;
+  const bool reg_on = (p.reg_coef > 0.f && p.reg_norm > 0);
+  const float* src = row_ptr(ent, b.node_ids[u]);
+  float* dst = w.NC + u * (long long)p.D;
+  const int nv = p.D >> 2;
+  float reg = 0.f;
+  for (int v0 = 0; v0 < nv; v0 += kWarp * KIT) {
+    float4 x[KIT];
+#pragma unroll
+    for (int it = 0; it < KIT; ++it) {
+      const int v = v0 + lane + kWarp * it;
+      x[it] = (v < nv) ? ld4_stream(src + 4 * v) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int it = 0; it < KIT; ++it) {
+      const int v = v0 + lane + kWarp * it;
+      if (v >= nv) continue;
+      st4(dst + 4 * v, x[it]);
+      if (reg_on) reg += abs_pow4_sum(x[it], p.reg_norm);
+    }
   }
+  reg = warp_sum(reg);
+  if (lane == 0) w.regp[p.B + p.Nn + u] = reg;
+}
+
+void launch_gather_nodes(const LaunchCtx& c, const StepParams& p, const TableView& ent, const BatchView& b,
+                         const StepWs& w) {
+  if (ent.n_shards > 1) KGE_LAUNCH(c, k_gather_nodes<4>, ceil_div(p.U, kWarpsPerBlock), kRowBlock, 0, p, ent, b, w);
+  else KGE_LAUNCH(c, k_gather_nodes<2>, ceil_div(p.U, kWarpsPerBlock), kRowBlock, 0, p, ent, b, w);
 }
 
 // dense-row variant: kge_score_pos (want_pos) / kge_score_neg (want_a + negatives' norms)
@@ -294,8 +324,7 @@ __global__ void __launch_bounds__(kRowBlock) k_prep_dense(StepParams p, const fl
 
 void launch_prep(const LaunchCtx& c, const StepParams& p, const TableView& ent, const TableView& rel,
                  const BatchView& b, const StepWs& w) {
-  const bool reg_on = (p.reg_coef > 0.f && p.reg_norm > 0);
-  long long jobs = p.B + p.Nn + (reg_on ? p.U : 0);
+  long long jobs = p.B + p.Nn;
   // sharded tables: deeper per-lane load batches hide the ~2 us NVLink latency; local HBM prefers occupancy
   if (ent.n_shards > 1) {
     KGE_DISPATCH_MODEL(p.model, KGE_LAUNCH(c, (k_prep<M, 4>), ceil_div(jobs, kWarpsPerBlock), kRowBlock, 0, p, ent, rel, b, w, 0LL));
@@ -307,8 +336,7 @@ void launch_prep(const LaunchCtx& c, const StepParams& p, const TableView& ent, 
 // negatives + unique-node jobs only (RESCAL runs its own per-edge kernel)
 void launch_prep_nonedge(const LaunchCtx& c, const StepParams& p, const TableView& ent, const TableView& rel,
                          const BatchView& b, const StepWs& w) {
-  const bool reg_on = (p.reg_coef > 0.f && p.reg_norm > 0);
-  long long jobs = p.Nn + (reg_on ? p.U : 0);
+  long long jobs = p.Nn;
   KGE_LAUNCH(c, (k_prep<KGE_DISTMULT, 1>), ceil_div(jobs, kWarpsPerBlock), kRowBlock, 0, p, ent, rel, b, w, p.B);
 }
 
@@ -490,8 +518,8 @@ __global__ void __launch_bounds__(kRowBlock) k_chain(StepParams p, TableView ent
   if (i >= p.B) return;
   const int lane = threadIdx.x & 31;
   const long long hl = b.head_local[i], tl = b.tail_local[i], rid = b.rel_ids[i];
-  const float* h = row_ptr(ent, b.node_ids[hl]);
-  const float* t = row_ptr(ent, b.node_ids[tl]);
+  const float* h = w.NC + hl * (long long)p.D;
+  const float* t = w.NC + tl * (long long)p.D;
   const float* r = row_ptr(rel, rid);
   const float* ga = w.GA + i * (long long)p.D;
   float* ngh = w.NG + hl * (long long)p.D;
@@ -638,56 +666,33 @@ __global__ void __launch_bounds__(kRowBlock) k_upd_nodes(StepParams p, TableView
   const long long id = b.node_ids[u];
   float* row = row_ptr(ent, id);
   float* ng = w.NG + u * (long long)p.D;
+  const float* nc = w.NC + u * (long long)p.D;      // the traced copy of the row (what the reference regularises)
   const int nv = p.D >> 2;
   const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-  float* st = state_ptr(ent, id);
-  if (nv <= 4 * kWarp) {
-    // D <= 512: the row and its gradient stay in registers -- one read and one write of the (possibly peer-GPU) row
-    float4 x[4], g[4];
-#pragma unroll
-    for (int it = 0; it < 4; ++it) {
-      const int v = lane + kWarp * it;
-      const bool ok = v < nv;
-      x[it] = ok ? ld4(row + 4 * v) : z;
-      g[it] = ok ? ld4(ng + 4 * v) : z;
-    }
-    float gs = 0.f;
-#pragma unroll
-    for (int it = 0; it < 4; ++it) {
-      g[it] = f4_add(g[it], reg_grad4(x[it], p.reg_norm, p.reg_coef));
-      gs += f4_dot(g[it], g[it]);
-    }
-    gs = warp_sum(gs) / (float)p.D;
-    float s_new = 0.f;
-    if (lane == 0) { s_new = *st + gs; *st = s_new; }
-    s_new = __shfl_sync(0xffffffffu, s_new, 0);
-    const float stdv = sqrtf(s_new) + 1e-10f;
-#pragma unroll
-    for (int it = 0; it < 4; ++it) {
-      const int v = lane + kWarp * it;
-      if (v >= nv) continue;
-      float4 tmp = make_float4((-p.lr * g[it].x) / stdv, (-p.lr * g[it].y) / stdv, (-p.lr * g[it].z) / stdv,
-                               (-p.lr * g[it].w) / stdv);
-      st4(row + 4 * v, f4_add(x[it], tmp));
-      st4(ng + 4 * v, z);
-    }
-    return;
-  }
+  const bool sharded = ent.n_shards > 1;
+  // pass 1 (local memory only): g = NG + reg'(x), mean(g^2)
   float gs = 0.f;
   for (int v = lane; v < nv; v += kWarp) {
-    float4 g = f4_add(ld4(ng + 4 * v), reg_grad4(ld4(row + 4 * v), p.reg_norm, p.reg_coef));
+    float4 g = f4_add(ld4(ng + 4 * v), reg_grad4(ld4(nc + 4 * v), p.reg_norm, p.reg_coef));
     gs += f4_dot(g, g);
   }
   gs = warp_sum(gs) / (float)p.D;
+  float* st = state_ptr(ent, id);
   float s_new = 0.f;
-  if (lane == 0) { s_new = *st + gs; *st = s_new; }
+  if (lane == 0) {
+    if (sharded) s_new = atomicAdd_system(st, gs) + gs;   // remote-safe: other GPUs may add to the same state
+    else { s_new = *st + gs; *st = s_new; }
+  }
   s_new = __shfl_sync(0xffffffffu, s_new, 0);
   const float stdv = sqrtf(s_new) + 1e-10f;
+  // pass 2: emb[id] += -lr * g / std.  Indices are unique, so on one GPU the new row is (traced copy + step) with
+  // no read of the table; across GPUs the step is a system-scope red.add (no read either, and atomic w.r.t. peers).
   for (int v = lane; v < nv; v += kWarp) {
-    float4 x = ld4(row + 4 * v);
+    float4 x = ld4(nc + 4 * v);
     float4 g = f4_add(ld4(ng + 4 * v), reg_grad4(x, p.reg_norm, p.reg_coef));
     float4 tmp = make_float4((-p.lr * g.x) / stdv, (-p.lr * g.y) / stdv, (-p.lr * g.z) / stdv, (-p.lr * g.w) / stdv);
-    st4(row + 4 * v, f4_add(x, tmp));
+    if (sharded) red_add4_sys(row + 4 * v, tmp);
+    else st4(row + 4 * v, f4_add(x, tmp));
     st4(ng + 4 * v, z);
   }
 }
@@ -823,7 +828,7 @@ __global__ void __launch_bounds__(kRowBlock) k_node_grad_reg(StepParams p, Table
   const long long u = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   if (u >= p.U) return;
   const int lane = threadIdx.x & 31;
-  const float* row = row_ptr(ent, b.node_ids[u]);
+  const float* row = w.NC + u * (long long)p.D;
   for (int v = lane; v < (p.D >> 2); v += kWarp)
     st4(out + u * (long long)p.D + 4 * v,
         f4_add(ld4(w.NG + u * (long long)p.D + 4 * v), reg_grad4(ld4(row + 4 * v), p.reg_norm, p.reg_coef)));
