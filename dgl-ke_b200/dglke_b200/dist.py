@@ -114,8 +114,10 @@ class ShardedTrainer:
         out = self.eng.forward_backward(node_ids, head_local, tail_local, rel_ids, neg_ids, chunk_size,
                                         neg_sample_size, neg_head, edge_weight, log4)
         _lib.check(lib.kge_rel_grad_dense(h.raw, self.rg.data_ptr(), self.rgs.data_ptr(), h.stream()))
+        # the relation all-reduce (NCCL stream) overlaps the entity Adagrad kernels, which do not touch rbuf
+        work = dist.all_reduce(self.rbuf, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
         self.eng.update()
-        dist.all_reduce(self.rbuf, op=dist.ReduceOp.SUM, group=self.group)
+        work.wait()
         _lib.check(lib.kge_rel_apply_dense(h.raw, self.rel.ref(), self.rg.data_ptr(), self.rgs.data_ptr(),
                                            float(self.hp.lr), h.stream()))
         return out
