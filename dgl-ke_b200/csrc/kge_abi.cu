@@ -552,29 +552,56 @@ KGE_API int kge_step_fused_host(kge_handle_t h, const kge_step_cfg_t* cfg, const
     if (cudaMallocHost(&h->pin, cap) != cudaSuccess) { cudaGetLastError(); return fail(KGE_ERR_NOMEM, "cudaMallocHost(%zu) failed", cap); }
     if (cudaMalloc(&h->dev_stage, cap) != cudaSuccess) { cudaGetLastError(); return fail(KGE_ERR_NOMEM, "cudaMalloc(%zu) failed", cap); }
     h->stage_bytes = cap;
-  } else {
-    // the previous step's H2D copy must have drained before the pinned buffer is overwritten
-    KGE_CUDA_OK(cudaStreamSynchronize(st));
   }
-  long long* ph = (long long*)h->pin;
   long long* pd = (long long*)h->dev_stage;
-  size_t o = 0;
   kge_batch_t bd{};
-  auto put = [&](const int64_t* src, long long n) { memcpy(ph + o, src, (size_t)n * 8); const int64_t* d = (const int64_t*)(pd + o); o += (size_t)n; return d; };
-  bd.node_ids = put(bh->node_ids, U); bd.n_nodes = U;
-  bd.head_local = put(bh->head_local, B);
-  bd.tail_local = put(bh->tail_local, B);
-  bd.rel_ids = put(bh->rel_ids, B);
-  bd.neg_ids = put(bh->neg_ids, Nn);
-  size_t wbytes = 0;
-  if (bh->edge_weight) {
-    size_t woff = align_up(n64 * 8);
-    memcpy(h->pin + woff, bh->edge_weight, (size_t)B * 4);
-    bd.edge_weight = (const float*)(h->dev_stage + woff);
-    wbytes = woff + (size_t)B * 4;
+  // Fast path: the caller's arrays are page-locked (e.g. torch pinned tensors) -> DMA straight from them.
+  auto is_pinned = [](const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+  };
+  const bool direct = is_pinned(bh->node_ids) && is_pinned(bh->head_local) && is_pinned(bh->tail_local) &&
+                      is_pinned(bh->rel_ids) && is_pinned(bh->neg_ids) && (!bh->edge_weight || is_pinned(bh->edge_weight));
+  size_t o = 0;
+  if (direct) {
+    auto put = [&](const int64_t* src, long long n) -> const int64_t* {
+      const int64_t* d = (const int64_t*)(pd + o);
+      cudaMemcpyAsync(pd + o, src, (size_t)n * 8, cudaMemcpyHostToDevice, st);
+      o += (size_t)n;
+      return d;
+    };
+    bd.node_ids = put(bh->node_ids, U); bd.n_nodes = U;
+    bd.head_local = put(bh->head_local, B);
+    bd.tail_local = put(bh->tail_local, B);
+    bd.rel_ids = put(bh->rel_ids, B);
+    bd.neg_ids = put(bh->neg_ids, Nn);
+    if (bh->edge_weight) {
+      size_t woff = align_up(n64 * 8);
+      cudaMemcpyAsync(h->dev_stage + woff, bh->edge_weight, (size_t)B * 4, cudaMemcpyHostToDevice, st);
+      bd.edge_weight = (const float*)(h->dev_stage + woff);
+    }
+    KGE_CUDA_OK(cudaGetLastError());
+  } else {
+    // the previous step's H2D copy must have drained before the library's pinned buffer is overwritten
+    KGE_CUDA_OK(cudaStreamSynchronize(st));
+    long long* ph = (long long*)h->pin;
+    auto put = [&](const int64_t* src, long long n) { memcpy(ph + o, src, (size_t)n * 8); const int64_t* d = (const int64_t*)(pd + o); o += (size_t)n; return d; };
+    bd.node_ids = put(bh->node_ids, U); bd.n_nodes = U;
+    bd.head_local = put(bh->head_local, B);
+    bd.tail_local = put(bh->tail_local, B);
+    bd.rel_ids = put(bh->rel_ids, B);
+    bd.neg_ids = put(bh->neg_ids, Nn);
+    size_t wbytes = 0;
+    if (bh->edge_weight) {
+      size_t woff = align_up(n64 * 8);
+      memcpy(h->pin + woff, bh->edge_weight, (size_t)B * 4);
+      bd.edge_weight = (const float*)(h->dev_stage + woff);
+      wbytes = woff + (size_t)B * 4;
+    }
+    size_t copy_bytes = bh->edge_weight ? wbytes : n64 * 8;
+    KGE_CUDA_OK(cudaMemcpyAsync(h->dev_stage, h->pin, copy_bytes, cudaMemcpyHostToDevice, st));
   }
-  size_t copy_bytes = bh->edge_weight ? wbytes : n64 * 8;
-  KGE_CUDA_OK(cudaMemcpyAsync(h->dev_stage, h->pin, copy_bytes, cudaMemcpyHostToDevice, st));
   int rc = kge_step_fused(h, cfg, ent, rel, &bd, h->dev_log4, stream);
   if (rc) return rc;
   if (log4_host) KGE_CUDA_OK(cudaMemcpyAsync(log4_host, h->dev_log4, 4 * sizeof(float), cudaMemcpyDeviceToHost, st));

@@ -206,8 +206,10 @@ def test_gather_bit_exact_and_unfused_ops():
     np.testing.assert_allclose(tab2.state_shards[0].cpu().numpy(), s2.numpy(), rtol=2e-5, atol=1e-9)
 
 
-def test_host_entry_point_and_repeat_steps():
-    """kge_step_fused_host (pinned staging + H2D/D2H) over several alternating steps vs the oracle."""
+@pytest.mark.parametrize("pinned", [False, True])
+def test_host_entry_point_and_repeat_steps(pinned):
+    """kge_step_fused_host over several alternating steps vs the oracle: pageable host arrays go through the
+    library's pinned staging buffer, page-locked ones are DMA'd directly."""
     hp = ko.Hyper(model="DistMult", hidden_dim=48, gamma=12.0, lr=0.1, reg_coef=1e-6, adversarial=True)
     ent, es, rel, rs = ko.init_tables(hp, 800, 9, seed=9)
     eng, (e, e_s, r, r_s) = _engine(hp, ent, es, rel, rs)
@@ -217,8 +219,8 @@ def test_host_entry_point_and_repeat_steps():
         si, C = _random_step(hp, 800, 9, 96, 32, 32, neg_head, seed=100 + step)
         fb = ko.train_step(hp, o[0], o[1], o[2], o[3], si["node_ids"], si["head_local"], si["tail_local"],
                            si["rel_ids"], si["neg_ids"], C, 32, 32, neg_head)
-        log = eng.step_host(si["node_ids"], si["head_local"], si["tail_local"], si["rel_ids"], si["neg_ids"], 32, 32,
-                            neg_head)
+        hb = [si[k].pin_memory() if pinned else si[k] for k in ("node_ids", "head_local", "tail_local", "rel_ids", "neg_ids")]
+        log = eng.step_host(hb[0], hb[1], hb[2], hb[3], hb[4], 32, 32, neg_head)
         eng.sync()
         np.testing.assert_allclose(log.numpy()[2], fb["log"]["loss"], rtol=5e-5)
     np.testing.assert_allclose(e.cpu().numpy(), o[0].numpy(), rtol=2e-4, atol=1e-6)
