@@ -128,3 +128,64 @@ def test_cli_trains_and_saves_reference_layout(tmp_path):
     cfg = json.load(open(os.path.join(out, "config.json")))
     assert cfg["model_name"] == "DistMult" and cfg["hidden_dim"] == 8 and "emp_file" in cfg
     np.testing.assert_array_equal(ent, m.entity_emb.emb.cpu().numpy())
+
+
+def _planted_graph(n_ent, n_rel, n_train, n_test, d, seed):
+    """Triples with learnable structure: tail = the entity nearest to head + relation in a hidden TransE space."""
+    rng = np.random.default_rng(seed)
+    E, R = rng.normal(size=(n_ent, d)), rng.normal(size=(n_rel, d)) * 0.7
+    h = rng.integers(0, n_ent, n_train + n_test)
+    r = rng.integers(0, n_rel, n_train + n_test)
+    tgt = E[h] + R[r]
+    t = np.array([int(np.argmin(((E - x) ** 2).sum(1))) for x in tgt])
+    tr = (h[:n_train], r[:n_train], t[:n_train])
+    te = (h[n_train:], r[n_train:], t[n_train:])
+    return tr, te
+
+
+def test_mrr_parity_at_equal_step_count():
+    """north_star: MRR within 1e-3 of the reference at equal step count.  Both sides start from the same tables and
+    consume the same seeded index stream for 150 steps (tail/head alternation); MRR (unfiltered, all entities as
+    candidates, both corruption sides) of held-out triples is then computed on each side with its own code path."""
+    from dglke_b200.general_models import KEModel
+    from dglke_b200.graph import TripleSampler, eval_batches
+    n_ent, n_rel, d, B, N, steps = 500, 8, 32, 200, 50, 150
+    tr, te = _planted_graph(n_ent, n_rel, 4000, 200, 8, seed=0)
+    args = _args(lr=0.1, neg_adversarial_sampling=True, regularization_coef=1e-7)
+    m = KEModel(args, "TransE_l2", n_ent, n_rel, d, 6.0)
+    hp = ko.Hyper(model="TransE_l2", hidden_dim=d, gamma=6.0, lr=0.1, reg_coef=1e-7, adversarial=True)
+    ent, rel = m.entity_emb.emb.cpu().clone(), m.relation_emb.emb.cpu().clone()
+    es, rs = th.zeros(n_ent), th.zeros(n_rel)
+    s1 = TripleSampler(tr[0], tr[1], tr[2], n_ent, n_rel, B, N, seed=3)
+    s2 = TripleSampler(tr[0], tr[1], tr[2], n_ent, n_rel, B, N, seed=3)
+    for _ in range(steps):
+        pg, ng = next(s1)
+        loss, log = m.forward(pg, ng, 0)
+        loss.backward()
+        m.update(0)
+        pg2, ng2 = next(s2)
+        hh, tt = pg2.all_edges()
+        ko.train_step(hp, ent, es, rel, rs, pg2.ndata["id"], hh, tt, pg2.edata["id"], ng2.ndata["id"], ng2.num_chunks,
+                      ng2.chunk_size, ng2.neg_sample_size, ng2.neg_head)
+
+    def oracle_mrr():
+        rr = []
+        H, R, T = (th.from_numpy(x) for x in te)
+        h, r, t = ent[H], rel[R], ent[T]
+        pos = ko.positive_score(hp, h, r, t)
+        for neg_head in (True, False):
+            neg = th.cat([ko.negative_score(hp, ent if neg_head else h[i:i + 1], r[i:i + 1],
+                                            t[i:i + 1] if neg_head else ent, 1, 1, n_ent, neg_head).reshape(1, -1)
+                          for i in range(len(H))])
+            rr += (1.0 / ko.rank_of_positive(pos, neg).double()).tolist()
+        return float(np.mean(rr))
+
+    logs = []
+    for neg_head in (True, False):
+        for pg, ng in eval_batches(te[0], te[1], te[2], n_ent, 50, neg_head):
+            m.forward_test(pg, ng, logs, 0)
+    mrr_gpu = float(np.mean([l["MRR"] for l in logs]))
+    mrr_ref = oracle_mrr()
+    print("MRR gpu %.5f oracle %.5f" % (mrr_gpu, mrr_ref))
+    assert mrr_ref > 0.05, "the planted graph should be learnable (got %.4f)" % mrr_ref
+    assert abs(mrr_gpu - mrr_ref) <= 1e-3, (mrr_gpu, mrr_ref)
