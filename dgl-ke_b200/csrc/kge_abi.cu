@@ -46,7 +46,6 @@ struct kge_context {
   long long launches = 0;
   int engine = -1;
   int rel_deferred = 0;
-  int fuse_loss = 0;       // score epilogue computes the loss (KGE_B200_FUSE_LOSS=1): slower with 4 epilogue warps, kept for study
   // device arena (grown on demand, never inside a graph capture)
   char* arena = nullptr;
   size_t arena_bytes = 0;
@@ -60,6 +59,9 @@ struct kge_context {
   float* red_partial = nullptr;      // k_reduce_log partials + ticket (persistent, zero-initialised once)
   size_t stage_bytes = 0;
   float* dev_log4 = nullptr;
+  // side stream: small latency-bound reductions (colsum, log scalars) run beside the gradient GEMMs
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_colsum = nullptr, ev_log = nullptr;
   // last step (for kge_update / kge_debug_read)
   StepParams last_p{};
   StepWs last_w{};
@@ -242,8 +244,7 @@ void launch_rescal_chain(const LaunchCtx&, const StepParams&, const TableView& e
                          const BatchView&, const StepWs&);
 // tcgen05 engine (kge_umma.cu): returns false when the shape is not handled (caller falls back to engine 0)
 bool umma_supported(const StepParams&);
-int umma_score(const LaunchCtx&, const StepParams&, const StepWs&, bool fuse_loss, const float* edge_w, char* err,
-               size_t errlen);
+int umma_score(const LaunchCtx&, const StepParams&, const StepWs&, char* err, size_t errlen);
 int umma_grad(const LaunchCtx&, const StepParams&, const StepWs&, bool side_b, char* err, size_t errlen);
 }  // namespace kge
 
@@ -270,9 +271,15 @@ KGE_API int kge_create(int device, kge_handle_t* out) {
   if (!h) return fail(KGE_ERR_NOMEM, "out of host memory");
   h->device = device;
   h->num_sms = prop.multiProcessorCount;
-  { const char* e = getenv("KGE_B200_FUSE_LOSS"); h->fuse_loss = (e && e[0] == '1') ? 1 : 0; }
+
   DeviceGuard g(device);
   if (cudaMalloc(&h->dev_log4, 4 * sizeof(float)) != cudaSuccess) { delete h; return fail(KGE_ERR_NOMEM, "cudaMalloc failed"); }
+  if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_colsum, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_log, cudaEventDisableTiming) != cudaSuccess) {
+    delete h; return fail(KGE_ERR_CUDA, "stream/event creation failed");
+  }
   if (cudaMalloc(&h->red_partial, 256 * sizeof(float)) != cudaSuccess || cudaMemset(h->red_partial, 0, 256 * sizeof(float)) != cudaSuccess) {
     delete h; return fail(KGE_ERR_NOMEM, "cudaMalloc failed");
   }
@@ -288,6 +295,10 @@ KGE_API int kge_destroy(kge_handle_t h) {
   if (h->dev_stage) cudaFree(h->dev_stage);
   if (h->pin) cudaFreeHost(h->pin);
   if (h->dev_log4) cudaFree(h->dev_log4);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_colsum) cudaEventDestroy(h->ev_colsum);
+  if (h->ev_log) cudaEventDestroy(h->ev_log);
+  if (h->side) cudaStreamDestroy(h->side);
   if (h->red_partial) cudaFree(h->red_partial);
   if (h->prof.created)
     for (int i = 0; i < Profiler::kMax; ++i) { cudaEventDestroy(h->prof.ev0[i]); cudaEventDestroy(h->prof.ev1[i]); }
@@ -358,7 +369,7 @@ static bool use_umma(kge_context* h, const StepParams& p) {
 
 static int run_score(kge_context* h, const LaunchCtx& c, const StepParams& p, const StepWs& w) {
   if (use_umma(h, p)) {
-    int rc = umma_score(c, p, w, false, nullptr, g_err, sizeof(g_err));
+    int rc = umma_score(c, p, w, g_err, sizeof(g_err));
     if (rc) return rc;
   } else {
     launch_score(c, p, w);
@@ -475,24 +486,35 @@ KGE_API int kge_forward_backward(kge_handle_t h, const kge_step_cfg_t* cfg, cons
   launch_gather_nodes(c, p, ve, b, w);      // pos_g.ndata['emb'] = entity_emb(pos_g.ndata['id'])  (general_models.py:548)
   if (p.model == KGE_RESCAL) launch_rescal_prep(c, p, ve, vr, b, w);
   else launch_prep(c, p, ve, vr, b, w);
-  if (h->fuse_loss && use_umma(h, p) && p.Ns <= 256) {
-    // score GEMM with the loss fused into its epilogue (one accumulator row = one positive's negatives)
-    launch_wbar(c, p, b.edge_weight, w);
-    if ((rc = umma_score(c, p, w, true, b.edge_weight, g_err, sizeof(g_err)))) return rc;
-    launch_reduce_log(c, p, b.edge_weight, w, log4 ? log4 : h->dev_log4, true);
-  } else {
-    if ((rc = run_score(h, c, p, w))) return rc;
-    launch_loss(c, p, w.pos, w.S, b.edge_weight, w, log4 ? log4 : h->dev_log4, true);
+  if ((rc = run_score(h, c, p, w))) return rc;
+  launch_wbar(c, p, b.edge_weight, w);
+  launch_loss_rows(c, p, w.pos, w.S, b.edge_weight, w);
+  // fork: colsum (needed by grad_b only) and the log scalars (needed by nobody on the device) leave the critical
+  // path and run on the side stream beside the gradient GEMMs; both joins happen before this call returns, so
+  // callers (and CUDA-graph capture) still see a single-stream contract
+  cudaStream_t main_st = (cudaStream_t)stream;
+  KGE_CUDA_OK(cudaEventRecord(h->ev_fork, main_st));
+  KGE_CUDA_OK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+  {
+    LaunchCtx cs = c;
+    cs.stream = h->side;
+    launch_colsum(cs, p, w);
+    KGE_CUDA_OK(cudaEventRecord(h->ev_colsum, h->side));
+    launch_reduce_log(cs, p, b.edge_weight, w, log4 ? log4 : h->dev_log4, true);
+    KGE_CUDA_OK(cudaEventRecord(h->ev_log, h->side));
   }
   if (use_umma(h, p)) {
     if ((rc = umma_grad(c, p, w, false, g_err, sizeof(g_err)))) return rc;
+    KGE_CUDA_OK(cudaStreamWaitEvent(main_st, h->ev_colsum, 0));
     if ((rc = umma_grad(c, p, w, true, g_err, sizeof(g_err)))) return rc;
   } else {
     launch_grad_a(c, p, w);
+    KGE_CUDA_OK(cudaStreamWaitEvent(main_st, h->ev_colsum, 0));
     launch_grad_b(c, p, w);
   }
   if (p.model == KGE_RESCAL) launch_rescal_chain(c, p, ve, vr, b, w);
   else launch_chain(c, p, ve, vr, b, w);
+  KGE_CUDA_OK(cudaStreamWaitEvent(main_st, h->ev_log, 0));
   KGE_CUDA_OK(cudaGetLastError());
   h->last_p = p; h->last_w = w; h->last_b = b; h->last_ent = ve; h->last_rel = vr; h->have_last = true;
   h->ng_dirty = true;

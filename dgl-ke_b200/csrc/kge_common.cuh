@@ -283,6 +283,8 @@ void launch_score(const LaunchCtx&, const StepParams&, const StepWs&);
 void launch_loss(const LaunchCtx&, const StepParams&, const float* pos, const float* S, const float* w,
                  const StepWs&, float* log4, bool want_reg);
 void launch_wbar(const LaunchCtx&, const StepParams&, const float* w, const StepWs&);
+void launch_loss_rows(const LaunchCtx&, const StepParams&, const float* pos, const float* S, const float* w, const StepWs&);
+void launch_colsum(const LaunchCtx&, const StepParams&, const StepWs&);
 void launch_reduce_log(const LaunchCtx&, const StepParams&, const float* w, const StepWs&, float* log4, bool want_reg);
 void launch_grad_a(const LaunchCtx&, const StepParams&, const StepWs&);
 void launch_grad_b(const LaunchCtx&, const StepParams&, const StepWs&);

@@ -351,6 +351,20 @@ void launch_prep_dense(const LaunchCtx& c, const StepParams& p, const float* hea
 // One warp per positive i: reads its Ns negative scores, writes the backward coefficients
 //   V_ij = dL/dneg_ij (bilinear, l1, RotatE)  |  dL/dneg_ij / dist_ij (TransE_l2),
 // the per-row loss terms, dL/dpos_i, and (TransE_l2) sum_j V_ij.
+// per-element math of k_loss: coefficient for the backward contraction + the loss term (loss.py:69-98)
+struct LossRow {
+  float w_i, inv2B, T, mx, den, uni;
+  int adversarial, l2;
+};
+__device__ __forceinline__ float loss_elem(const LossRow& r, float sc, float dist, float& nls, float& rs) {
+  const float pij = r.adversarial ? expf(sc * r.T - r.mx) / r.den : r.uni;
+  nls += pij * (softplusf(sc) * r.w_i);
+  const float g = pij * sigmoidf(sc) * r.w_i * r.inv2B;       // dL/dneg_ij
+  float coef = g;
+  if (r.l2) { coef = g / dist; rs += coef; }                  // dist = |a-b| from the score kernel
+  return coef;
+}
+
 __global__ void __launch_bounds__(kRowBlock) k_loss(StepParams p, const float* __restrict__ pos,
                                                      const float* __restrict__ S, const float* __restrict__ wt,
                                                      const float* __restrict__ wbar, float* __restrict__ V,
@@ -362,31 +376,64 @@ __global__ void __launch_bounds__(kRowBlock) k_loss(StepParams p, const float* _
   const int lane = threadIdx.x & 31;
   const float* s = S + i * (long long)p.Ns;
   float* v = V + i * (long long)p.Ns;
-  const float w_i = wt ? wt[i] : 1.f;
-  const float inv2B = 0.5f / (float)p.B;
-  float mx = -INFINITY, den = 1.f;
-  if (p.adversarial) {
-    for (int j = lane; j < p.Ns; j += kWarp) mx = fmaxf(mx, s[j] * p.adv_temperature);
-    mx = warp_max(mx);
-    float d = 0.f;
-    for (int j = lane; j < p.Ns; j += kWarp) d += expf(s[j] * p.adv_temperature - mx);
-    den = warp_sum(d);
-  }
+  LossRow r;
+  r.w_i = wt ? wt[i] : 1.f;
+  r.inv2B = 0.5f / (float)p.B;
+  r.T = p.adv_temperature; r.mx = -INFINITY; r.den = 1.f; r.uni = 1.f / (float)p.Ns;
+  r.adversarial = p.adversarial; r.l2 = (p.model == KGE_TRANSE_L2);
+  const long long chunk = i / p.Cs;
+  const int il = (int)(i % p.Cs), nblk = slab_blocks(p.Ns);
   float nls = 0.f, rs = 0.f;
-  const float uni = 1.f / (float)p.Ns;
-  for (int j = lane; j < p.Ns; j += kWarp) {
-    float sc = s[j];
-    float pij = p.adversarial ? expf(sc * p.adv_temperature - mx) / den : uni;
-    nls += pij * (softplusf(sc) * w_i);
-    float g = pij * sigmoidf(sc) * w_i * inv2B;       // dL/dneg_ij
-    float coef = g;
-    if (p.model == KGE_TRANSE_L2) { float dist = v[j]; coef = g / dist; rs += coef; }   // v[j] = |a-b| from k_score
-    v[j] = coef;
-    if (Vhi) {
-      float hh, ll;
-      split_tf32(coef, hh, ll);
-      const long long o = slab_off(i / p.Cs, slab_blocks(p.Ns), p.Cs, (int)(i % p.Cs), j);
-      Vhi[o] = hh; Vlo[o] = ll;
+  if (p.Ns <= 8 * kWarp) {
+    // row in registers: every global load of the row is issued up front, the three passes run on registers
+    float sc[8], ds[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int j = lane + kWarp * q;
+      sc[q] = (j < p.Ns) ? s[j] : -INFINITY;
+      ds[q] = (r.l2 && j < p.Ns) ? v[j] : 1.f;
+    }
+    if (p.adversarial) {
+      float mx = -INFINITY;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) mx = fmaxf(mx, sc[q] * r.T);     // padding contributes -inf
+      r.mx = warp_max(mx);
+      float d = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) if (lane + kWarp * q < p.Ns) d += expf(sc[q] * r.T - r.mx);
+      r.den = warp_sum(d);
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int j = lane + kWarp * q;
+      if (j >= p.Ns) continue;
+      const float coef = loss_elem(r, sc[q], ds[q], nls, rs);
+      v[j] = coef;
+      if (Vhi) {
+        float hh, ll;
+        split_tf32(coef, hh, ll);
+        const long long o = slab_off(chunk, nblk, p.Cs, il, j);
+        Vhi[o] = hh; Vlo[o] = ll;
+      }
+    }
+  } else {
+    if (p.adversarial) {
+      float mx = -INFINITY;
+      for (int j = lane; j < p.Ns; j += kWarp) mx = fmaxf(mx, s[j] * r.T);
+      r.mx = warp_max(mx);
+      float d = 0.f;
+      for (int j = lane; j < p.Ns; j += kWarp) d += expf(s[j] * r.T - r.mx);
+      r.den = warp_sum(d);
+    }
+    for (int j = lane; j < p.Ns; j += kWarp) {
+      const float coef = loss_elem(r, s[j], r.l2 ? v[j] : 1.f, nls, rs);
+      v[j] = coef;
+      if (Vhi) {
+        float hh, ll;
+        split_tf32(coef, hh, ll);
+        const long long o = slab_off(chunk, nblk, p.Cs, il, j);
+        Vhi[o] = hh; Vlo[o] = ll;
+      }
     }
   }
   nls = warp_sum(nls);
@@ -396,8 +443,8 @@ __global__ void __launch_bounds__(kRowBlock) k_loss(StepParams p, const float* _
     float wb = wt ? *wbar : 1.f;        // loss.py:75,82: [B] * [B,1] -> mean(pl) * mean(w)
     pl[i] = softplusf(-ps);
     nl[i] = nls;
-    gpos[i] = -sigmoidf(-ps) * wb * inv2B;
-    if (p.model == KGE_TRANSE_L2) rowsum[i] = rs;
+    gpos[i] = -sigmoidf(-ps) * wb * r.inv2B;
+    if (r.l2) rowsum[i] = rs;
   }
 }
 
@@ -498,12 +545,21 @@ void launch_reduce_log(const LaunchCtx& c, const StepParams& p, const float* wt,
                wt ? w.wbar : nullptr, w.red_partial, w.red_ticket, log4);
 }
 
+void launch_loss_rows(const LaunchCtx& c, const StepParams& p, const float* pos, const float* S, const float* wt,
+                      const StepWs& w) {
+  KGE_LAUNCH(c, k_loss, ceil_div(p.B, kWarpsPerBlock), kRowBlock, 0, p, pos, S, wt, w.wbar, w.V, w.gpos, w.rowsum,
+             w.pl, w.nl, w.Vhi, w.Vlo);
+}
+
+void launch_colsum(const LaunchCtx& c, const StepParams& p, const StepWs& w) {
+  if (p.model == KGE_TRANSE_L2) KGE_LAUNCH(c, k_colsum, dim3(ceil_div(p.Ns, 32), p.C), 256, 0, p, w.V, w.colsum);
+}
+
 void launch_loss(const LaunchCtx& c, const StepParams& p, const float* pos, const float* S, const float* wt,
                  const StepWs& w, float* log4, bool want_reg) {
   launch_wbar(c, p, wt, w);
-  KGE_LAUNCH(c, k_loss, ceil_div(p.B, kWarpsPerBlock), kRowBlock, 0, p, pos, S, wt, w.wbar, w.V, w.gpos, w.rowsum,
-             w.pl, w.nl, w.Vhi, w.Vlo);
-  if (p.model == KGE_TRANSE_L2) KGE_LAUNCH(c, k_colsum, dim3(ceil_div(p.Ns, 32), p.C), 256, 0, p, w.V, w.colsum);
+  launch_loss_rows(c, p, pos, S, wt, w);
+  launch_colsum(c, p, w);
   launch_reduce_log(c, p, wt, w, log4, want_reg);
 }
 

@@ -5,12 +5,13 @@
 //   GEMM2  GA[c] = V[c]   . Bn[c]       (Cs x D,  K = Ns)   A K-major, B MN-major
 //   GEMM3  GB[c] = V[c]^T . A[c]        (Ns x D,  K = Cs)   both operands MN-major
 //
-// fp32 fidelity on TF32 tensor cores: every operand is split x = hi + lo (both rounded to TF32) by
-// k_split_tf32 and each k-step issues hi*hi + hi*lo + lo*hi (3xTF32), accumulating in fp32 in TMEM.
+// fp32 fidelity on TF32 tensor cores: every operand is split x = hi + lo (both rounded to TF32) by its
+// producer (k_prep / k_loss, kge_common.cuh:split_tf32) and each k-step issues hi*hi + hi*lo + lo*hi (3xTF32), accumulating in fp32 in TMEM.
 //
-// One CTA per 128 x Nt output tile (Nt <= 256): warp 0 = TMA producer (cp.async.bulk.tensor, 128B
-// swizzle, mbarrier pipeline), warp 1 = TMEM allocator + single-thread tcgen05.mma issuer,
-// warps 2-5 = epilogue (tcgen05.ld 32x32b: one accumulator row per thread).
+// One CTA per 128 x Nt output tile (Nt <= 256): warp 0 = TMA producer (cp.async.bulk.tensor over the
+// contiguous slab layout, 128B swizzle, 2-stage mbarrier pipeline), warp 1 = TMEM allocator + single-thread
+// tcgen05.mma issuer, warps 2-9 = epilogue (tcgen05.ld 32x32b: one accumulator row per thread, two warps
+// per TMEM lane quarter splitting the columns).
 #include <cuda.h>
 #include <cstdio>
 #include <cstdlib>
@@ -132,20 +133,11 @@ struct GemmArgs {
   const float* a2;       // SCORE l2
   const float* b2;
   const float* colsum;   // GB l2
-  // fused loss epilogue of the score GEMM (k_loss semantics, loss.py:69-98)
-  int fuse_loss, adversarial;
-  float adv_temperature, inv2B;
-  const float* pos;      // [B] positive scores
-  const float* wt;       // [B] edge weights or null
-  const float* wbar;     // [1] mean edge weight (with wt)
-  float *Vhi, *Vlo;      // [B, Ns] backward coefficients, TF32 split
-  float *rowsum, *gpos, *pl, *nl;   // [B]
-  float* colsum_acc;     // [Nn] zeroed by the host; TransE_l2 only
   unsigned long long* dbg;   // optional per-CTA timestamps (KGE_B200_UMMA_TIMING=1): start, first full, mainloop end, end
 };
 
 // smem layout per stage: [A_hi | A_lo | B_hi | B_lo], each tile 1024-byte aligned
-template <bool A_MN, bool B_MN, int MODE, bool FUSE>
+template <bool A_MN, bool B_MN, int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 k_umma_gemm(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
             const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, GemmArgs g) {
@@ -263,7 +255,7 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CU
       umma_commit(&tmem_full_bar);           // accumulator complete
     }
   } else {
-    // ===================== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====================
+    // ===================== epilogue: warps 2..9, TMEM lane quarter = warp % 4 =====================
     if (MODE == G_SCORE && g.model == KGE_TRANSE_L2) {
       // stage the tile's |b_j|^2 once (every row of the tile needs all of them) while the mainloop runs
       const int et = threadIdx.x - 64;                 // 0..255
@@ -274,124 +266,18 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CU
     if (g.dbg && threadIdx.x == 64) g.dbg[cta_lin * 6 + 2] = gtime();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int q = warp & 3;
-    // two warps share a TMEM lane quarter and split the tile's columns (the fused-loss variant needs whole rows:
-    // there only the first warp of each quarter works)
+    // two warps share a TMEM lane quarter and split the tile's columns
     const int ehalf = (warp - 2) >> 2;
-    const int Nt_half = FUSE ? Nt : (((Nt >> 1) + 15) & ~15);
+    const int Nt_half = ((Nt >> 1) + 15) & ~15;
     const int col_begin = ehalf ? Nt_half : 0;
-    const int col_end = FUSE ? (ehalf ? 0 : Nt) : (ehalf ? Nt : Nt_half);
+    const int col_end = ehalf ? Nt : Nt_half;
     const int row_in_tile = q * 32 + lane;                 // accumulator row (M index) owned by this thread
     const int m = m0 + row_in_tile;
     const int Mrows = g.rowsA_per_chunk;
     const bool row_ok = m < Mrows;
     const uint32_t taddr_row = tmem_base + ((uint32_t)(q * 32) << 16);
     // Nt is a multiple of 16; Ns, D are multiples of 8: every 8-column group is entirely valid or entirely padding
-    if (MODE == G_SCORE && FUSE) {
-      if (ehalf == 0) {
-      // ---- score + loss fused: this thread owns row i of the chunk's [Cs x Ns] score tile (single N tile)
-      const long long gi = (long long)c * g.Cs + (row_ok ? m : 0);
-      const bool l2 = g.model == KGE_TRANSE_L2;
-      const float a2v = l2 ? g.a2[gi] : 0.f;
-      const float w_i = (g.wt && row_ok) ? g.wt[gi] : 1.f;
-      const float T = g.adv_temperature;
-      // score (and distance) of 8 columns starting at j from 8 accumulator values
-      auto scores8 = [&](const float* acc, int j, float* sc, float* d) {
-        if (l2) {
-          float4 bq0 = *reinterpret_cast<const float4*>(&b2s[j]), bq1 = *reinterpret_cast<const float4*>(&b2s[j + 4]);
-          const float bb[8] = {bq0.x, bq0.y, bq0.z, bq0.w, bq1.x, bq1.y, bq1.z, bq1.w};
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            float sq = fmaf(-2.f, acc[e], bb[e]) + a2v;
-            d[e] = sqrtf(fmaxf(sq, 1e-30f));
-            sc[e] = g.gamma - d[e];
-          }
-        } else {
-#pragma unroll
-          for (int e = 0; e < 8; ++e) { sc[e] = acc[e]; d[e] = 1.f; }
-        }
-      };
-      float mx = -INFINITY, den = 1.f;
-      if (g.adversarial) {
-        for (int col = 0; col < Nt; col += 16) {
-          float v[16];
-          tmem_ld16(taddr_row + col, v);
-#pragma unroll
-          for (int h8 = 0; h8 < 2; ++h8) {
-            const int j = col + h8 * 8;
-            if (j >= g.Ns) continue;
-            float sc[8], d[8];
-            scores8(v + h8 * 8, j, sc, d);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) mx = fmaxf(mx, sc[e] * T);
-          }
-        }
-        float dsum = 0.f;
-        for (int col = 0; col < Nt; col += 16) {
-          float v[16];
-          tmem_ld16(taddr_row + col, v);
-#pragma unroll
-          for (int h8 = 0; h8 < 2; ++h8) {
-            const int j = col + h8 * 8;
-            if (j >= g.Ns) continue;
-            float sc[8], d[8];
-            scores8(v + h8 * 8, j, sc, d);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) dsum += expf(sc[e] * T - mx);
-          }
-        }
-        den = dsum;
-      }
-      const float uni = 1.f / (float)g.Ns;
-      float nls = 0.f, rs = 0.f;
-      for (int col = 0; col < Nt; col += 16) {
-        float v[16];
-        tmem_ld16(taddr_row + col, v);
-#pragma unroll
-        for (int h8 = 0; h8 < 2; ++h8) {
-          const int j = col + h8 * 8;
-          if (j >= g.Ns) continue;                     // uniform across the warp
-          float sc[8], d[8], cf[8];
-          scores8(v + h8 * 8, j, sc, d);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            float pij = g.adversarial ? expf(sc[e] * T - mx) / den : uni;
-            nls += pij * (softplusf(sc[e]) * w_i);
-            float gg = pij * sigmoidf(sc[e]) * w_i * g.inv2B;
-            cf[e] = l2 ? gg / d[e] : gg;
-            if (!row_ok) cf[e] = 0.f;
-            rs += cf[e];
-          }
-          if (row_ok) {
-            float4 h0, l0, h1, l1;
-            split_tf32_4(make_float4(cf[0], cf[1], cf[2], cf[3]), h0, l0);
-            split_tf32_4(make_float4(cf[4], cf[5], cf[6], cf[7]), h1, l1);
-            const long long o = gi * g.Ns + j;
-            const long long ov = slab_off(c, slab_blocks(g.Ns), g.Cs, m, j);
-            st4(g.Vhi + ov, h0); st4(g.Vhi + ov + 4, h1);
-            st4(g.Vlo + ov, l0); st4(g.Vlo + ov + 4, l1);
-            st4(g.out + o, make_float4(sc[0], sc[1], sc[2], sc[3]));
-            st4(g.out + o + 4, make_float4(sc[4], sc[5], sc[6], sc[7]));
-          }
-          if (l2) {
-            // colsum[c, j] += sum over the 32 rows of this warp (then one atomic per column and warp)
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              float t = warp_sum(cf[e]);
-              if (lane == e) atomicAdd(g.colsum_acc + (long long)c * g.Ns + j + e, t);
-            }
-          }
-        }
-      }
-      if (row_ok) {
-        const float ps = g.pos[gi];
-        const float wb = g.wt ? *g.wbar : 1.f;
-        g.pl[gi] = softplusf(-ps);
-        g.nl[gi] = nls;
-        g.gpos[gi] = -sigmoidf(-ps) * wb * g.inv2B;
-        if (l2) g.rowsum[gi] = rs;
-      }
-      }
-    } else if (MODE == G_SCORE) {
+    if (MODE == G_SCORE) {
       const long long gi = (long long)c * g.Cs + m;
       const bool l2 = g.model == KGE_TRANSE_L2;
       const float a2v = (row_ok && l2) ? g.a2[gi] : 0.f;
@@ -491,23 +377,6 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CU
   }
 }
 
-// x -> (hi, lo): hi = rna_tf32(x), lo = rna_tf32(x - hi)
-__global__ void k_split_tf32(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, long long n4) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (; i < n4; i += stride) {
-    float4 v = ld4(x + 4 * i), h, l;
-#define KGE_SPLIT(c_)                                                            \
-    { uint32_t hb; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v.c_));       \
-      h.c_ = __uint_as_float(hb); float r = v.c_ - h.c_; uint32_t lb;            \
-      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(r)); l.c_ = __uint_as_float(lb); }
-    KGE_SPLIT(x) KGE_SPLIT(y) KGE_SPLIT(z) KGE_SPLIT(w)
-#undef KGE_SPLIT
-    st4(hi + 4 * i, h);
-    st4(lo + 4 * i, l);
-  }
-}
-
 // ---- host side ----------------------------------------------------------------------------------
 typedef CUresult (*encode_fn_t)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                 const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -580,25 +449,27 @@ size_t smem_bytes_for(int Nt, bool b_mn) {
   return (size_t)kStages * (2 * kTileM * 128 + 2 * b) + 1024;
 }
 
-template <bool A_MN, bool B_MN, int MODE, bool FUSE>
+template <bool A_MN, bool B_MN, int MODE>
 int launch_gemm(const LaunchCtx& c, const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh,
                 const CUtensorMap& bl, const GemmArgs& g, int ntiles_n, int Nt_max, char* err, size_t errlen) {
   size_t smem = smem_bytes_for(Nt_max, B_MN);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_umma_gemm<A_MN, B_MN, MODE, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  static bool attr_set[64] = {};          // the opt-in shared-memory size is a per-device function attribute
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(k_umma_gemm<A_MN, B_MN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) { snprintf(err, errlen, "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return KGE_ERR_CUDA; }
-    attr_set = true;
+    attr_set[dev] = true;
   }
   dim3 grid(ntiles_n, (g.rowsA_per_chunk + kTileM - 1) / kTileM, g.C);
-  const char* nm = MODE == G_SCORE ? (FUSE ? "k_umma_gemm<score+loss S=A.Bn^T>" : "k_umma_gemm<score S=A.Bn^T>")
+  const char* nm = MODE == G_SCORE ? "k_umma_gemm<score S=A.Bn^T>"
                                    : (MODE == G_GA ? "k_umma_gemm<grad_a GA=V.Bn>" : "k_umma_gemm<grad_b GB=V^T.A>");
   static const bool timing = getenv("KGE_B200_UMMA_TIMING") != nullptr;
   GemmArgs ga = g;
   unsigned long long* dbg = nullptr;
   const size_t nct = (size_t)grid.x * grid.y * grid.z;
   if (timing) { cudaMalloc(&dbg, nct * 6 * sizeof(unsigned long long)); ga.dbg = dbg; }
-  KGE_LAUNCH_NAMED(c, nm, (k_umma_gemm<A_MN, B_MN, MODE, FUSE>), grid, kThreads, smem, ah, al, bh, bl, ga);
+  KGE_LAUNCH_NAMED(c, nm, (k_umma_gemm<A_MN, B_MN, MODE>), grid, kThreads, smem, ah, al, bh, bl, ga);
   if (timing) {
     cudaStreamSynchronize(c.stream);
     unsigned long long* hbuf = (unsigned long long*)malloc(nct * 6 * sizeof(unsigned long long));
@@ -623,14 +494,6 @@ int launch_gemm(const LaunchCtx& c, const CUtensorMap& ah, const CUtensorMap& al
   return KGE_OK;
 }
 
-void split(const LaunchCtx& c, const float* x, float* hi, float* lo, long long n) {
-  long long n4 = n / 4;
-  int grid = (int)((n4 + 255) / 256);
-  if (grid > c.num_sms * 16) grid = c.num_sms * 16;
-  if (grid < 1) grid = 1;
-  KGE_LAUNCH(c, k_split_tf32, grid, 256, 0, x, hi, lo, n4);
-}
-
 }  // namespace
 
 bool umma_supported(const StepParams& p) {
@@ -639,8 +502,7 @@ bool umma_supported(const StepParams& p) {
 }
 
 // S = A . Bn^T  (+ TransE_l2 distance epilogue)
-int umma_score(const LaunchCtx& c, const StepParams& p, const StepWs& w, bool fuse_loss, const float* edge_w, char* err,
-               size_t errlen) {
+int umma_score(const LaunchCtx& c, const StepParams& p, const StepWs& w, char* err, size_t errlen) {
   // operands arrive already split: k_prep writes A / Bn as TF32 hi/lo, k_loss writes V hi/lo
   const int Nt_max = p.Ns >= 256 ? 256 : ((p.Ns + 15) & ~15);
   CUtensorMap ah, al, bh, bl;
@@ -655,18 +517,7 @@ int umma_score(const LaunchCtx& c, const StepParams& p, const StepWs& w, bool fu
   g.model = p.model; g.gamma = p.gamma; g.reg_coef = p.reg_coef; g.reg_norm = p.reg_norm;
   g.Cs = p.Cs; g.Ns = p.Ns; g.D = p.D;
   g.out = w.S; g.out2 = w.V; g.a2 = w.a2; g.b2 = w.b2; g.colsum = nullptr;
-  g.fuse_loss = (fuse_loss && p.Ns <= 256) ? 1 : 0;
-  if (g.fuse_loss) {
-    g.adversarial = p.adversarial; g.adv_temperature = p.adv_temperature; g.inv2B = 0.5f / (float)p.B;
-    g.pos = w.pos; g.wt = edge_w; g.wbar = w.wbar; g.Vhi = w.Vhi; g.Vlo = w.Vlo;
-    g.rowsum = w.rowsum; g.gpos = w.gpos; g.pl = w.pl; g.nl = w.nl; g.colsum_acc = w.colsum;
-    if (p.model == KGE_TRANSE_L2) {
-      cudaError_t e = cudaMemsetAsync(w.colsum, 0, (size_t)p.Nn * sizeof(float), c.stream);
-      if (e != cudaSuccess) { snprintf(err, errlen, "cudaMemsetAsync(colsum): %s", cudaGetErrorString(e)); return KGE_ERR_CUDA; }
-    }
-  }
-  if (g.fuse_loss) return launch_gemm<false, false, G_SCORE, true>(c, ah, al, bh, bl, g, (p.Ns + 255) / 256, Nt_max, err, errlen);
-  return launch_gemm<false, false, G_SCORE, false>(c, ah, al, bh, bl, g, (p.Ns + 255) / 256, Nt_max, err, errlen);
+  return launch_gemm<false, false, G_SCORE>(c, ah, al, bh, bl, g, (p.Ns + 255) / 256, Nt_max, err, errlen);
 }
 
 // side_b == false: GA = V . Bn ; side_b == true: G_neg = V^T . A (+ epilogue), in place over Bn
@@ -684,7 +535,7 @@ int umma_grad(const LaunchCtx& c, const StepParams& p, const StepWs& w, bool sid
       return KGE_ERR_CUDA;
     g.a_nblk = slab_blocks(p.Ns); g.a_R = p.Cs; g.b_nblk = slab_blocks(p.D); g.b_R = p.Ns;
     g.mode = G_GA; g.rowsA_per_chunk = p.Cs; g.rowsB_per_chunk = 0; g.krows_per_chunk = p.Ns; g.out = w.GA;
-    return launch_gemm<false, true, G_GA, false>(c, ah, al, bh, bl, g, (p.D + 255) / 256, Nt_max, err, errlen);
+    return launch_gemm<false, true, G_GA>(c, ah, al, bh, bl, g, (p.D + 255) / 256, Nt_max, err, errlen);
   }
   // A operand: V^T: stored V [B, Ns] = [rows = K = i][cols = M = j] MN-major; B operand: A hi/lo [B, D] MN-major
   const long long rowsV = p.B * (long long)slab_blocks(p.Ns), rowsA = p.B * (long long)slab_blocks(p.D);
@@ -693,7 +544,7 @@ int umma_grad(const LaunchCtx& c, const StepParams& p, const StepWs& w, bool sid
     return KGE_ERR_CUDA;
   g.a_nblk = slab_blocks(p.Ns); g.a_R = p.Cs; g.b_nblk = slab_blocks(p.D); g.b_R = p.Cs;
   g.mode = G_GB; g.rowsA_per_chunk = p.Ns; g.rowsB_per_chunk = 0; g.krows_per_chunk = p.Cs; g.out = w.Bn;
-  return launch_gemm<true, true, G_GB, false>(c, ah, al, bh, bl, g, (p.D + 255) / 256, Nt_max, err, errlen);
+  return launch_gemm<true, true, G_GB>(c, ah, al, bh, bl, g, (p.D + 255) / 256, Nt_max, err, errlen);
 }
 
 }  // namespace kge
