@@ -44,8 +44,8 @@ def test_kemodel_three_call_step_matches_oracle(model, de):
         for k in fb["log"]:
             np.testing.assert_allclose(log[k], fb["log"][k], rtol=5e-5, atol=1e-9)
         np.testing.assert_allclose(float(loss), fb["loss"], rtol=5e-5)
-    np.testing.assert_allclose(m.entity_emb.emb.cpu().numpy(), ent.numpy(), rtol=2e-4, atol=2e-6)
-    np.testing.assert_allclose(m.relation_emb.emb.cpu().numpy(), rel.numpy(), rtol=2e-4, atol=2e-6)
+    np.testing.assert_allclose(m.entity_emb.emb.cpu().numpy(), ent.numpy(), rtol=2e-4, atol=1e-5)
+    np.testing.assert_allclose(m.relation_emb.emb.cpu().numpy(), rel.numpy(), rtol=2e-4, atol=1e-5)
     np.testing.assert_allclose(m.entity_emb.state_sum.cpu().numpy(), es.numpy(), rtol=2e-4, atol=1e-9)
 
 
@@ -145,8 +145,9 @@ def _planted_graph(n_ent, n_rel, n_train, n_test, d, seed):
 
 def test_mrr_parity_at_equal_step_count():
     """north_star: MRR within 1e-3 of the reference at equal step count.  Both sides start from the same tables and
-    consume the same seeded index stream for 150 steps (tail/head alternation); MRR (unfiltered, all entities as
-    candidates, both corruption sides) of held-out triples is then computed on each side with its own code path."""
+    consume the same seeded index stream for 100 steps (tail/head alternation); MRR of held-out triples (all entities
+    as candidates, both corruption sides, the positive itself filtered out -- otherwise its own near-tie with the
+    positive score is a coin flip per query) is then computed on each side with its own code path."""
     from dglke_b200.general_models import KEModel
     from dglke_b200.graph import TripleSampler, eval_batches
     n_ent, n_rel, d, B, N, steps = 500, 8, 32, 200, 50, 100
@@ -177,16 +178,29 @@ def test_mrr_parity_at_equal_step_count():
             neg = th.cat([ko.negative_score(hp, ent if neg_head else h[i:i + 1], r[i:i + 1],
                                             t[i:i + 1] if neg_head else ent, 1, 1, n_ent, neg_head).reshape(1, -1)
                           for i in range(len(H))])
-            rr += (1.0 / ko.rank_of_positive(pos, neg).double()).tolist()
+            own = H if neg_head else T                       # the positive itself is not a negative
+            hit = neg >= pos.view(-1, 1)
+            hit[th.arange(len(H)), own] = False
+            rr += (1.0 / (1 + hit.sum(1)).double()).tolist()
         return float(np.mean(rr))
 
+    # GPU side: filtered ranking through forward_test (neg_g.edata['bias'] == -1 marks the filtered candidate)
+    m.args.eval_filter = True
     logs = []
     for neg_head in (True, False):
+        off = 0
         for pg, ng in eval_batches(te[0], te[1], te[2], n_ent, 50, neg_head):
+            nb = pg.number_of_edges()
+            own = th.from_numpy((te[0] if neg_head else te[2])[off:off + nb])
+            bias = th.zeros(nb, n_ent)
+            bias[th.arange(nb), own] = -1
+            ng.edata["bias"] = bias
+            off += nb
             m.forward_test(pg, ng, logs, 0)
     mrr_gpu = float(np.mean([l["MRR"] for l in logs]))
     mrr_ref = oracle_mrr()
     drift = float((m.entity_emb.emb.cpu() - ent).abs().max())
     print("MRR gpu %.5f oracle %.5f  max|entity table drift| %.3e" % (mrr_gpu, mrr_ref, drift))
+    assert drift < 1e-4, "training trajectories diverged: max |entity table difference| = %.3e" % drift
     assert mrr_ref > 0.05, "the planted graph should be learnable (got %.4f)" % mrr_ref
     assert abs(mrr_gpu - mrr_ref) <= 1e-3, (mrr_gpu, mrr_ref)
