@@ -59,9 +59,6 @@ struct kge_context {
   float* red_partial = nullptr;      // k_reduce_log partials + ticket (persistent, zero-initialised once)
   size_t stage_bytes = 0;
   float* dev_log4 = nullptr;
-  // side stream: small latency-bound reductions (colsum, log scalars) run beside the gradient GEMMs
-  cudaStream_t side = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_colsum = nullptr, ev_log = nullptr;
   // last step (for kge_update / kge_debug_read)
   StepParams last_p{};
   StepWs last_w{};
@@ -274,12 +271,7 @@ KGE_API int kge_create(int device, kge_handle_t* out) {
 
   DeviceGuard g(device);
   if (cudaMalloc(&h->dev_log4, 4 * sizeof(float)) != cudaSuccess) { delete h; return fail(KGE_ERR_NOMEM, "cudaMalloc failed"); }
-  if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&h->ev_colsum, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&h->ev_log, cudaEventDisableTiming) != cudaSuccess) {
-    delete h; return fail(KGE_ERR_CUDA, "stream/event creation failed");
-  }
+
   if (cudaMalloc(&h->red_partial, 256 * sizeof(float)) != cudaSuccess || cudaMemset(h->red_partial, 0, 256 * sizeof(float)) != cudaSuccess) {
     delete h; return fail(KGE_ERR_NOMEM, "cudaMalloc failed");
   }
@@ -295,10 +287,6 @@ KGE_API int kge_destroy(kge_handle_t h) {
   if (h->dev_stage) cudaFree(h->dev_stage);
   if (h->pin) cudaFreeHost(h->pin);
   if (h->dev_log4) cudaFree(h->dev_log4);
-  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
-  if (h->ev_colsum) cudaEventDestroy(h->ev_colsum);
-  if (h->ev_log) cudaEventDestroy(h->ev_log);
-  if (h->side) cudaStreamDestroy(h->side);
   if (h->red_partial) cudaFree(h->red_partial);
   if (h->prof.created)
     for (int i = 0; i < Profiler::kMax; ++i) { cudaEventDestroy(h->prof.ev0[i]); cudaEventDestroy(h->prof.ev1[i]); }

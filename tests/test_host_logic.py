@@ -89,3 +89,29 @@ def test_eval_batches_one_chunk_all_entities():
     assert len(b) == 2
     pg, ng = b[0]
     assert (ng.num_chunks, ng.chunk_size, ng.neg_sample_size, ng.neg_head) == (1, 2, 10, True)
+
+
+def test_lazy_log_and_fused_loss_read_device_scalars_lazily():
+    """log dict semantics of the reference (pos_loss, neg_loss, loss, regularization floats; loss excludes reg,
+    general_models.py:569-576) on top of the device log4 buffer."""
+    from dglke_b200.loss import LazyLog, FusedLoss
+    log4 = th.tensor([0.25, 0.75, 0.5, 0.125])
+    log = LazyLog(log4, has_reg=True)
+    log4.zero_()                                   # the log owns a snapshot
+    assert sorted(log.keys()) == ["loss", "neg_loss", "pos_loss", "regularization"]
+    assert log["loss"] == 0.5 and log["regularization"] == 0.125 and "pos_loss" in log
+    assert sum(l[k] for l in [log, log] for k in ["loss"]) == 1.0      # train loop's averaging idiom
+    assert sorted(k for k in LazyLog(th.zeros(4), has_reg=False)) == ["loss", "neg_loss", "pos_loss"]
+    loss = FusedLoss(th.tensor([0.25, 0.75, 0.5, 0.125]), with_reg=True)
+    assert loss.backward() is None and abs(float(loss) - 0.625) < 1e-7 and loss.item() == float(loss)
+
+
+def test_unsupported_options_raise_instead_of_falling_back():
+    from dglke_b200.loss import LossGenerator
+    with pytest.raises(NotImplementedError):
+        LossGenerator(None, "Hinge")
+    with pytest.raises(NotImplementedError):
+        LossGenerator(None, "Logsigmoid", pairwise=True)
+    from dglke_b200 import _lib
+    with pytest.raises(_lib.KgeError):
+        _lib.make_cfg("TransR", 8, 8, 12.0, 0.1, 0.1, 0.0, 3, False, 1.0, False, 8, 8, 8)
