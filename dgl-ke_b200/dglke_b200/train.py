@@ -7,8 +7,9 @@ All reference flags parse.  What differs, and why:
   * data: there is no network in this environment, so built-in dataset names select the dataset's SHAPE
     (entities / relations / training edges) and triples are drawn synthetically unless --data_files
     points at udd_hrt-style integer triple files (entity_file relation_file train_file [valid] [test]);
-  * --gpu is required (no CPU path); several GPUs => launch with torchrun, one process per GPU, and the
-    entity table is row-sharded over the GPUs (dglke_b200.dist) instead of --mix_cpu_gpu's host table;
+  * --gpu is required (no CPU path).  This CLI drives ONE GPU; the multi-GPU path (entity table row-sharded over the
+    GPUs instead of --mix_cpu_gpu's host table, one process per GPU under torchrun) is the
+    dglke_b200.dist.ShardedTrainer API that bench.py --gpus N uses -- wiring it into this CLI is on the next list;
   * sampling is numpy-based (DGL's C++ sampler is out of scope).
 """
 import os

@@ -175,8 +175,10 @@ KGE_API int kge_step_fused(kge_handle_t h, const kge_step_cfg_t* cfg, const kge_
                    const kge_table_t* rel, const kge_batch_t* batch, float* log4, void* stream);
 
 /* Same as kge_step_fused but the batch index arrays (and edge weights) are HOST memory, as they
- * come out of the sampler: they are staged through pinned memory and copied H2D on `stream`,
- * and the four log scalars are copied back to log4_host (D2H) -- call kge_sync to read them. */
+ * come out of the sampler.  Pageable arrays are staged through the handle's pinned buffer (they may be
+ * reused as soon as the call returns); page-locked arrays (cudaHostAlloc / torch pin_memory) are DMA'd
+ * directly and must stay unchanged until kge_sync.  The four log scalars are copied back to log4_host
+ * (D2H) on `stream` -- call kge_sync before reading them. */
 KGE_API int kge_step_fused_host(kge_handle_t h, const kge_step_cfg_t* cfg, const kge_table_t* ent,
                         const kge_table_t* rel, const kge_batch_t* batch_host, float* log4_host,
                         void* stream);
