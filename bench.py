@@ -377,6 +377,7 @@ def run_ours(args):
                    "l2": "cold: 256 MiB written between timed steps" if not args.no_flush else "warm (no flush)",
                    "launch": "one CUDA graph per step" if graphs is not None else "eager launches",
                    "sampling": "excluded (pre-generated seeded batches), as on the reference arm",
+                   "arithmetic": "fp32 rows; contractions on tcgen05 as 3xTF32 (hi/lo split) with fp32 accumulation" if model in ("TransE_l2", "DistMult", "ComplEx", "RESCAL") else "fp32 CUDA-core tiles",
                    "bytes_per_edge": bpe},
         "e2e": {"value": e2e, "unit": "edges/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 16,
                 "ms_per_step": ms_e2e / K},
