@@ -304,15 +304,11 @@ def run_ours(args):
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         return float(tt.item())
 
-    launches0 = eng.h.launch_count()
     clk = ClockSampler(local_rank) if rank == 0 else None
     if graphs is not None:
         ms_dev = timed(lambda k: graphs[k % NB].replay())
-        launches = (eng.h.launch_count() - launches0)  # graph replays do not pass through the library
-        launches = None
     else:
         ms_dev = timed(step_dev)
-        launches = eng.h.launch_count() - launches0
     clocks = clk.stop() if clk else None
 
     # launches per step, counted from one eager step

@@ -92,10 +92,9 @@ def load_library():
     lib.kge_device_free.argtypes = [vp, vp]
     lib.kge_ipc_export.argtypes = [vp, vp, C.c_char_p, P(i64)]
     lib.kge_ipc_open.argtypes = [vp, C.c_char_p, i64, P(vp)]
-    for name in EXPORTS:
-        fn = getattr(lib, name)
-        if fn.restype is C.c_int and name not in ("kge_abi_version",):
-            pass
+    missing = [name for name in EXPORTS if not hasattr(lib, name)]
+    if missing:
+        raise KgeError("libkge_b200.so at %s lacks symbols %s (stale build?)" % (LIB_PATH, missing))
     _lib = lib
     return lib
 
