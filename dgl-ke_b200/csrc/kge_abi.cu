@@ -17,6 +17,7 @@
 
 namespace kge {
 bool umma_supported(const StepParams&);
+bool fused_supported(const StepParams&);
 }
 using namespace kge;
 
@@ -56,7 +57,11 @@ struct kge_context {
   // pinned + device staging for the *_host entry points
   char* pin = nullptr;
   char* dev_stage = nullptr;
-  float* red_partial = nullptr;      // k_reduce_log partials + ticket (persistent, zero-initialised once)
+  float* red_partial = nullptr;      // k_reduce_log partials + ticket + k_update barrier counters (persistent, zero-initialised once)
+  float* rel_dense = nullptr;        // [n_rel * Dr | n_rel] per-relation gradient sums of the fused step (zero between steps)
+  size_t rel_dense_floats = 0;
+  float* dump_v = nullptr;           // test hook (kge_debug_set_dump): coefficient matrices of the fused kernel
+  int fused_mode = -1;               // -1 default (fused kernel whenever the shape allows), 0 off
   size_t stage_bytes = 0;
   float* dev_log4 = nullptr;
   // last step (for kge_update / kge_debug_read)
@@ -144,7 +149,7 @@ int make_params(const kge_step_cfg_t* cfg, long long n_nodes, StepParams* p, boo
   p->C = (int)(cfg->batch / cfg->chunk_size);
   p->Nn = (long long)p->C * p->Ns;
   p->U = n_nodes;
-  p->rel_deferred = 0;
+  p->rel_deferred = 0; p->rel_dense = 0; p->use_nc = 1; p->fused = 0;
   (void)need_tables;
   return KGE_OK;
 }
@@ -152,29 +157,47 @@ int make_params(const kge_step_cfg_t* cfg, long long n_nodes, StepParams* p, boo
 size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 // Carves the step workspace out of the arena; grows the arena if needed.
-int carve(kge_context* h, const StepParams& p, StepWs* w, cudaStream_t stream) {
+// Layout rule: every buffer whose size depends only on (B, Ns, D) comes first, the buffers that depend on the unique-node
+// count U (NC, regp) come last -- the TMA tensor maps of the GEMM operands are cached by base address, and U changes
+// every step.
+struct CarveOpt {
+  bool force_tiles = false;   // fp32 CUDA-core tiles regardless of the handle's engine (kge_score_neg for RESCAL)
+  bool want_scores = true;    // fused path: keep a [B, Ns] score matrix for kge_debug_read
+};
+
+bool use_fused(kge_context* h, const StepParams& p) {
+  return h->engine != 0 && h->fused_mode != 0 && fused_supported(p);
+}
+
+int carve(kge_context* h, const StepParams& p, StepWs* w, cudaStream_t stream, const CarveOpt& opt = CarveOpt()) {
   const size_t f = sizeof(float);
   const size_t BD = (size_t)p.B * p.D, ND = (size_t)p.Nn * p.D, BNs = (size_t)p.B * p.Ns;
   const size_t U = (size_t)(p.U > 0 ? p.U : 0);
   const bool rescal = p.model == KGE_RESCAL;
+  const bool um = !opt.force_tiles && (h->engine != 0) && umma_supported(p);
+  const bool fused = p.fused != 0;
   size_t need = 0;
   auto take = [&](size_t floats) { size_t off = need; need += align_up(floats * f); return off; };
   // NG first, sized for the largest possible node count (2B): rows >= U are never written, rows < U are
-  // re-zeroed by k_upd_nodes, so one fill keeps the whole region zero across steps with varying U
+  // re-zeroed by the node update, so one fill keeps the whole region zero across steps with varying U
   size_t oNG = take((U ? (size_t)2 * p.B : 0) * p.D);
-  size_t oNC = take(U * p.D);
-  size_t oA = take(BD), oBn = take(ND), oGA = take(BD), oGR = take((size_t)p.B * p.Dr);
-  size_t oS = take(BNs), oV = take(BNs);
+  size_t oA = (um || fused) ? 0 : take(BD);
+  size_t oBn = take(ND), oGA = take(BD);
+  size_t oGR = p.rel_dense ? 0 : take((size_t)p.B * p.Dr);
+  size_t oS = (!fused || opt.want_scores) ? take(BNs) : 0;
+  size_t oV = fused ? 0 : take(BNs);
   size_t opos = take(p.B), ogpos = take(p.B), opn = take(p.B), oa2 = take(p.B), ob2 = take(p.Nn);
   size_t ors = take(p.B), ocs = take(p.Nn), opl = take(p.B), onl = take(p.B);
-  size_t oreg = take((size_t)p.B + p.Nn + U), owb = take(4), ogsr = take(p.B);
+  size_t owb = take(4), ogsr = take(p.B), ogsn = take(p.Nn), osm = take(p.B), osk = take(p.B);
   size_t oMt = rescal ? take(BD) : 0;
-  const bool um = (h->engine != 0) && umma_supported(p);
   // slab layout pads the blocked dimension to a multiple of 32 (+ one slab of slack for box overruns)
   const size_t sA = (size_t)p.B * slab_blocks(p.D) * 32 + 8192, sB = (size_t)p.Nn * slab_blocks(p.D) * 32 + 8192;
   const size_t sV = (size_t)p.B * slab_blocks(p.Ns) * 32 + 8192;
   size_t oAh = um ? take(sA) : 0, oAl = um ? take(sA) : 0, oBh = um ? take(sB) : 0, oBl = um ? take(sB) : 0;
-  size_t oVh = um ? take(sV) : 0, oVl = um ? take(sV) : 0;
+  size_t oVh = (um && !fused) ? take(sV) : 0, oVl = (um && !fused) ? take(sV) : 0;
+  // U-dependent tail
+  size_t oNC = p.use_nc ? take(U * p.D) : 0;
+  size_t oreg = take((size_t)p.B + p.Nn + (U ? (size_t)2 * p.B : 0));
   if (need > h->arena_bytes) {
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(stream, &cs);
@@ -189,16 +212,40 @@ int carve(kge_context* h, const StepParams& p, StepWs* w, cudaStream_t stream) {
     h->arena_bytes = bytes;
   }
   char* a = h->arena;
-  w->NG = (float*)(a + oNG); w->NC = (float*)(a + oNC); w->A = (float*)(a + oA); w->Bn = (float*)(a + oBn); w->GA = (float*)(a + oGA);
-  w->GR = (float*)(a + oGR); w->S = (float*)(a + oS); w->V = (float*)(a + oV);
+  auto at = [&](size_t off, bool on) { return on ? (float*)(a + off) : nullptr; };
+  w->NG = (float*)(a + oNG); w->NC = at(oNC, p.use_nc != 0); w->A = at(oA, !(um || fused)); w->Bn = (float*)(a + oBn);
+  w->GA = (float*)(a + oGA); w->GR = at(oGR, !p.rel_dense); w->S = at(oS, !fused || opt.want_scores); w->V = at(oV, !fused);
   w->pos = (float*)(a + opos); w->gpos = (float*)(a + ogpos); w->pnorm = (float*)(a + opn);
   w->a2 = (float*)(a + oa2); w->b2 = (float*)(a + ob2); w->rowsum = (float*)(a + ors); w->colsum = (float*)(a + ocs);
   w->pl = (float*)(a + opl); w->nl = (float*)(a + onl); w->regp = (float*)(a + oreg); w->wbar = (float*)(a + owb); w->gsr = (float*)(a + ogsr);
+  w->gsn = (float*)(a + ogsn); w->stat_m = (float*)(a + osm); w->stat_k = (float*)(a + osk);
   w->red_partial = h->red_partial; w->red_ticket = (unsigned int*)(h->red_partial + 192);
+  w->sync_ctr = (unsigned int*)(h->red_partial + 200);
+  w->rg = nullptr; w->rgs = nullptr;
   w->Mt = rescal ? (float*)(a + oMt) : nullptr;
-  w->Ahi = um ? (float*)(a + oAh) : nullptr; w->Alo = um ? (float*)(a + oAl) : nullptr;
-  w->Bhi = um ? (float*)(a + oBh) : nullptr; w->Blo = um ? (float*)(a + oBl) : nullptr;
-  w->Vhi = um ? (float*)(a + oVh) : nullptr; w->Vlo = um ? (float*)(a + oVl) : nullptr;
+  w->Ahi = at(oAh, um); w->Alo = at(oAl, um); w->Bhi = at(oBh, um); w->Blo = at(oBl, um);
+  w->Vhi = at(oVh, um && !fused); w->Vlo = at(oVl, um && !fused);
+  return KGE_OK;
+}
+
+// dense per-relation gradient buffers of the fused single-GPU step (zero between steps: the update re-zeroes what it consumes)
+int ensure_rel_dense(kge_context* h, const TableView& rel, StepWs* w, cudaStream_t stream) {
+  const size_t need = (size_t)rel.num_rows * rel.dim + (size_t)rel.num_rows;
+  if (need != h->rel_dense_floats) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(stream, &cs);
+    if (cs != cudaStreamCaptureStatusNone)
+      return fail(KGE_ERR_INVALID_ARG, "relation gradient buffer must be (re)allocated but the stream is capturing: run one eager step first");
+    KGE_CUDA_OK(cudaStreamSynchronize(stream));
+    if (h->rel_dense) cudaFree(h->rel_dense);
+    h->rel_dense = nullptr; h->rel_dense_floats = 0;
+    cudaError_t e = cudaMalloc(&h->rel_dense, need * sizeof(float));
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(KGE_ERR_NOMEM, "cudaMalloc(%zu) for the relation gradient sums failed", need * sizeof(float)); }
+    KGE_CUDA_OK(cudaMemsetAsync(h->rel_dense, 0, need * sizeof(float), stream));
+    h->rel_dense_floats = need;
+  }
+  w->rg = h->rel_dense;
+  w->rgs = h->rel_dense + (size_t)rel.num_rows * rel.dim;
   return KGE_OK;
 }
 
@@ -243,6 +290,10 @@ void launch_rescal_chain(const LaunchCtx&, const StepParams&, const TableView& e
 bool umma_supported(const StepParams&);
 int umma_score(const LaunchCtx&, const StepParams&, const StepWs&, char* err, size_t errlen);
 int umma_grad(const LaunchCtx&, const StepParams&, const StepWs&, bool side_b, char* err, size_t errlen);
+// fused contraction (kge_fused.cu): mode 0 = P (scores, loss, GA), mode 1 = N (G_neg, mean squares)
+bool fused_supported(const StepParams&);
+int fused_launch(const LaunchCtx&, const StepParams&, const StepWs&, int mode, const float* wt, float* dumpS, float* dumpV,
+                 char* err, size_t errlen);
 }  // namespace kge
 
 extern "C" {
@@ -268,6 +319,7 @@ KGE_API int kge_create(int device, kge_handle_t* out) {
   if (!h) return fail(KGE_ERR_NOMEM, "out of host memory");
   h->device = device;
   h->num_sms = prop.multiProcessorCount;
+  if (const char* ev = getenv("KGE_B200_FUSED")) h->fused_mode = atoi(ev) ? 1 : 0;   // A/B switch for benchmarks
 
   DeviceGuard g(device);
   if (cudaMalloc(&h->dev_log4, 4 * sizeof(float)) != cudaSuccess) { delete h; return fail(KGE_ERR_NOMEM, "cudaMalloc failed"); }
@@ -288,6 +340,7 @@ KGE_API int kge_destroy(kge_handle_t h) {
   if (h->pin) cudaFreeHost(h->pin);
   if (h->dev_log4) cudaFree(h->dev_log4);
   if (h->red_partial) cudaFree(h->red_partial);
+  if (h->rel_dense) cudaFree(h->rel_dense);
   if (h->prof.created)
     for (int i = 0; i < Profiler::kMax; ++i) { cudaEventDestroy(h->prof.ev0[i]); cudaEventDestroy(h->prof.ev1[i]); }
   delete h;
@@ -333,6 +386,19 @@ KGE_API int kge_set_engine(kge_handle_t h, int engine) {
   if (!h) return fail(KGE_ERR_INVALID_ARG, "handle is null");
   if (engine < -1 || engine > 1) return fail(KGE_ERR_INVALID_ARG, "engine must be -1, 0 or 1");
   h->engine = engine;
+  return KGE_OK;
+}
+
+KGE_API int kge_set_fused(kge_handle_t h, int mode) {
+  if (!h) return fail(KGE_ERR_INVALID_ARG, "handle is null");
+  if (mode < -1 || mode > 1) return fail(KGE_ERR_INVALID_ARG, "mode must be -1, 0 or 1");
+  h->fused_mode = mode;
+  return KGE_OK;
+}
+
+KGE_API int kge_debug_set_dump(kge_handle_t h, float* coef_dump) {
+  if (!h) return fail(KGE_ERR_INVALID_ARG, "handle is null");
+  h->dump_v = coef_dump;
   return KGE_OK;
 }
 
@@ -396,7 +462,11 @@ KGE_API int kge_score_neg(kge_handle_t h, const kge_step_cfg_t* cfg, const float
   if (rc) return rc;
   DeviceGuard g(h->device);
   StepWs w{};
-  rc = carve(h, p, &w, (cudaStream_t)stream);
+  // RESCAL: the a-side kernel (M_r . p) does not split the dense negative rows for the tensor-core engine; its
+  // stand-alone negative score runs on the fp32 tile kernels
+  CarveOpt opt;
+  opt.force_tiles = (p.model == KGE_RESCAL);
+  rc = carve(h, p, &w, (cudaStream_t)stream, opt);
   if (rc) return rc;
   h->ng_ptr = nullptr;      // this carve overlays the node-gradient region
   LaunchCtx c = lctx(h, stream);
@@ -408,7 +478,8 @@ KGE_API int kge_score_neg(kge_handle_t h, const kge_step_cfg_t* cfg, const float
   StepWs w2 = w;
   w2.Bn = const_cast<float*>(negrows);
   w2.S = out;
-  rc = run_score(h, c, p, w2);
+  if (opt.force_tiles) launch_score(c, p, w2);
+  else rc = run_score(h, c, p, w2);
   if (rc) return rc;
   KGE_CUDA_OK(cudaGetLastError());
   h->have_last = false;
@@ -451,8 +522,10 @@ KGE_API int kge_adagrad(kge_handle_t h, const kge_table_t* table, const int64_t*
   return KGE_OK;
 }
 
-KGE_API int kge_forward_backward(kge_handle_t h, const kge_step_cfg_t* cfg, const kge_table_t* ent, const kge_table_t* rel,
-                         const kge_batch_t* batch, float* log4, void* stream) {
+// One step's forward + backward.  `fused_step`: called from kge_step_fused (nobody reads per-edge relation gradients or
+// the score matrix; head/tail rows may be read straight from the table; the log scalars are reduced by the update).
+static int forward_backward_impl(kge_handle_t h, const kge_step_cfg_t* cfg, const kge_table_t* ent, const kge_table_t* rel,
+                                 const kge_batch_t* batch, float* log4, void* stream, bool fused_step) {
   if (!h) return fail(KGE_ERR_INVALID_ARG, "handle is null");
   StepParams p;
   int rc = make_params(cfg, batch ? batch->n_nodes : 0, &p, true);
@@ -466,36 +539,60 @@ KGE_API int kge_forward_backward(kge_handle_t h, const kge_step_cfg_t* cfg, cons
   if (ve.dim != p.D || vr.dim != p.Dr)
     return fail(KGE_ERR_INVALID_ARG, "table dims (%d,%d) do not match cfg (%d,%d)", ve.dim, vr.dim, p.D, p.Dr);
   DeviceGuard g(h->device);
+  p.fused = use_fused(h, p) ? 1 : 0;
+  // fused step on one GPU: nothing can change a table row between its gather and the node update, so the gathered
+  // copy NC is skipped; relation gradients are summed per relation (<= 256 MB of sums) instead of stored per edge
+  p.use_nc = (fused_step && ve.n_shards == 1) ? 0 : 1;
+  p.rel_dense = (fused_step && !p.rel_deferred && p.model != KGE_RESCAL &&
+                 (size_t)vr.num_rows * (size_t)vr.dim <= ((size_t)64 << 20)) ? 1 : 0;
   StepWs w{};
-  if ((rc = carve(h, p, &w, (cudaStream_t)stream))) return rc;
+  CarveOpt opt;
+  opt.want_scores = !fused_step;
+  if ((rc = carve(h, p, &w, (cudaStream_t)stream, opt))) return rc;
+  if (p.rel_dense && (rc = ensure_rel_dense(h, vr, &w, (cudaStream_t)stream))) return rc;
   LaunchCtx c = lctx(h, stream);
   BatchView b = bview(batch);
   ensure_ng_zero(h, p, w, c, false);
-  launch_gather_nodes(c, p, ve, b, w);      // pos_g.ndata['emb'] = entity_emb(pos_g.ndata['id'])  (general_models.py:548)
+  if (p.use_nc) launch_gather_nodes(c, p, ve, b, w);      // pos_g.ndata['emb'] = entity_emb(pos_g.ndata['id'])  (general_models.py:548)
   if (p.model == KGE_RESCAL) launch_rescal_prep(c, p, ve, vr, b, w);
   else launch_prep(c, p, ve, vr, b, w);
-  if ((rc = run_score(h, c, p, w))) return rc;
-  // single-stream schedule.  (Running k_colsum / k_reduce_log on a side stream beside the gradient GEMMs gained
-  // ~4 % but coincided with two sporadic parity failures that could not be investigated within the GPU budget;
-  // reverted until it can be race-checked.)
-  launch_loss(c, p, w.pos, w.S, b.edge_weight, w, log4 ? log4 : h->dev_log4, true);
-  if (use_umma(h, p)) {
-    if ((rc = umma_grad(c, p, w, false, g_err, sizeof(g_err)))) return rc;
-    if ((rc = umma_grad(c, p, w, true, g_err, sizeof(g_err)))) return rc;
+  float* logdst = log4 ? log4 : h->dev_log4;
+  if (p.fused) {
+    launch_wbar(c, p, b.edge_weight, w);
+    if ((rc = fused_launch(c, p, w, 0, b.edge_weight, fused_step ? nullptr : w.S, h->dump_v, g_err, sizeof(g_err)))) return rc;
+    if ((rc = fused_launch(c, p, w, 1, b.edge_weight, nullptr,
+                           h->dump_v ? h->dump_v + (size_t)p.B * p.Ns : nullptr, g_err, sizeof(g_err)))) return rc;
   } else {
-    launch_grad_a(c, p, w);
-    launch_grad_b(c, p, w);
+    if ((rc = run_score(h, c, p, w))) return rc;
+    launch_wbar(c, p, b.edge_weight, w);
+    launch_loss_rows(c, p, w.pos, w.S, b.edge_weight, w);
+    launch_colsum(c, p, w);
+    if (use_umma(h, p)) {
+      if ((rc = umma_grad(c, p, w, false, g_err, sizeof(g_err)))) return rc;
+      if ((rc = umma_grad(c, p, w, true, g_err, sizeof(g_err)))) return rc;
+    } else {
+      launch_grad_a(c, p, w);
+      launch_grad_b(c, p, w);
+    }
   }
   if (p.model == KGE_RESCAL) launch_rescal_chain(c, p, ve, vr, b, w);
   else launch_chain(c, p, ve, vr, b, w);
+  // 3-call API: the log scalars are due now; fused step: the update kernel reduces them (it also produces the unique
+  // nodes' share of the regulariser when NC is skipped)
+  if (!fused_step) launch_reduce_log(c, p, b.edge_weight, w, logdst, true);
   KGE_CUDA_OK(cudaGetLastError());
   h->last_p = p; h->last_w = w; h->last_b = b; h->last_ent = ve; h->last_rel = vr; h->have_last = true;
   h->ng_dirty = true;
   return KGE_OK;
 }
 
-KGE_API int kge_update(kge_handle_t h, const kge_step_cfg_t* cfg, const kge_table_t* ent, const kge_table_t* rel,
-               const kge_batch_t* batch, void* stream) {
+KGE_API int kge_forward_backward(kge_handle_t h, const kge_step_cfg_t* cfg, const kge_table_t* ent, const kge_table_t* rel,
+                         const kge_batch_t* batch, float* log4, void* stream) {
+  return forward_backward_impl(h, cfg, ent, rel, batch, log4, stream, false);
+}
+
+static int update_impl(kge_handle_t h, const kge_step_cfg_t* cfg, const kge_table_t* ent, const kge_table_t* rel,
+                       const kge_batch_t* batch, float* log4, void* stream) {
   if (!h) return fail(KGE_ERR_INVALID_ARG, "handle is null");
   if (!h->have_last) return fail(KGE_ERR_INVALID_ARG, "kge_update without a preceding kge_forward_backward");
   StepParams p;
@@ -508,20 +605,30 @@ KGE_API int kge_update(kge_handle_t h, const kge_step_cfg_t* cfg, const kge_tabl
   if ((rc = make_view(ent, &ve, "entity"))) return rc;
   if ((rc = make_view(rel, &vr, "relation"))) return rc;
   DeviceGuard g(h->device);
-  p.lr = cfg->lr;
-  p.rel_deferred = h->last_p.rel_deferred;
-  launch_update(lctx(h, stream), p, ve, vr, bview(batch), h->last_w);
+  StepParams q = h->last_p;       // the schedule flags (fused / use_nc / rel_dense / rel_deferred) of the forward pass
+  q.lr = cfg->lr;
+  BatchView b = bview(batch);
+  if (launch_update(lctx(h, stream), q, ve, vr, b, h->last_w, log4, b.edge_weight) != KGE_OK)
+    return fail(KGE_ERR_CUDA, "cooperative launch of k_update failed: %s (set KGE_B200_NO_COOP=1 for the three-launch form)",
+                cudaGetErrorString(cudaPeekAtLastError()));
   KGE_CUDA_OK(cudaGetLastError());
   h->ng_dirty = false;
   h->have_last = false;   // gradients consumed (NG re-zeroed, like `self.trace = []`, tensor_models.py:362)
   return KGE_OK;
 }
 
+KGE_API int kge_update(kge_handle_t h, const kge_step_cfg_t* cfg, const kge_table_t* ent, const kge_table_t* rel,
+               const kge_batch_t* batch, void* stream) {
+  return update_impl(h, cfg, ent, rel, batch, nullptr, stream);
+}
+
+// Fused schedule (one GPU, supported shape): k_prep -> k_fused<P> -> k_fused<N> -> k_chain -> k_update = 5 launches.
 KGE_API int kge_step_fused(kge_handle_t h, const kge_step_cfg_t* cfg, const kge_table_t* ent, const kge_table_t* rel,
                    const kge_batch_t* batch, float* log4, void* stream) {
-  int rc = kge_forward_backward(h, cfg, ent, rel, batch, log4, stream);
+  if (!h) return fail(KGE_ERR_INVALID_ARG, "handle is null");
+  int rc = forward_backward_impl(h, cfg, ent, rel, batch, log4, stream, true);
   if (rc) return rc;
-  return kge_update(h, cfg, ent, rel, batch, stream);
+  return update_impl(h, cfg, ent, rel, batch, log4 ? log4 : h->dev_log4, stream);
 }
 
 KGE_API int kge_step_fused_host(kge_handle_t h, const kge_step_cfg_t* cfg, const kge_table_t* ent, const kge_table_t* rel,

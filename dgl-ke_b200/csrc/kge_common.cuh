@@ -49,6 +49,9 @@ struct StepParams {
   long long Nn; // C * Ns negative rows
   long long U;  // unique positive nodes
   int rel_deferred;  // 1: relation Adagrad is applied later from dense all-reduced buffers (multi-GPU)
+  int rel_dense;     // 1: k_chain sums relation gradients per relation into ws.rg / ws.rgs (fused single-GPU step)
+  int use_nc;        // 1: head/tail rows are read from the gathered copy NC (3-call API, sharded tables); 0: from the table
+  int fused;         // 1: contraction by the fused tcgen05 kernel (kge_fused.cu): operands exist only as TF32 hi/lo slabs
 };
 
 // Device workspace of one step (all pointers into the handle's arena).
@@ -73,7 +76,13 @@ struct StepWs {
   float* nl;       // [B]      negative loss terms (already reduced over j)
   float* regp;     // [B + Nn + U] partial sums of |x|^p
   float* wbar;     // [1]      mean edge weight
-  float* gsr;      // [B]      mean(GR_i^2) per edge (deferred relation update)
+  float* gsr;      // [B]      mean(GR_i^2) per edge (relation Adagrad phase 1)
+  float* gsn;      // [Nn]     mean(G_neg_j^2) per negative row (fused kernel, mode N)
+  float* stat_m;   // [B]      softmax shift of row i, log2 domain (fused kernel: mode P -> mode N)
+  float* stat_k;   // [B]      w_i / (2B den_i)                    (fused kernel: mode P -> mode N)
+  float* rg;       // [n_rel, Dr] dense per-relation gradient sums (rel_dense), zero between steps
+  float* rgs;      // [n_rel]     dense per-relation sums of mean(g^2)          , zero between steps
+  unsigned int* sync_ctr;     // [4] grid-barrier counters of k_update (zero between launches)
   float* red_partial;         // [64 * 3] partial sums of k_reduce_log
   unsigned int* red_ticket;   // [1] completion ticket of k_reduce_log (zero between launches)
   float* Mt;       // [B, D]   RESCAL: M_r t  (tail mode needs it next to A = M_r h)
@@ -91,6 +100,13 @@ struct BatchView {
   const long long* neg_ids;
   const float* edge_weight;
 };
+
+// row of the positive graph's local node `loc` (pos_g.ndata['emb'][loc], general_models.py:548): the gathered copy,
+// or the table row itself when nothing can have changed it since the gather (single-GPU fused step)
+__device__ __forceinline__ const float* node_row(const StepParams& p, const TableView& ent, const BatchView& b,
+                                                 const StepWs& w, long long loc) {
+  return p.use_nc ? (w.NC + loc * (long long)p.D) : row_ptr(ent, b.node_ids[loc]);
+}
 
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
@@ -290,14 +306,14 @@ void launch_grad_a(const LaunchCtx&, const StepParams&, const StepWs&);
 void launch_grad_b(const LaunchCtx&, const StepParams&, const StepWs&);
 void launch_chain(const LaunchCtx&, const StepParams&, const TableView& ent, const TableView& rel,
                   const BatchView&, const StepWs&);
-void launch_update(const LaunchCtx&, const StepParams&, const TableView& ent, const TableView& rel,
-                   const BatchView&, const StepWs&);
+// ExternalEmbedding.update of the step's three trace entries; log4 != null also reduces the log scalars (fused step)
+int launch_update(const LaunchCtx&, const StepParams&, const TableView& ent, const TableView& rel,
+                  const BatchView&, const StepWs&, float* log4, const float* wt);
 void launch_adagrad(const LaunchCtx&, const TableView& t, const long long* idx, const float* grad,
                     long long n, float lr);
 void launch_node_grad_with_reg(const LaunchCtx&, const StepParams&, const TableView& ent,
                                const BatchView&, const StepWs&, float* out);
 void launch_fill_zero(const LaunchCtx&, float* p, long long n);
-void launch_update_entities(const LaunchCtx&, const StepParams&, const TableView& ent, const BatchView&, const StepWs&);
 void launch_rel_grad_dense(const LaunchCtx&, const StepParams&, const BatchView&, const StepWs&, float* rg, float* rgs);
 void launch_rel_apply_dense(const LaunchCtx&, const TableView& rel, float* rg, float* rgs, float lr);
 

@@ -1,0 +1,537 @@
+// kge_fused.cu -- the fused contraction kernel of the step (tcgen05 / TMEM / TMA, sm_100a):
+//
+//   S = X . Y^T  (tensor cores, accumulator in TMEM)  ->  loss / self-adversarial softmax / backward
+//   coefficients V computed from TMEM in registers  ->  V (TF32 hi/lo) written back to TMEM
+//   ->  G = V . Y  (tensor cores, A operand read from TMEM)  ->  epilogue.
+//
+// The negative-score matrix S and the coefficient matrix V never leave the SM.  The kernel runs twice per step:
+//
+//   mode P  lanes = positives i, columns = negatives j:   S = A.Bn^T, row softmax (thread-local), GA = V.Bn
+//           replaces create_neg (score_fun.py:91-108,268-286,345-376,427-449), LossGenerator.get_total_loss
+//           (loss.py:69-98) and the dL/da half of loss.backward()
+//   mode N  lanes = negatives j, columns = positives i:   S^T = Bn.A^T, V^T from the row statistics mode P left
+//           behind, G_neg = V^T.A - colsum*b + reg'(b), mean(G_neg^2)  (the dL/db half of loss.backward() plus
+//           phase 1 of ExternalEmbedding.update for the negatives, tensor_models.py:316-328)
+//
+// Recomputing S in the second orientation costs one extra tensor-core GEMM per chunk and removes every HBM/L2 round
+// trip of S and V (and the k_loss / k_colsum / k_state_add launches).  fp32 fidelity: operands are TF32 hi/lo pairs
+// and every k-step issues hi*hi + hi*lo + lo*hi (3xTF32, fp32 accumulation in TMEM).
+//
+// CTA = 320 threads: warp 0 TMA producer, warp 1 TMEM allocator + single-thread tcgen05.mma issuer, warps 2-9
+// epilogue (two warps per TMEM lane quarter, splitting the columns).  Persistent over (chunk, 128-row tile) work
+// items.  TMEM columns: [0,N1) S -> V_hi | [N1,2N1) distances -> V_lo | [2N1, 2N1+Wc) accumulator of GEMM2, which is
+// processed in Wc-wide column chunks of the output (Wc = 96 at Ns = 200).  Shared memory: one 216 KB ring used as
+// nS1 stages {X_hi,X_lo,Y_hi,Y_lo} by GEMM1 and as nS2 stages {Y_hi,Y_lo} (MN-major) by GEMM2.
+#include <cuda.h>
+#include <cstdio>
+#include <cstdlib>
+#include "kge_common.cuh"
+#include "kge_tc.cuh"
+
+namespace kge {
+
+using namespace tc;
+
+namespace {
+
+constexpr int kTileM = 128;
+constexpr int kThreadsF = 320;
+constexpr int kMaxS1 = 4, kMaxS2 = 8;
+constexpr uint32_t kRingBytes = 216 * 1024;
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+enum { F_P = 0, F_N = 1 };
+
+struct FusedArgs {
+  int model, adversarial;
+  float gamma, Tl2e, inv2B, uni;
+  float reg_coef;
+  int reg_norm;
+  int C, Rx, Ry, D;      // rows per chunk on the lane side / on the column side, row length
+  int N1;                // Ry rounded up to 16 (UMMA N of GEMM1, TMEM region width)
+  int nblkD;             // 32-column slab blocks of D
+  int Wc;                // GEMM2 output-column chunk (multiple of 32)
+  int nS1, nS2;
+  uint32_t stage1Bytes, stage2Bytes;
+  const float* x2;       // |x|^2 per lane-side row   (TransE_l2)
+  const float* y2;       // |y|^2 per column-side row (TransE_l2)
+  // mode P
+  const float* pos;      // [B] positive scores
+  const float* wt;       // [B] edge weights or null
+  const float* wbar;     // [1] mean edge weight (with wt)
+  float *gpos, *rowsum, *pl, *nl, *stat_m, *stat_k;
+  float* dumpS;          // optional [C*Rx, Ry]: negative scores (kge_debug_read)
+  float* dumpV;          // optional [C*Rx, Ry]: backward coefficients (tests)
+  // mode N
+  const float* cstat_m;  // per positive: softmax shift (log2 domain)
+  const float* cstat_k;  // per positive: w_i / (2B den_i)  (or w_i / (2B Ns))
+  const float *Xhi, *Xlo;  // slabs of the lane-side rows (negatives): b = hi + lo in the epilogue
+  float* gsn;            // [C*Rx] mean(G_neg^2)
+  float* out;            // P: GA [C*Rx, D]; N: G_neg [C*Rx, D]
+};
+
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+template <int MODE>
+__global__ void __launch_bounds__(kThreadsF, 1)
+k_fused(const __grid_constant__ CUtensorMap mXh, const __grid_constant__ CUtensorMap mXl,
+        const __grid_constant__ CUtensorMap mYh1, const __grid_constant__ CUtensorMap mYl1,
+        const __grid_constant__ CUtensorMap mYh2, const __grid_constant__ CUtensorMap mYl2, FusedArgs g) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full1[kMaxS1], empty1[kMaxS1], full2[kMaxS2], empty2[kMaxS2];
+  __shared__ __align__(8) uint64_t s_full, v_ready, acc_full, acc_empty;
+  __shared__ uint32_t tmem_slot;
+  __shared__ __align__(16) float colA[256], colB[256], colC[256];
+  __shared__ float xch[4][2][kTileM];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* ring = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+
+  const int mtiles = (g.Rx + kTileM - 1) / kTileM;
+  const int ntiles = g.C * mtiles;
+  const int nkb1 = (g.D + 31) >> 5;
+  const int nkb2 = (g.Ry + 31) >> 5;
+  const int nchunks = (g.D + g.Wc - 1) / g.Wc;
+  const uint32_t yBytes1 = (uint32_t)g.N1 * 128u;
+  const uint32_t yBytes2 = (uint32_t)(g.Wc >> 5) * 4096u;
+  const uint32_t colR2 = (uint32_t)g.N1, colAcc = 2u * (uint32_t)g.N1;
+  const bool l2 = g.model == KGE_TRANSE_L2;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kMaxS1; ++s) { mbar_init(&full1[s], 1); mbar_init(&empty1[s], 1); }
+    for (int s = 0; s < kMaxS2; ++s) { mbar_init(&full2[s], 1); mbar_init(&empty2[s], 1); }
+    mbar_init(&s_full, 1); mbar_init(&v_ready, 8); mbar_init(&acc_full, 1); mbar_init(&acc_empty, 8);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mXh); tma_prefetch_desc(&mXl); tma_prefetch_desc(&mYh1);
+    tma_prefetch_desc(&mYl1); tma_prefetch_desc(&mYh2); tma_prefetch_desc(&mYl2);
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      uint32_t n1 = 0, n2 = 0;      // stage fills issued so far (GEMM1 / GEMM2)
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int c = tile / mtiles, m0 = (tile % mtiles) * kTileM;
+        // the ring is about to be re-used with the GEMM1 layout: every GEMM2 stage of the previous tile must be consumed
+        for (uint32_t k = (n2 > (uint32_t)g.nS2 ? n2 - g.nS2 : 0); k < n2; ++k) mbar_wait(&empty2[k % g.nS2], (k / g.nS2) & 1);
+        for (int kb = 0; kb < nkb1; ++kb, ++n1) {
+          const uint32_t s = n1 % g.nS1;
+          mbar_wait(&empty1[s], ((n1 / g.nS1) & 1) ^ 1);
+          uint8_t* st = ring + (size_t)s * g.stage1Bytes;
+          mbar_expect_tx(&full1[s], 2u * 16384u + 2u * yBytes1);
+          // slab layout: TMA row of (chunk c, 32-column block kb, row r) = (c * nblkD + kb) * R + r
+          const int yx = (c * g.nblkD + kb) * g.Rx + m0;
+          const int yy = (c * g.nblkD + kb) * g.Ry;
+          tma_load_2d(st, &mXh, &full1[s], 0, yx);
+          tma_load_2d(st + 16384, &mXl, &full1[s], 0, yx);
+          tma_load_2d(st + 32768, &mYh1, &full1[s], 0, yy);
+          tma_load_2d(st + 32768 + yBytes1, &mYl1, &full1[s], 0, yy);
+        }
+        // GEMM2 stages overlay the GEMM1 stages: wait until the tensor core has consumed all of them
+        for (uint32_t k = (n1 > (uint32_t)g.nS1 ? n1 - g.nS1 : 0); k < n1; ++k) mbar_wait(&empty1[k % g.nS1], (k / g.nS1) & 1);
+        for (int ch = 0; ch < nchunks; ++ch) {
+          const int d0 = ch * g.Wc;
+          int nb = (g.D - d0 + 31) >> 5;
+          if (nb > (g.Wc >> 5)) nb = g.Wc >> 5;
+          for (int kb = 0; kb < nkb2; ++kb, ++n2) {
+            const uint32_t s = n2 % g.nS2;
+            mbar_wait(&empty2[s], ((n2 / g.nS2) & 1) ^ 1);
+            uint8_t* st = ring + (size_t)s * g.stage2Bytes;
+            mbar_expect_tx(&full2[s], 2u * (uint32_t)nb * 4096u);
+            for (int b = 0; b < nb; ++b) {
+              const int yy = (c * g.nblkD + (d0 >> 5) + b) * g.Ry + kb * 32;
+              tma_load_2d(st + b * 4096, &mYh2, &full2[s], 0, yy);
+              tma_load_2d(st + yBytes2 + b * 4096, &mYl2, &full2[s], 0, yy);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer (one thread) ================================
+    if (lane == 0) {
+      uint32_t n1 = 0, n2 = 0, nacc = 0, it = 0;
+      const uint32_t idesc1 = make_idesc(kTileM, g.N1, false, false);
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        // ---- GEMM1: S = X . Y^T, K = D ----
+        uint32_t accumulate = 0;
+        for (int kb = 0; kb < nkb1; ++kb, ++n1) {
+          const uint32_t s = n1 % g.nS1;
+          mbar_wait(&full1[s], (n1 / g.nS1) & 1);
+          tc_fence_after();
+          const uint32_t st = smem_u32(ring + (size_t)s * g.stage1Bytes);
+          const uint32_t sXh = st, sXl = st + 16384, sYh = st + 32768, sYl = st + 32768 + yBytes1;
+          const int kleft = g.D - kb * 32;
+          const int ksteps = kleft >= 32 ? 4 : (kleft >> 3);
+          for (int ks = 0; ks < ksteps; ++ks) {
+            const uint32_t off = ks * 32u;     // K-major: +32 bytes per k-step inside the 128-byte swizzle span
+            const uint64_t dXh = make_desc(sXh + off, 16, 1024), dXl = make_desc(sXl + off, 16, 1024);
+            const uint64_t dYh = make_desc(sYh + off, 16, 1024), dYl = make_desc(sYl + off, 16, 1024);
+            umma_tf32(tmem_base, dXh, dYh, idesc1, accumulate);
+            umma_tf32(tmem_base, dXh, dYl, idesc1, 1u);
+            umma_tf32(tmem_base, dXl, dYh, idesc1, 1u);
+            accumulate = 1u;
+          }
+          umma_commit(&empty1[s]);
+        }
+        umma_commit(&s_full);
+        // ---- the epilogue warps turn S into V (hi | lo) in TMEM ----
+        mbar_wait(&v_ready, it & 1);
+        tc_fence_after();
+        // ---- GEMM2: G[:, chunk] = V . Y[:, chunk], K = Ry, A operand from TMEM ----
+        for (int ch = 0; ch < nchunks; ++ch, ++nacc) {
+          const int d0 = ch * g.Wc;
+          int nb = (g.D - d0 + 31) >> 5;
+          if (nb > (g.Wc >> 5)) nb = g.Wc >> 5;
+          const uint32_t idesc2 = make_idesc(kTileM, nb * 32, false, true);
+          mbar_wait(&acc_empty, (nacc & 1) ^ 1);
+          tc_fence_after();
+          uint32_t acc2 = 0;
+          for (int kb = 0; kb < nkb2; ++kb, ++n2) {
+            const uint32_t s = n2 % g.nS2;
+            mbar_wait(&full2[s], (n2 / g.nS2) & 1);
+            tc_fence_after();
+            const uint32_t st = smem_u32(ring + (size_t)s * g.stage2Bytes);
+            const int kleft = g.Ry - kb * 32;
+            const int ksteps = kleft >= 32 ? 4 : (kleft >> 3);
+            for (int ks = 0; ks < ksteps; ++ks) {
+              // MN-major B (128B swizzle, 32B atoms): k-atoms of 4 rows (512 B, SBO), one k-step = 2 atoms = 1024 B,
+              // LBO = 4096 between the 32-wide column blocks
+              const uint64_t dYh = make_desc(st + ks * 1024u, 4096, 512, 1);
+              const uint64_t dYl = make_desc(st + yBytes2 + ks * 1024u, 4096, 512, 1);
+              const uint32_t aHi = tmem_base + (uint32_t)(kb * 32 + ks * 8);
+              const uint32_t aLo = aHi + colR2;
+              umma_tf32_ts(tmem_base + colAcc, aHi, dYh, idesc2, acc2);
+              umma_tf32_ts(tmem_base + colAcc, aHi, dYl, idesc2, 1u);
+              umma_tf32_ts(tmem_base + colAcc, aLo, dYh, idesc2, 1u);
+              acc2 = 1u;
+            }
+            umma_commit(&empty2[s]);
+          }
+          umma_commit(&acc_full);
+        }
+      }
+    }
+  } else {
+    // ================================ epilogue warps 2..9 ================================
+    const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    const int ehalf = (warp - 2) >> 2;            // two warps share a quarter and split the columns
+    const int row = q * 32 + lane;                // accumulator row = lane-side row inside the tile
+    const int et = threadIdx.x - 64;              // 0..255
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int h0 = ((g.N1 >> 1) + 15) & ~15;
+    const int cb = ehalf ? h0 : 0, ce = ehalf ? g.N1 : h0;
+    uint32_t nacc = 0, it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int c = tile / mtiles, m0 = (tile % mtiles) * kTileM;
+      const int m = m0 + row;
+      const bool row_ok = m < g.Rx;
+      const long long gx = (long long)c * g.Rx + m;
+      epi_bar();                                  // everybody is done with the previous tile's shared constants
+      for (int y = et; y < g.N1; y += 256) {
+        const bool ok = y < g.Ry;
+        const long long gy = (long long)c * g.Ry + y;
+        colA[y] = (l2 && ok) ? g.y2[gy] : 0.f;
+        if (MODE == F_N) { colB[y] = ok ? g.cstat_m[gy] : 0.f; colC[y] = ok ? g.cstat_k[gy] : 0.f; }
+      }
+      epi_bar();
+      const float x2v = (l2 && row_ok) ? g.x2[gx] : 0.f;
+      float colsum = 0.f;
+      mbar_wait(&s_full, it & 1);
+      tc_fence_after();
+
+      if (MODE == F_P) {
+        const float w_i = (g.wt && row_ok) ? g.wt[gx] : 1.f;
+        const float kw = w_i * g.inv2B;
+        // ---- pass A: scores (distance epilogue for TransE_l2), running max ----
+        float mxl = -INFINITY;
+        for (int col = cb; col < ce; col += 16) {
+          float v[16], dd[16];
+          tmem_ld16(trow + col, v);
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            float s = v[e];
+            if (l2) {
+              // batched_l2_dist (score_fun.py:26-34): (|b|^2 - 2 a.b) + |a|^2, clamp 1e-30, sqrt
+              const float sq = fmaf(-2.f, v[e], colA[col + e]) + x2v;
+              dd[e] = sqrta(fmaxf(sq, 1e-30f));
+              s = g.gamma - dd[e];
+              v[e] = s;
+            }
+            if (col + e < g.Ry) mxl = fmaxf(mxl, s * g.Tl2e);
+          }
+          if (g.dumpS && row_ok) {
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4)
+              if (col + q4 * 4 < g.Ry) st4(g.dumpS + gx * g.Ry + col + q4 * 4, make_float4(v[q4 * 4], v[q4 * 4 + 1], v[q4 * 4 + 2], v[q4 * 4 + 3]));
+          }
+          if (l2) tmem_st16(trow + colR2 + col, dd);
+        }
+        if (l2) tmem_wait_st();
+        float rden = g.uni;
+        if (g.adversarial) {
+          xch[0][ehalf][row] = mxl;
+          epi_bar();
+          mxl = fmaxf(mxl, xch[0][ehalf ^ 1][row]);
+          // ---- pass B: softmax denominator ----
+          float den = 0.f;
+          for (int col = cb; col < ce; col += 16) {
+            float v[16];
+            tmem_ld16(trow + (l2 ? colR2 : 0u) + col, v);
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              const float s = l2 ? g.gamma - v[e] : v[e];
+              if (col + e < g.Ry) den += ex2a(fmaf(s, g.Tl2e, -mxl));
+            }
+          }
+          xch[1][ehalf][row] = den;
+          epi_bar();
+          den += xch[1][ehalf ^ 1][row];
+          rden = 1.f / den;
+        } else {
+          mxl = 0.f;
+        }
+        // ---- pass C: loss terms + backward coefficients, written back to TMEM as TF32 hi | lo ----
+        float nls = 0.f, rs = 0.f;
+        for (int col = cb; col < ce; col += 16) {
+          float v[16], hi[16], lo[16];
+          tmem_ld16(trow + (l2 ? colR2 : 0u) + col, v);
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const float d = v[e];
+            const float s = l2 ? g.gamma - d : d;
+            const float p = g.adversarial ? ex2a(fmaf(s, g.Tl2e, -mxl)) * rden : g.uni;
+            const float t = ex2a(-fabsf(s) * kLog2e);
+            const float r1 = rcpa(1.f + t);
+            const float sig = (s >= 0.f) ? r1 : t * r1;                       // sigmoid(s)
+            const float sp = fmaxf(s, 0.f) + kLn2 * lg2a(1.f + t);           // -logsigmoid(-s)
+            float coef = p * sig * kw;                                        // dL/dneg_ij
+            if (l2) coef = (d > 1.5e-15f) ? coef * rcpa(d) : 0.f;             // clamped distance: zero gradient (clamp_min_)
+            const bool ok = row_ok && (col + e < g.Ry);
+            if (!ok) coef = 0.f;
+            if (ok) nls += p * sp;
+            rs += coef;
+            split_tf32(coef, hi[e], lo[e]);
+            v[e] = coef;
+          }
+          if (g.dumpV && row_ok) {
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4)
+              if (col + q4 * 4 < g.Ry) st4(g.dumpV + gx * g.Ry + col + q4 * 4, make_float4(v[q4 * 4], v[q4 * 4 + 1], v[q4 * 4 + 2], v[q4 * 4 + 3]));
+          }
+          tmem_st16(trow + col, hi);
+          tmem_st16(trow + colR2 + col, lo);
+        }
+        xch[2][ehalf][row] = nls;
+        xch[3][ehalf][row] = rs;
+        epi_bar();
+        if (ehalf == 0 && row_ok) {
+          nls += xch[2][1][row];
+          rs += xch[3][1][row];
+          const float ps = g.pos[gx];
+          const float wb = g.wt ? *g.wbar : 1.f;        // loss.py:75,82: [B] * [B,1] -> mean(pl) * mean(w)
+          g.pl[gx] = softplusf(-ps);
+          g.nl[gx] = nls * w_i;
+          g.gpos[gx] = -sigmoidf(-ps) * wb * g.inv2B;
+          if (l2) g.rowsum[gx] = rs;
+          g.stat_m[gx] = mxl;
+          g.stat_k[gx] = kw * rden;
+        }
+      } else {
+        // ---- mode N: one pass, the softmax statistics of every column (positive) come from mode P ----
+        float cs = 0.f;
+        for (int col = cb; col < ce; col += 16) {
+          float v[16], hi[16], lo[16];
+          tmem_ld16(trow + col, v);
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            float s = v[e], d = 1.f;
+            if (l2) {
+              const float sq = fmaf(-2.f, v[e], x2v) + colA[col + e];
+              d = sqrta(fmaxf(sq, 1e-30f));
+              s = g.gamma - d;
+            }
+            const float pe = g.adversarial ? ex2a(fmaf(s, g.Tl2e, -colB[col + e])) : 1.f;
+            const float t = ex2a(-fabsf(s) * kLog2e);
+            const float r1 = rcpa(1.f + t);
+            const float sig = (s >= 0.f) ? r1 : t * r1;
+            float coef = pe * colC[col + e] * sig;
+            if (l2) coef = (d > 1.5e-15f) ? coef * rcpa(d) : 0.f;
+            if (!(row_ok && (col + e < g.Ry))) coef = 0.f;
+            cs += coef;
+            split_tf32(coef, hi[e], lo[e]);
+            v[e] = coef;
+          }
+          if (g.dumpV && row_ok) {
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4)
+              if (col + q4 * 4 < g.Ry) st4(g.dumpV + gx * g.Ry + col + q4 * 4, make_float4(v[q4 * 4], v[q4 * 4 + 1], v[q4 * 4 + 2], v[q4 * 4 + 3]));
+          }
+          tmem_st16(trow + col, hi);
+          tmem_st16(trow + colR2 + col, lo);
+        }
+        xch[2][ehalf][row] = cs;
+        epi_bar();
+        colsum = cs + xch[2][ehalf ^ 1][row];
+      }
+      // V is complete in TMEM: hand it to the MMA thread
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&v_ready);
+
+      // ---- GEMM2 epilogue, one output-column chunk at a time ----
+      float gsq = 0.f;
+      float* orow = g.out + gx * (long long)g.D;
+      for (int ch = 0; ch < nchunks; ++ch, ++nacc) {
+        const int d0 = ch * g.Wc;
+        int nb = (g.D - d0 + 31) >> 5;
+        if (nb > (g.Wc >> 5)) nb = g.Wc >> 5;
+        const int Nc = nb * 32;
+        const int hc = ((Nc >> 1) + 15) & ~15;
+        const int cb2 = ehalf ? hc : 0, ce2 = ehalf ? Nc : hc;
+        const int npieces = (ce2 - cb2 + 15) >> 4;
+        mbar_wait(&acc_full, nacc & 1);
+        tc_fence_after();
+        auto release = [&]() {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty);
+        };
+        auto process = [&](const uint32_t* r, int col) {
+          if (!row_ok) return;
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const int k = d0 + col + q4 * 4;
+            if (k >= g.D) continue;
+            float4 o = make_float4(__uint_as_float(r[q4 * 4]), __uint_as_float(r[q4 * 4 + 1]),
+                                   __uint_as_float(r[q4 * 4 + 2]), __uint_as_float(r[q4 * 4 + 3]));
+            if (MODE == F_N) {
+              const long long so = slab_off(c, g.nblkD, g.Rx, m, k);
+              const float4 b = f4_add(ld4(g.Xhi + so), ld4(g.Xlo + so));
+              if (l2) o = f4_fma(b, -colsum, o);                 // sum_i V_ij a_i - (sum_i V_ij) b_j
+              o = f4_add(o, reg_grad4(b, g.reg_norm, g.reg_coef));
+              gsq += f4_dot(o, o);
+            }
+            st4(orow + k, o);
+          }
+        };
+        if (npieces <= 3) {
+          // whole half-chunk in registers: the accumulator is released before any global traffic
+          uint32_t r[48];
+#pragma unroll
+          for (int pc = 0; pc < 3; ++pc)
+            if (pc < npieces) tmem_ld16_nowait(trow + colAcc + cb2 + pc * 16, r + pc * 16);
+          tmem_wait_ld();
+          release();
+#pragma unroll
+          for (int pc = 0; pc < 3; ++pc)
+            if (pc < npieces) process(r + pc * 16, cb2 + pc * 16);
+        } else {
+          for (int pc = 0; pc < npieces; ++pc) {
+            uint32_t r[16];
+            tmem_ld16_nowait(trow + colAcc + cb2 + pc * 16, r);
+            tmem_wait_ld();
+            if (pc == npieces - 1) release();
+            process(r, cb2 + pc * 16);
+          }
+          if (npieces == 0) release();
+        }
+      }
+      if (MODE == F_N) {
+        epi_bar();                       // xch[2] (colsum exchange) has been read by everybody
+        xch[3][ehalf][row] = gsq;
+        epi_bar();
+        if (ehalf == 0 && row_ok) g.gsn[gx] = (gsq + xch[3][1][row]) / (float)g.D;
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+int pad16(int x) { return (x + 15) & ~15; }
+
+}  // namespace
+
+// The fused kernel keeps a whole row of the chunk's score matrix in TMEM twice (hi | lo) next to the GEMM2
+// accumulator: 2 * pad16(columns) + 32 <= 512 TMEM columns.
+bool fused_supported(const StepParams& p) {
+  const bool model_ok = p.model == KGE_TRANSE_L2 || p.model == KGE_DISTMULT || p.model == KGE_COMPLEX || p.model == KGE_RESCAL;
+  if (!model_ok) return false;
+  if ((p.D % 8) || (p.Cs % 8) || (p.Ns % 8) || p.D < 32 || p.Cs < 8 || p.Ns < 8) return false;
+  return pad16(p.Cs) <= 240 && pad16(p.Ns) <= 240;
+}
+
+// mode 0 (P): S = A.Bn^T -> loss, coefficients -> GA;  mode 1 (N): S^T -> coefficients -> G_neg (+ mean square)
+int fused_launch(const LaunchCtx& c, const StepParams& p, const StepWs& w, int mode, const float* wt, float* dumpS,
+                 float* dumpV, char* err, size_t errlen) {
+  FusedArgs g{};
+  g.model = p.model; g.adversarial = p.adversarial;
+  g.gamma = p.gamma; g.Tl2e = p.adv_temperature * kLog2e; g.inv2B = 0.5f / (float)p.B; g.uni = 1.f / (float)p.Ns;
+  g.reg_coef = p.reg_coef; g.reg_norm = p.reg_norm;
+  g.C = p.C; g.D = p.D; g.nblkD = slab_blocks(p.D);
+  const bool P = mode == 0;
+  g.Rx = P ? p.Cs : p.Ns; g.Ry = P ? p.Ns : p.Cs;
+  g.N1 = pad16(g.Ry);
+  int wc = (512 - 2 * g.N1) & ~31;
+  if (wc > 256) wc = 256;
+  const int dpad = (p.D + 31) & ~31;
+  if (wc > dpad) wc = dpad;
+  g.Wc = wc;
+  g.stage1Bytes = 2u * 16384u + 2u * (uint32_t)g.N1 * 128u;
+  g.stage2Bytes = 2u * (uint32_t)(wc >> 5) * 4096u;
+  g.nS1 = (int)(kRingBytes / g.stage1Bytes); if (g.nS1 > kMaxS1) g.nS1 = kMaxS1;
+  g.nS2 = (int)(kRingBytes / g.stage2Bytes); if (g.nS2 > kMaxS2) g.nS2 = kMaxS2;
+  if (g.nS1 < 2 || g.nS2 < 2 || wc < 32) { snprintf(err, errlen, "fused kernel: shape does not fit (N1=%d)", g.N1); return KGE_ERR_UNSUPPORTED; }
+  const float *Xh = P ? w.Ahi : w.Bhi, *Xl = P ? w.Alo : w.Blo, *Yh = P ? w.Bhi : w.Ahi, *Yl = P ? w.Blo : w.Alo;
+  g.x2 = P ? w.a2 : w.b2; g.y2 = P ? w.b2 : w.a2;
+  g.pos = w.pos; g.wt = wt; g.wbar = w.wbar;
+  g.gpos = w.gpos; g.rowsum = w.rowsum; g.pl = w.pl; g.nl = w.nl; g.stat_m = w.stat_m; g.stat_k = w.stat_k;
+  g.dumpS = P ? dumpS : nullptr; g.dumpV = dumpV;
+  g.cstat_m = w.stat_m; g.cstat_k = w.stat_k;
+  g.Xhi = Xh; g.Xlo = Xl;
+  g.gsn = w.gsn;
+  g.out = P ? w.GA : w.Bn;
+  const long long rowsX = (long long)p.C * g.Rx * g.nblkD, rowsY = (long long)p.C * g.Ry * g.nblkD;
+  CUtensorMap mXh, mXl, mYh1, mYl1, mYh2, mYl2;
+  if (!tc_make_map(&mXh, Xh, rowsX, 32, kTileM, err, errlen) || !tc_make_map(&mXl, Xl, rowsX, 32, kTileM, err, errlen) ||
+      !tc_make_map(&mYh1, Yh, rowsY, 32, g.N1, err, errlen) || !tc_make_map(&mYl1, Yl, rowsY, 32, g.N1, err, errlen) ||
+      !tc_make_map(&mYh2, Yh, rowsY, 32, 32, err, errlen, true) || !tc_make_map(&mYl2, Yl, rowsY, 32, 32, err, errlen, true))
+    return KGE_ERR_CUDA;
+  const size_t smem = kRingBytes + 1024;
+  static bool attr_set[2][64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !attr_set[mode][dev]) {
+    cudaError_t e = P ? cudaFuncSetAttribute(k_fused<F_P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                      : cudaFuncSetAttribute(k_fused<F_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { snprintf(err, errlen, "cudaFuncSetAttribute(k_fused): %s", cudaGetErrorString(e)); return KGE_ERR_CUDA; }
+    attr_set[mode][dev] = true;
+  }
+  const int mtiles = (g.Rx + kTileM - 1) / kTileM;
+  int grid = p.C * mtiles;
+  if (grid > c.num_sms) grid = c.num_sms;
+  if (P) KGE_LAUNCH_NAMED(c, "k_fused<P: S=A.Bn^T, loss, GA=V.Bn>", k_fused<F_P>, grid, kThreadsF, smem, mXh, mXl, mYh1, mYl1, mYh2, mYl2, g);
+  else KGE_LAUNCH_NAMED(c, "k_fused<N: S^T, G_neg=V^T.A, mean sq>", k_fused<F_N>, grid, kThreadsF, smem, mXh, mXl, mYh1, mYl1, mYh2, mYl2, g);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { snprintf(err, errlen, "k_fused launch: %s", cudaGetErrorString(e)); return KGE_ERR_CUDA; }
+  return KGE_OK;
+}
+
+}  // namespace kge

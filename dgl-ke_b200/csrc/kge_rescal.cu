@@ -33,8 +33,8 @@ __global__ void __launch_bounds__(kBlock) k_rescal_fwd(StepParams p, const float
     // kge_score_neg passes the negatives in place of the corrupted side: only the kept side is read
     if (!want_pos) { if (p.neg_head) h = t; else t = h; }
   } else {
-    h = w.NC + b.head_local[i] * (long long)D;
-    t = w.NC + b.tail_local[i] * (long long)D;
+    h = node_row(p, ent, b, w, b.head_local[i]);
+    t = node_row(p, ent, b, w, b.tail_local[i]);
     M = row_ptr(rel, b.rel_ids[i]);
   }
   for (int k = threadIdx.x; k < D; k += kBlock) { sh[k] = h[k]; st[k] = t[k]; }
@@ -125,8 +125,8 @@ __global__ void __launch_bounds__(kBlock) k_rescal_bwd(StepParams p, TableView e
   __shared__ float red[kWarps];
   const long long i = blockIdx.x;
   const long long hl = b.head_local[i], tl = b.tail_local[i], rid = b.rel_ids[i];
-  const float* h = w.NC + hl * (long long)D;
-  const float* t = w.NC + tl * (long long)D;
+  const float* h = node_row(p, ent, b, w, hl);
+  const float* t = node_row(p, ent, b, w, tl);
   const float* M = row_ptr(rel, rid);
   float* GR = w.GR + i * (long long)p.Dr;
   const float g = w.gpos[i];
@@ -190,8 +190,7 @@ __global__ void __launch_bounds__(kBlock) k_rescal_bwd(StepParams p, TableView e
   if (threadIdx.x == 0) {
     float s = 0.f;
     for (int q = 0; q < kWarps; ++q) s += red[q];
-    if (p.rel_deferred) w.gsr[i] = s / (float)p.Dr;
-    else table_atomic_add(rel, state_ptr(rel, rid), s / (float)p.Dr);
+    w.gsr[i] = s / (float)p.Dr;     // added to the relation's state_sum by the update (Adagrad phase 1)
   }
 }
 

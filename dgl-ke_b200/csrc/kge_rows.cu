@@ -186,8 +186,8 @@ __global__ void __launch_bounds__(kRowBlock) k_prep(StepParams p, TableView ent,
   const int lane = threadIdx.x & 31;
   const bool reg_on = (p.reg_coef > 0.f && p.reg_norm > 0);
   if (job < p.B) {
-    const float* h = w.NC + b.head_local[job] * (long long)p.D;     // local copies made by k_gather_nodes
-    const float* t = w.NC + b.tail_local[job] * (long long)p.D;
+    const float* h = node_row(p, ent, b, w, b.head_local[job]);     // local copies made by k_gather_nodes, or table rows
+    const float* t = node_row(p, ent, b, w, b.tail_local[job]);
     const float* r = row_ptr(rel, b.rel_ids[job]);
     float pos, a2, reg, nrm;
     const long long ro = job * (long long)p.D;
@@ -205,7 +205,8 @@ __global__ void __launch_bounds__(kRowBlock) k_prep(StepParams p, TableView ent,
   if (job < p.Nn) {
     const float* src = row_ptr(ent, b.neg_ids[job]);
     const long long ro = job * (long long)p.D;
-    const RowOut bo{w.Bn + ro, w.Bhi, w.Blo, job / p.Ns, slab_blocks(p.D), p.Ns, (int)(job % p.Ns)};
+    // fused contraction: the negatives exist only as TF32 hi/lo slabs (Bn receives their gradient later)
+    const RowOut bo{p.fused ? nullptr : w.Bn + ro, w.Bhi, w.Blo, job / p.Ns, slab_blocks(p.D), p.Ns, (int)(job % p.Ns)};
     float b2 = 0.f, reg = 0.f;
     const int nv = p.D >> 2;
     for (int v0 = 0; v0 < nv; v0 += kWarp * KIT) {
@@ -361,7 +362,8 @@ __device__ __forceinline__ float loss_elem(const LossRow& r, float sc, float dis
   nls += pij * (softplusf(sc) * r.w_i);
   const float g = pij * sigmoidf(sc) * r.w_i * r.inv2B;       // dL/dneg_ij
   float coef = g;
-  if (r.l2) { coef = g / dist; rs += coef; }                  // dist = |a-b| from the score kernel
+  // dist = |a-b| from the score kernel; a clamped distance (sq <= 1e-30) has zero gradient in the reference (clamp_min_)
+  if (r.l2) { coef = (dist > 1.5e-15f) ? g / dist : 0.f; rs += coef; }
   return coef;
 }
 
@@ -490,32 +492,32 @@ __global__ void __launch_bounds__(1024) k_mean(const float* __restrict__ x, long
 // log4 = {pos_loss, neg_loss, loss (no reg), reg}.  kRedBlocks CTAs reduce fixed slices into partials;
 // the CTA that finishes last (ticket counter) adds the partials in index order => deterministic.
 constexpr int kRedBlocks = 64;
-__global__ void __launch_bounds__(256) k_reduce_log(StepParams p, const float* __restrict__ pl,
-                                                     const float* __restrict__ nl, const float* __restrict__ regp,
-                                                     long long nreg, const float* __restrict__ wbar,
-                                                     float* __restrict__ partial, unsigned int* __restrict__ ticket,
-                                                     float* __restrict__ log4) {
+__device__ void reduce_log_part(const StepParams& p, const StepWs& w, long long nreg, const float* wbar, float* log4,
+                                int bid, int nb) {
   __shared__ float sh[32];
   __shared__ bool last;
+  const float *pl = w.pl, *nl = w.nl, *regp = w.regp;
+  float* partial = w.red_partial;
+  unsigned int* ticket = w.red_ticket;
   float a = 0.f, b = 0.f, r = 0.f;
-  const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
+  const long long t0 = (long long)bid * blockDim.x + threadIdx.x, stride = (long long)nb * blockDim.x;
   for (long long i = t0; i < p.B; i += stride) { a += pl[i]; b += nl[i]; }
   for (long long i = t0; i < nreg; i += stride) r += regp[i];
   a = block_sum(a, sh);
   b = block_sum(b, sh);
   r = block_sum(r, sh);
   if (threadIdx.x == 0) {
-    partial[blockIdx.x * 3 + 0] = a; partial[blockIdx.x * 3 + 1] = b; partial[blockIdx.x * 3 + 2] = r;
+    partial[bid * 3 + 0] = a; partial[bid * 3 + 1] = b; partial[bid * 3 + 2] = r;
     __threadfence();
     unsigned int t = atomicAdd(ticket, 1u);
-    last = (t == gridDim.x - 1);
+    last = (t == (unsigned int)nb - 1);
   }
   __syncthreads();
   if (last) {
     __threadfence();
-    // fixed-order tree over the kRedBlocks partials (one per thread of warp 0..1), deterministic
+    // fixed-order tree over the partials (one per thread), deterministic
     float sa = 0.f, sb = 0.f, sr = 0.f;
-    if (threadIdx.x < gridDim.x) {
+    if ((int)threadIdx.x < nb) {
       sa = ((volatile float*)partial)[threadIdx.x * 3 + 0];
       sb = ((volatile float*)partial)[threadIdx.x * 3 + 1];
       sr = ((volatile float*)partial)[threadIdx.x * 3 + 2];
@@ -533,6 +535,13 @@ __global__ void __launch_bounds__(256) k_reduce_log(StepParams p, const float* _
   }
 }
 
+// log4 = {pos_loss, neg_loss, loss (no reg), reg}.  kRedBlocks CTAs reduce fixed slices into partials;
+// the CTA that finishes last (ticket counter) adds the partials in index order => deterministic.
+__global__ void __launch_bounds__(256) k_reduce_log(StepParams p, StepWs w, long long nreg, const float* __restrict__ wbar,
+                                                     float* __restrict__ log4) {
+  reduce_log_part(p, w, nreg, wbar, log4, blockIdx.x, gridDim.x);
+}
+
 void launch_wbar(const LaunchCtx& c, const StepParams& p, const float* wt, const StepWs& w) {
   if (wt) KGE_LAUNCH(c, k_mean, 1, 1024, 0, wt, p.B, w.wbar);
 }
@@ -541,8 +550,7 @@ void launch_reduce_log(const LaunchCtx& c, const StepParams& p, const float* wt,
                        bool want_reg) {
   const bool reg_on = want_reg && (p.reg_coef > 0.f && p.reg_norm > 0);
   if (log4)
-    KGE_LAUNCH(c, k_reduce_log, kRedBlocks, 256, 0, p, w.pl, w.nl, w.regp, reg_on ? (p.B + p.Nn + p.U) : 0,
-               wt ? w.wbar : nullptr, w.red_partial, w.red_ticket, log4);
+    KGE_LAUNCH(c, k_reduce_log, kRedBlocks, 256, 0, p, w, reg_on ? (p.B + p.Nn + p.U) : 0, wt ? w.wbar : nullptr, log4);
 }
 
 void launch_loss_rows(const LaunchCtx& c, const StepParams& p, const float* pos, const float* S, const float* wt,
@@ -574,13 +582,16 @@ __global__ void __launch_bounds__(kRowBlock) k_chain(StepParams p, TableView ent
   if (i >= p.B) return;
   const int lane = threadIdx.x & 31;
   const long long hl = b.head_local[i], tl = b.tail_local[i], rid = b.rel_ids[i];
-  const float* h = w.NC + hl * (long long)p.D;
-  const float* t = w.NC + tl * (long long)p.D;
+  const float* h = node_row(p, ent, b, w, hl);
+  const float* t = node_row(p, ent, b, w, tl);
   const float* r = row_ptr(rel, rid);
   const float* ga = w.GA + i * (long long)p.D;
   float* ngh = w.NG + hl * (long long)p.D;
   float* ngt = w.NG + tl * (long long)p.D;
-  float* gr = w.GR + i * (long long)p.Dr;
+  // relation gradient: its own row per edge (what the reference traces), or summed per relation (fused step)
+  float* gr = p.rel_dense ? (w.rg + rid * (long long)p.Dr) : (w.GR + i * (long long)p.Dr);
+  const bool dense = p.rel_dense != 0;
+  auto rel_out = [&](int col, float4 v) { if (dense) red_add4(gr + col, v); else st4(gr + col, v); };
   const float gp = w.gpos[i];
   float gs = 0.f;
 
@@ -636,14 +647,14 @@ __global__ void __launch_bounds__(kRowBlock) k_chain(StepParams p, TableView ent
       if (MODEL == KGE_COMPLEX) {
         float4 g0 = f4_add(dcr, reg_grad4(cr, p.reg_norm, p.reg_coef));
         float4 g1 = f4_add(dci, reg_grad4(ci, p.reg_norm, p.reg_coef));
-        st4(gr + 4 * v, g0); st4(gr + half + 4 * v, g1);
+        rel_out(4 * v, g0); rel_out(half + 4 * v, g1);
         gs += f4_dot(g0, g0) + f4_dot(g1, g1);
       } else {
         // d/dphase = -dc*sin + ds*cos ; d/dr = d/dphase / (emb_init/pi)
         float4 dth = f4_sub(f4_mul(dci, cr), f4_mul(dcr, ci));
         float4 g0 = make_float4(dth.x / den, dth.y / den, dth.z / den, dth.w / den);
         g0 = f4_add(g0, reg_grad4(ph, p.reg_norm, p.reg_coef));
-        st4(gr + 4 * v, g0);
+        rel_out(4 * v, g0);
         gs += f4_dot(g0, g0);
       }
     }
@@ -691,15 +702,16 @@ __global__ void __launch_bounds__(kRowBlock) k_chain(StepParams p, TableView ent
         red_add4(ngh + 4 * v, dh);
         red_add4(ngt + 4 * v, dt);
         dr = f4_add(dr, reg_grad4(r4, p.reg_norm, p.reg_coef));
-        st4(gr + 4 * v, dr);
+        rel_out(4 * v, dr);
         gs += f4_dot(dr, dr);
       }
     }
   }
+  // mean(g^2) of this edge's relation row: added to state_sum by the update (Adagrad phase 1), never here
   gs = warp_sum(gs);
   if (lane == 0) {
-    if (p.rel_deferred) w.gsr[i] = gs / (float)p.Dr;
-    else table_atomic_add(rel, state_ptr(rel, rid), gs / (float)p.Dr);
+    if (dense) atomicAdd(w.rgs + rid, gs / (float)p.Dr);
+    else w.gsr[i] = gs / (float)p.Dr;
   }
 }
 
@@ -713,26 +725,68 @@ void launch_chain(const LaunchCtx& c, const StepParams& p, const TableView& ent,
 }
 
 // ------------------------------------------------------------------------------------------ a10
-// Entity entry 1: the unique positive nodes (indices unique => no atomics, state and row are
-// updated by the same warp).  Also re-zeroes NG for the next step.
-__global__ void __launch_bounds__(kRowBlock) k_upd_nodes(StepParams p, TableView ent, BatchView b, StepWs w) {
-  const long long u = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-  if (u >= p.U) return;
-  const int lane = threadIdx.x & 31;
+// ExternalEmbedding.update (tensor_models.py:304-362) of the step's trace entries, as ONE kernel of three phases
+// separated by grid barriers (cooperative launch: every CTA is resident), or as three launches of one phase each:
+//
+//   phase 1  entity entry 1: the unique positive nodes.  Indices are unique => state and row are updated by the
+//            same warp without atomics (across GPUs: system-scope atomics).  Re-zeroes NG.  Also the dense
+//            per-relation Adagrad of the fused step (rel_dense: unique rows as well).
+//   phase 2  Adagrad phase 1 of the entries with possibly duplicated indices: state_sum[idx] += mean(g^2) for every
+//            row of entity entry 2 (negatives) and of the relation entry (per edge).
+//   phase 3  their phase 2: emb[idx] += -lr * g / (sqrt(state_sum[idx]) + 1e-10), then (fused step) the log scalars.
+//
+// The barriers reproduce the reference's order: entry 1 completes before entry 2 adds to state_sum; inside an entry
+// every state add lands before any row is scaled.
+struct UpdArgs {
+  StepParams p;
+  TableView ent, rel;
+  BatchView b;
+  StepWs w;
+  float* log4;          // non-null: phase 3 also reduces {pos_loss, neg_loss, loss, reg}
+  const float* wt;      // edge weights (for the log scalars) or null
+  int phase_lo, phase_hi;
+};
+
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// all CTAs of the (co-resident) grid; ctr is zero on entry and is left at gridDim.x
+__device__ __forceinline__ void grid_barrier(unsigned int* ctr) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(ctr, 1u);
+    while (ld_acquire_u32(ctr) < gridDim.x) __nanosleep(40);
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void upd_node(const StepParams& p, const TableView& ent, const BatchView& b, const StepWs& w,
+                                         long long u, int lane) {
   const long long id = b.node_ids[u];
   float* row = row_ptr(ent, id);
   float* ng = w.NG + u * (long long)p.D;
-  const float* nc = w.NC + u * (long long)p.D;      // the traced copy of the row (what the reference regularises)
+  const float* nc = node_row(p, ent, b, w, u);      // the traced copy of the row (what the reference regularises)
   const int nv = p.D >> 2;
   const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
   const bool sharded = ent.n_shards > 1;
-  // pass 1 (local memory only): g = NG + reg'(x), mean(g^2)
-  float gs = 0.f;
+  const bool reg_on = (p.reg_coef > 0.f && p.reg_norm > 0);
+  // pass 1: g = NG + reg'(x), mean(g^2)
+  float gs = 0.f, reg = 0.f;
   for (int v = lane; v < nv; v += kWarp) {
-    float4 g = f4_add(ld4(ng + 4 * v), reg_grad4(ld4(nc + 4 * v), p.reg_norm, p.reg_coef));
+    const float4 x = ld4(nc + 4 * v);
+    float4 g = f4_add(ld4(ng + 4 * v), reg_grad4(x, p.reg_norm, p.reg_coef));
     gs += f4_dot(g, g);
+    if (reg_on && !p.use_nc) reg += abs_pow4_sum(x, p.reg_norm);
   }
   gs = warp_sum(gs) / (float)p.D;
+  if (!p.use_nc) {            // no k_gather_nodes ran: this node's share of the regulariser is produced here
+    reg = warp_sum(reg);
+    if (lane == 0) w.regp[p.B + p.Nn + u] = reg;
+  }
   float* st = state_ptr(ent, id);
   float s_new = 0.f;
   if (lane == 0) {
@@ -741,8 +795,8 @@ __global__ void __launch_bounds__(kRowBlock) k_upd_nodes(StepParams p, TableView
   }
   s_new = __shfl_sync(0xffffffffu, s_new, 0);
   const float stdv = sqrtf(s_new) + 1e-10f;
-  // pass 2: emb[id] += -lr * g / std.  Indices are unique, so on one GPU the new row is (traced copy + step) with
-  // no read of the table; across GPUs the step is a system-scope red.add (no read either, and atomic w.r.t. peers).
+  // pass 2: emb[id] += -lr * g / std.  Indices are unique, so on one GPU the new row is (traced copy + step);
+  // across GPUs the step is a system-scope red.add (atomic w.r.t. peers).
   for (int v = lane; v < nv; v += kWarp) {
     float4 x = ld4(nc + 4 * v);
     float4 g = f4_add(ld4(ng + 4 * v), reg_grad4(x, p.reg_norm, p.reg_coef));
@@ -753,7 +807,141 @@ __global__ void __launch_bounds__(kRowBlock) k_upd_nodes(StepParams p, TableView
   }
 }
 
-// Entity entry 2, phase 1: state_sum[neg_id] += mean(G_neg^2)   (duplicates accumulate)
+// dense per-relation Adagrad (unique rows): summing the occurrences first is the same math as
+// ExternalEmbedding.update, every occurrence is scaled by the same final state (tensor_models.py:352-361)
+__device__ __forceinline__ void upd_rel_dense(const TableView& rel, float* rg, float* rgs, long long r, float lr, int lane) {
+  const float gs = rgs[r];
+  if (gs == 0.f) return;           // relation not touched this step
+  float* st = state_ptr(rel, r);
+  float s_new = 0.f;
+  if (lane == 0) { s_new = *st + gs; *st = s_new; }
+  s_new = __shfl_sync(0xffffffffu, s_new, 0);
+  __syncwarp();
+  if (lane == 0) rgs[r] = 0.f;
+  const float stdv = sqrtf(s_new) + 1e-10f;
+  float* row = row_ptr(rel, r);
+  float* g = rg + r * (long long)rel.dim;
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int v = lane; v < (rel.dim >> 2); v += kWarp) {
+    float4 x = ld4(g + 4 * v), e = ld4(row + 4 * v);
+    st4(row + 4 * v, f4_add(e, make_float4((-lr * x.x) / stdv, (-lr * x.y) / stdv, (-lr * x.z) / stdv, (-lr * x.w) / stdv)));
+    st4(g + 4 * v, z);
+  }
+}
+
+__device__ __forceinline__ void apply_row(const TableView& t, long long id, const float* g, int dim, float lr, int lane) {
+  const float stdv = sqrtf(*state_ptr(t, id)) + 1e-10f;
+  float* row = row_ptr(t, id);
+  for (int v = lane; v < (dim >> 2); v += kWarp) {
+    float4 x = ld4(g + 4 * v);
+    table_red_add4(t, row + 4 * v, make_float4((-lr * x.x) / stdv, (-lr * x.y) / stdv, (-lr * x.z) / stdv, (-lr * x.w) / stdv));
+  }
+  for (int k = ((dim >> 2) << 2) + lane; k < dim; k += kWarp) atomicAdd(row + k, (-lr * g[k]) / stdv);
+}
+
+__device__ void reduce_log_part(const StepParams& p, const StepWs& w, long long nreg, const float* wbar, float* log4,
+                                int bid, int nb);
+
+__global__ void __launch_bounds__(kRowBlock) k_update(UpdArgs a) {
+  const StepParams& p = a.p;
+  const StepWs& w = a.w;
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * kWarpsPerBlock;
+  const bool rel_edge = !p.rel_deferred && !p.rel_dense;      // relation entry handled per edge, here
+  for (int phase = a.phase_lo; phase <= a.phase_hi; ++phase) {
+    if (phase == 1) {
+      const long long nrel = p.rel_dense ? a.rel.num_rows : 0;
+      for (long long j = warp0; j < p.U + nrel; j += nwarps) {
+        if (j < p.U) upd_node(p, a.ent, a.b, w, j, lane);
+        else upd_rel_dense(a.rel, w.rg, w.rgs, j - p.U, p.lr, lane);
+      }
+    } else if (phase == 2) {
+      if (p.fused) {
+        // mean(G_neg^2) came out of the fused kernel's epilogue: one scalar atomic per negative row
+        const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x, nt = (long long)gridDim.x * blockDim.x;
+        for (long long j = t0; j < p.Nn; j += nt) table_atomic_add(a.ent, state_ptr(a.ent, a.b.neg_ids[j]), w.gsn[j]);
+      } else {
+        for (long long j = warp0; j < p.Nn; j += nwarps) {
+          const float* g = w.Bn + j * (long long)p.D;
+          float gs = 0.f;
+          for (int v = lane; v < (p.D >> 2); v += kWarp) { float4 x = ld4(g + 4 * v); gs += f4_dot(x, x); }
+          gs = warp_sum(gs);
+          if (lane == 0) table_atomic_add(a.ent, state_ptr(a.ent, a.b.neg_ids[j]), gs / (float)p.D);
+        }
+      }
+      if (rel_edge) {
+        const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x, nt = (long long)gridDim.x * blockDim.x;
+        for (long long i = t0; i < p.B; i += nt) table_atomic_add(a.rel, state_ptr(a.rel, a.b.rel_ids[i]), w.gsr[i]);
+      }
+    } else {
+      const long long nr = rel_edge ? p.B : 0;
+      for (long long j = warp0; j < p.Nn + nr; j += nwarps) {
+        if (j < p.Nn) apply_row(a.ent, a.b.neg_ids[j], w.Bn + j * (long long)p.D, p.D, p.lr, lane);
+        else apply_row(a.rel, a.b.rel_ids[j - p.Nn], w.GR + (j - p.Nn) * (long long)p.Dr, p.Dr, p.lr, lane);
+      }
+      if (a.log4) {
+        const int nb = gridDim.x < 64 ? gridDim.x : 64;
+        const bool reg_on = (p.reg_coef > 0.f && p.reg_norm > 0);
+        if ((int)blockIdx.x < nb)
+          reduce_log_part(p, w, reg_on ? (p.B + p.Nn + p.U) : 0, a.wt ? w.wbar : nullptr, a.log4, blockIdx.x, nb);
+      }
+    }
+    if (phase < a.phase_hi) grid_barrier(w.sync_ctr + (phase - 1));
+  }
+  if (a.phase_hi > a.phase_lo) {
+    // leave the barrier counters at zero for the next launch: the last CTA to get here resets them
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      if (atomicAdd(w.sync_ctr + 3, 1u) == gridDim.x - 1) {
+        w.sync_ctr[0] = 0u; w.sync_ctr[1] = 0u; w.sync_ctr[2] = 0u;
+        __threadfence();
+        w.sync_ctr[3] = 0u;
+      }
+    }
+  }
+}
+
+int launch_update(const LaunchCtx& c, const StepParams& p, const TableView& ent, const TableView& rel,
+                  const BatchView& b, const StepWs& w, float* log4, const float* wt) {
+  UpdArgs a{p, ent, rel, b, w, log4, wt, 1, 3};
+  // job counts per phase (warps): nodes (+ relations), negatives (+ edges), negatives + edges
+  const long long nrel = p.rel_dense ? rel.num_rows : 0;
+  const long long nr = (!p.rel_deferred && !p.rel_dense) ? p.B : 0;
+  long long jobs = p.U + nrel;
+  if (p.Nn + nr > jobs) jobs = p.Nn + nr;
+  static int occ[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && occ[dev] == 0) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_update, kRowBlock, 0) != cudaSuccess || n < 1) n = 1;
+    occ[dev] = n;
+  }
+  static const bool no_coop = getenv("KGE_B200_NO_COOP") != nullptr;
+  const int max_resident = c.num_sms * (dev >= 0 && dev < 64 ? occ[dev] : 1);
+  int grid = ceil_div(jobs, kWarpsPerBlock);
+  if (!no_coop) {
+    if (grid > max_resident) grid = max_resident;
+    void* args[] = {&a};
+    prof_begin(c, "k_update<nodes | state adds | apply>");
+    cudaError_t e = cudaLaunchCooperativeKernel((void*)k_update, dim3(grid), dim3(kRowBlock), args, 0, c.stream);
+    prof_end(c);
+    if (c.launch_counter) ++*c.launch_counter;
+    if (e == cudaSuccess) return KGE_OK;
+    cudaGetLastError();
+    return KGE_ERR_CUDA;
+  }
+  for (int ph = 1; ph <= 3; ++ph) {
+    a.phase_lo = a.phase_hi = ph;
+    const char* nm = ph == 1 ? "k_update<nodes>" : (ph == 2 ? "k_update<state adds>" : "k_update<apply>");
+    KGE_LAUNCH_NAMED(c, nm, k_update, grid, kRowBlock, 0, a);
+  }
+  return KGE_OK;
+}
+
+// one trace entry with possibly duplicated indices (kge_adagrad)
 __global__ void __launch_bounds__(kRowBlock) k_state_add(TableView t, const long long* __restrict__ idx,
                                                           const float* __restrict__ grad, long long n, int dim) {
   const long long j = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
@@ -766,64 +954,11 @@ __global__ void __launch_bounds__(kRowBlock) k_state_add(TableView t, const long
   gs = warp_sum(gs);
   if (lane == 0) table_atomic_add(t, state_ptr(t, idx[j]), gs / (float)dim);
 }
-
-// phase 2 of an entry with possibly duplicated indices: emb[idx] += -lr * g / (sqrt(state[idx]) + 1e-10)
 __global__ void __launch_bounds__(kRowBlock) k_apply(TableView t, const long long* __restrict__ idx,
                                                       const float* __restrict__ grad, long long n, int dim, float lr) {
   const long long j = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   if (j >= n) return;
-  const int lane = threadIdx.x & 31;
-  const long long id = idx[j];
-  const float stdv = sqrtf(*state_ptr(t, id)) + 1e-10f;
-  const float* g = grad + j * (long long)dim;
-  float* row = row_ptr(t, id);
-  for (int v = lane; v < (dim >> 2); v += kWarp) {
-    float4 x = ld4(g + 4 * v);
-    table_red_add4(t, row + 4 * v, make_float4((-lr * x.x) / stdv, (-lr * x.y) / stdv, (-lr * x.z) / stdv, (-lr * x.w) / stdv));
-  }
-  for (int k = ((dim >> 2) << 2) + lane; k < dim; k += kWarp) atomicAdd(row + k, (-lr * g[k]) / stdv);
-}
-
-void launch_update_entities(const LaunchCtx& c, const StepParams& p, const TableView& ent, const BatchView& b,
-                            const StepWs& w) {
-  // entity entry 1 (unique positive nodes) -- must finish before entry 2 touches state_sum
-  KGE_LAUNCH(c, k_upd_nodes, ceil_div(p.U, kWarpsPerBlock), kRowBlock, 0, p, ent, b, w);
-  // entity entry 2 (negatives; their gradient lives where the gathered rows were)
-  KGE_LAUNCH(c, k_state_add, ceil_div(p.Nn, kWarpsPerBlock), kRowBlock, 0, ent, b.neg_ids, w.Bn, p.Nn, p.D);
-  KGE_LAUNCH(c, k_apply, ceil_div(p.Nn, kWarpsPerBlock), kRowBlock, 0, ent, b.neg_ids, w.Bn, p.Nn, p.D, p.lr);
-}
-
-// negatives (entity entry 2, phase 2) and relation rows in ONE launch: job space [0,Nn) | [Nn, Nn+B)
-__global__ void __launch_bounds__(kRowBlock) k_apply2(TableView ent, const long long* __restrict__ neg_ids,
-                                                       const float* __restrict__ gneg, long long Nn, int D,
-                                                       TableView rel, const long long* __restrict__ rel_ids,
-                                                       const float* __restrict__ grel, long long B, int Dr, float lr) {
-  long long j = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  const bool is_rel = j >= Nn;
-  if (is_rel) j -= Nn;
-  if (is_rel && j >= B) return;
-  const TableView& t = is_rel ? rel : ent;
-  const int dim = is_rel ? Dr : D;
-  const long long id = is_rel ? rel_ids[j] : neg_ids[j];
-  const float stdv = sqrtf(*state_ptr(t, id)) + 1e-10f;
-  const float* g = (is_rel ? grel : gneg) + j * (long long)dim;
-  float* row = row_ptr(t, id);
-  for (int v = lane; v < (dim >> 2); v += kWarp) {
-    float4 x = ld4(g + 4 * v);
-    table_red_add4(t, row + 4 * v, make_float4((-lr * x.x) / stdv, (-lr * x.y) / stdv, (-lr * x.z) / stdv, (-lr * x.w) / stdv));
-  }
-}
-
-void launch_update(const LaunchCtx& c, const StepParams& p, const TableView& ent, const TableView& rel,
-                   const BatchView& b, const StepWs& w) {
-  if (p.rel_deferred) { launch_update_entities(c, p, ent, b, w); return; }
-  // entity entry 1 (unique positive nodes) -- must finish before entry 2 touches state_sum
-  KGE_LAUNCH(c, k_upd_nodes, ceil_div(p.U, kWarpsPerBlock), kRowBlock, 0, p, ent, b, w);
-  KGE_LAUNCH(c, k_state_add, ceil_div(p.Nn, kWarpsPerBlock), kRowBlock, 0, ent, b.neg_ids, w.Bn, p.Nn, p.D);
-  // entry 2 rows + relation rows (their state was accumulated by k_chain)
-  KGE_LAUNCH(c, k_apply2, ceil_div(p.Nn + p.B, kWarpsPerBlock), kRowBlock, 0, ent, b.neg_ids, w.Bn, p.Nn, p.D, rel,
-             b.rel_ids, w.GR, p.B, p.Dr, p.lr);
+  apply_row(t, idx[j], grad + j * (long long)dim, dim, lr, threadIdx.x & 31);
 }
 
 // ---- multi-GPU relation path: per-edge gradients -> dense per-relation sums (all-reduced by the host
@@ -884,7 +1019,7 @@ __global__ void __launch_bounds__(kRowBlock) k_node_grad_reg(StepParams p, Table
   const long long u = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   if (u >= p.U) return;
   const int lane = threadIdx.x & 31;
-  const float* row = w.NC + u * (long long)p.D;
+  const float* row = node_row(p, ent, b, w, u);
   for (int v = lane; v < (p.D >> 2); v += kWarp)
     st4(out + u * (long long)p.D + 4 * v,
         f4_add(ld4(w.NG + u * (long long)p.D + 4 * v), reg_grad4(ld4(row + 4 * v), p.reg_norm, p.reg_coef)));

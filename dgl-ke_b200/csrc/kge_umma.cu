@@ -16,8 +16,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include "kge_common.cuh"
+#include "kge_tc.cuh"
 
 namespace kge {
+
+using namespace tc;
 
 namespace {
 
@@ -29,90 +32,6 @@ constexpr int kThreads = 320;                // warp 0 TMA, warp 1 MMA, warps 2.
 constexpr int kTmemCols = 256;
 
 enum { G_SCORE = 0, G_GA = 1, G_GB = 2 };
-
-__device__ __forceinline__ unsigned long long gtime() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-  } while (!done);
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int y) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y) : "memory");
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
-  uint32_t r[8];
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-  uint32_t r[16];
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                 "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-               : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// shared-memory matrix descriptor, 128-byte swizzle (cute::UMMA::SmemDescriptor bit layout)
-// layout_type: 2 = SWIZZLE_128B (K-major operands), 1 = SWIZZLE_128B_BASE32B (the only layout the
-// tensor core accepts for MN-major tf32 operands; matches TMA's SWIZZLE_128B_ATOM_32B)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type = 2) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;            // descriptor version (Blackwell)
-  d |= (uint64_t)layout_type << 61;
-  return d;
-}
-// instruction descriptor: D=f32, A=B=tf32, majors, N>>3, M>>4 (cute::UMMA::InstrDescriptor)
-__host__ __device__ inline uint32_t make_idesc(int M, int N, bool a_mn, bool b_mn) {
-  uint32_t d = 0;
-  d |= 1u << 4;                      // c_format = F32
-  d |= 2u << 7;                      // a_format = TF32
-  d |= 2u << 10;                     // b_format = TF32
-  d |= (a_mn ? 1u : 0u) << 15;
-  d |= (b_mn ? 1u : 0u) << 16;
-  d |= (uint32_t)(N >> 3) << 17;
-  d |= (uint32_t)(M >> 4) << 24;
-  return d;
-}
 
 struct GemmArgs {
   int mode;              // G_SCORE / G_GA / G_GB
@@ -396,9 +315,9 @@ encode_fn_t get_encode() {
 
 // cuTensorMapEncodeTiled costs ~0.1 ms per call on this driver; the workspace matrices keep their
 // addresses between steps, so the encoded maps are cached (per host thread).
-struct MapKey { const void* base; long long rows, cols; int box_rows; bool mn; };
+struct MapKey { const void* base; long long rows, cols; int box_rows; bool mn; int dev; };
 struct MapCache {
-  static constexpr int kN = 32;
+  static constexpr int kN = 64;
   MapKey keys[kN];
   CUtensorMap maps[kN];
   int n = 0, next = 0;
@@ -411,16 +330,18 @@ bool make_map_uncached(CUtensorMap* m, const float* base, long long rows, long l
 bool make_map(CUtensorMap* m, const float* base, long long rows, long long cols, int box_rows, char* err, size_t errlen,
               bool mn_major = false) {
   MapCache& mc = g_maps;
+  int dev = 0;
+  cudaGetDevice(&dev);
   for (int i = 0; i < mc.n; ++i) {
     const MapKey& k = mc.keys[i];
-    if (k.base == base && k.rows == rows && k.cols == cols && k.box_rows == box_rows && k.mn == mn_major) {
+    if (k.base == base && k.rows == rows && k.cols == cols && k.box_rows == box_rows && k.mn == mn_major && k.dev == dev) {
       *m = mc.maps[i];
       return true;
     }
   }
   if (!make_map_uncached(m, base, rows, cols, box_rows, err, errlen, mn_major)) return false;
   int slot = mc.n < MapCache::kN ? mc.n++ : (mc.next++ % MapCache::kN);
-  mc.keys[slot] = MapKey{base, rows, cols, box_rows, mn_major};
+  mc.keys[slot] = MapKey{base, rows, cols, box_rows, mn_major, dev};
   mc.maps[slot] = *m;
   return true;
 }
@@ -495,6 +416,11 @@ int launch_gemm(const LaunchCtx& c, const CUtensorMap& ah, const CUtensorMap& al
 }
 
 }  // namespace
+
+bool tc_make_map(CUtensorMap* m, const float* base, long long rows, long long cols, int box_rows, char* err, size_t errlen,
+                 bool mn_major) {
+  return make_map(m, base, rows, cols, box_rows, err, errlen, mn_major);
+}
 
 bool umma_supported(const StepParams& p) {
   const bool model_ok = p.model == KGE_TRANSE_L2 || p.model == KGE_DISTMULT || p.model == KGE_COMPLEX || p.model == KGE_RESCAL;

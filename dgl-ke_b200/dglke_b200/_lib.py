@@ -18,7 +18,7 @@ BUF_POS_SCORE, BUF_NEG_SCORE, BUF_NODE_GRAD, BUF_NEG_GRAD, BUF_REL_GRAD = range(
 EXPORTS = ["kge_abi_version", "kge_last_error", "kge_create", "kge_destroy", "kge_gather", "kge_score_pos",
            "kge_score_neg", "kge_loss_grad", "kge_adagrad", "kge_forward_backward", "kge_update",
            "kge_step_fused", "kge_step_fused_host", "kge_sync", "kge_debug_read", "kge_launch_count",
-           "kge_set_engine", "kge_profile_enable", "kge_profile_read", "kge_set_relation_mode",
+           "kge_set_engine", "kge_set_fused", "kge_debug_set_dump", "kge_profile_enable", "kge_profile_read", "kge_set_relation_mode",
            "kge_rel_grad_dense", "kge_rel_apply_dense", "kge_device_alloc", "kge_device_free", "kge_ipc_export",
            "kge_ipc_open"]
 
@@ -83,6 +83,8 @@ def load_library():
     lib.kge_launch_count.argtypes = [vp]
     lib.kge_launch_count.restype = i64
     lib.kge_set_engine.argtypes = [vp, C.c_int]
+    lib.kge_set_fused.argtypes = [vp, C.c_int]
+    lib.kge_debug_set_dump.argtypes = [vp, vp]
     lib.kge_profile_enable.argtypes = [vp, C.c_int]
     lib.kge_profile_read.argtypes = [vp, C.c_char_p, C.c_int, P(f32), C.c_int]
     lib.kge_set_relation_mode.argtypes = [vp, C.c_int]
@@ -143,6 +145,15 @@ class Handle:
 
     def set_engine(self, engine):
         check(self.lib.kge_set_engine(self._h, int(engine)))
+
+    def set_fused(self, mode):
+        """-1 / 1: fused tcgen05 contraction kernel when the shape allows (default); 0: separate GEMM + loss kernels."""
+        check(self.lib.kge_set_fused(self._h, int(mode)))
+
+    def set_dump(self, tensor):
+        """test hook: device float tensor of 2 * batch * Ns elements receiving the fused kernel's coefficients (or None)"""
+        self._dump_keep = tensor
+        check(self.lib.kge_debug_set_dump(self._h, C.c_void_p(tensor.data_ptr()) if tensor is not None else None))
 
     def profile_enable(self, on=True):
         check(self.lib.kge_profile_enable(self._h, 1 if on else 0))

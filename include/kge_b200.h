@@ -209,6 +209,15 @@ KGE_API int kge_profile_read(kge_handle_t h, char* names, int names_len, float* 
  * (bilinear models), -1 = library default. */
 KGE_API int kge_set_engine(kge_handle_t h, int engine);
 
+/* Selects the contraction schedule of the bilinear / L2 models: -1 (default) or 1 = the fused tcgen05 kernel
+ * (score -> loss -> coefficients in TMEM -> gradient GEMM, kge_fused.cu) whenever the chunk shape fits its TMEM budget
+ * (chunk_size, neg_sample_size <= 240), 0 = separate GEMM / loss kernels. */
+KGE_API int kge_set_fused(kge_handle_t h, int mode);
+/* Test hook: when non-null, the fused kernel also writes its backward coefficients dL/dneg_ij (/ dist_ij for
+ * TransE_l2) to coef_dump: [batch, Ns] as seen by the positive-side pass, then [C*Ns, chunk_size] as recomputed by the
+ * negative-side pass (device memory, 2 * batch * Ns floats). */
+KGE_API int kge_debug_set_dump(kge_handle_t h, float* coef_dump);
+
 /* --- multi-GPU: row-range sharded entity table over peer-mapped HBM, replicated relation table ---
  * Replaces --mix_cpu_gpu's host-pinned shared table (general_models.py:230-231, train.py:92-95):
  * each rank allocates its shard, exports it with kge_ipc_export, opens every peer's shard with
