@@ -60,7 +60,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA graphs (profiling)")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
-    ap.add_argument("--cpu-procs", type=int, default=0, help="reference arm: worker processes (0 = probe 8/16/32/64/all and use the fastest)")
+    ap.add_argument("--cpu-procs", type=int, default=16, help="reference arm: Hogwild worker processes (default 16, capped by the host's cores: the fastest count on the 128-vCPU GPU hosts, pinned so that the GPU/CPU ratio does not move with a probe; 0 = probe 8/16/32/64/all and use the fastest)")
+    ap.add_argument("--cpu-impl", default="auto", choices=["auto", "reference", "port"], help="reference arm: the unmodified reference installed under baseline/_ref, or the oracle port")
     ap.add_argument("--cpu-batch", type=int, default=1000, help="reference arm: batch per worker (dglke_train's 1000)")
     return ap.parse_args()
 
@@ -88,27 +89,31 @@ def run_reference(args):
     B = args.cpu_batch // neg * neg or neg
     steps, warm = max(1, args.steps), max(1, args.warmup)
     t0 = time.time()
-    # "All the host threads it can use": Hogwild workers contend on the shared tables (FB15k has only 15k entity rows),
-    # so more workers is not monotonically faster -- on the 128-vCPU GPU-box hosts 16 workers reach ~3x the
-    # throughput of 128.  Probe a few worker counts briefly and time the best one.
-    cands = [args.cpu_procs] if args.cpu_procs else sorted({c for c in (8, 16, 32, 64, ncpu) if c <= ncpu} or {ncpu})
+    impl = args.cpu_impl
+    if impl == "auto":
+        impl = "reference" if cpu_bench.reference_installed() else "port"
+    # Hogwild workers contend on the shared tables (FB15k has only 15k entity rows), so more workers is not
+    # monotonically faster -- on the 128-vCPU GPU-box hosts 16 workers reach ~3x the throughput of 128.  The count is
+    # pinned (--cpu-procs, default 16); --cpu-procs 0 probes a few counts briefly and times the best one.
+    cands = [min(args.cpu_procs, ncpu)] if args.cpu_procs else sorted({c for c in (8, 16, 32, 64, ncpu) if c <= ncpu} or {ncpu})
     probe = {}
     if len(cands) > 1:
         for c in cands:
-            probe[c] = cpu_bench.hogwild_edges_per_sec(hp, n_ent_cpu, n_rel, B, neg, 3, 1, c)[0]
+            probe[c] = cpu_bench.hogwild_edges_per_sec(hp, n_ent_cpu, n_rel, B, neg, 3, 1, c, impl=impl)[0]
         nproc = max(probe, key=probe.get)
     else:
         nproc = cands[0]
-    eps, wall = cpu_bench.hogwild_edges_per_sec(hp, n_ent_cpu, n_rel, B, neg, steps, warm, nproc)
+    eps, wall = cpu_bench.hogwild_edges_per_sec(hp, n_ent_cpu, n_rel, B, neg, steps, warm, nproc, impl=impl)
     line = {
         "impl": "reference", "metric": METRIC, "value": eps, "unit": "edges/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warm, "ms_per_step": wall / steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": desc, "batch_per_worker": B, "workers": nproc,
                    "entities": n_ent_cpu, "entities_scaled_down": scaled,
-                   "note": "oracle port of the reference's PyTorch step (oracle/kge_oracle.py), dglke_train's "
-                           "process model: Hogwild workers on shared-memory tables, 1 thread each; sampling excluded"},
-        "cpu_baseline": {"value": eps, "unit": "edges/s", "cores": nproc, "kind": "port",
+                   "note": ("the UNMODIFIED reference (baseline/_ref: KEModel.forward -> loss.backward() -> update, dgl stubbed) "
+                            if impl == "reference" else "oracle port of the reference's PyTorch step (oracle/kge_oracle.py) ") +
+                           "under dglke_train's process model: Hogwild workers on shared-memory tables, 1 thread each; sampling excluded"},
+        "cpu_baseline": {"value": eps, "unit": "edges/s", "cores": nproc, "kind": impl,
                          "sample": "%d workers x %d steps x %d edges (%.1f s wall incl. setup and probe); probe edges/s by workers: %s"
                                    % (nproc, steps, B, time.time() - t0, {k: round(v) for k, v in probe.items()})},
         "e2e": {"value": eps, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -166,7 +171,7 @@ class ClockSampler:
 def cpu_baseline_subprocess(args):
     """Times the CPU oracle on a bounded sample in a fresh process (before CUDA is initialised here)."""
     cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", args.workload,
-           "--steps", "8", "--warmup", "2"]
+           "--steps", "8", "--warmup", "2", "--cpu-procs", str(args.cpu_procs), "--cpu-impl", args.cpu_impl]
     if args.n_ent:
         cmd += ["--n-ent", str(args.n_ent)]
     env = dict(os.environ)
@@ -359,11 +364,14 @@ def run_ours(args):
     e2e = edges / (ms_e2e * 1e-3)
     # roofline of the step's kernels: algorithmic bytes of one launch set (= one step) / summed kernel time
     achieved = B * bpe / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else 0.0
-    traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(args.workload)
-    except Exception:
-        pass
+    # DRAM traffic of one step from the committed ncu --set full capture -- only when that capture was taken on exactly
+    # this workload / batch / schedule on one GPU (profiles/summarize.py writes the key); null otherwise
+    traffic, traffic_key = None, "%s|B=%d|launches=%d" % (args.workload, B, per_step_launches)
+    if world == 1:
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json"))).get(traffic_key)
+        except Exception:
+            pass
     line = {
         "metric": METRIC, "value": value, "unit": "edges/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -379,7 +387,7 @@ def run_ours(args):
                 "ms_per_step": ms_e2e / K},
         "gpu_launches": gpu_launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                     "frac": achieved / hbm_peak, "traffic": traffic, "traffic_key": traffic_key, "peak_source": peak_src,
                      "kernel": "all %d kernels of one step (CUDA events around each launch, L2 flushed)" % per_step_launches,
                      "algorithmic_bytes_per_launch_set": B * bpe,
                      "kernel_ms": {k: round(v, 5) for k, v in sorted(prof.items(), key=lambda kv: -kv[1])},

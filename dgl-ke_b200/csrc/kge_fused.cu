@@ -69,6 +69,7 @@ struct FusedArgs {
   const float *Xhi, *Xlo;  // slabs of the lane-side rows (negatives): b = hi + lo in the epilogue
   float* gsn;            // [C*Rx] mean(G_neg^2)
   float* out;            // P: GA [C*Rx, D]; N: G_neg [C*Rx, D]
+  unsigned long long* dbg;   // optional per-CTA timestamps of the first tile (KGE_B200_FUSED_TIMING=1)
 };
 
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
@@ -116,6 +117,7 @@ k_fused(const __grid_constant__ CUtensorMap mXh, const __grid_constant__ CUtenso
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  if (g.dbg && threadIdx.x == 0) g.dbg[blockIdx.x * 8 + 0] = gtime();
 
   if (warp == 0) {
     // ================================ TMA producer ================================
@@ -169,6 +171,7 @@ k_fused(const __grid_constant__ CUtensorMap mXh, const __grid_constant__ CUtenso
         for (int kb = 0; kb < nkb1; ++kb, ++n1) {
           const uint32_t s = n1 % g.nS1;
           mbar_wait(&full1[s], (n1 / g.nS1) & 1);
+          if (g.dbg && n1 == 0) g.dbg[blockIdx.x * 8 + 1] = gtime();
           tc_fence_after();
           const uint32_t st = smem_u32(ring + (size_t)s * g.stage1Bytes);
           const uint32_t sXh = st, sXl = st + 16384, sYh = st + 32768, sYl = st + 32768 + yBytes1;
@@ -250,6 +253,8 @@ k_fused(const __grid_constant__ CUtensorMap mXh, const __grid_constant__ CUtenso
       float colsum = 0.f;
       mbar_wait(&s_full, it & 1);
       tc_fence_after();
+      const bool probe = g.dbg && it == 0 && threadIdx.x == 64;
+      if (probe) g.dbg[blockIdx.x * 8 + 2] = gtime();
 
       if (MODE == F_P) {
         const float w_i = (g.wt && row_ok) ? g.wt[gx] : 1.f;
@@ -390,6 +395,7 @@ k_fused(const __grid_constant__ CUtensorMap mXh, const __grid_constant__ CUtenso
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&v_ready);
+      if (probe) g.dbg[blockIdx.x * 8 + 3] = gtime();
 
       // ---- GEMM2 epilogue, one output-column chunk at a time ----
       float gsq = 0.f;
@@ -404,6 +410,8 @@ k_fused(const __grid_constant__ CUtensorMap mXh, const __grid_constant__ CUtenso
         const int npieces = (ce2 - cb2 + 15) >> 4;
         mbar_wait(&acc_full, nacc & 1);
         tc_fence_after();
+        if (probe && ch == 0) g.dbg[blockIdx.x * 8 + 4] = gtime();
+        if (probe && ch == nchunks - 1) g.dbg[blockIdx.x * 8 + 5] = gtime();
         auto release = [&]() {
           tc_fence_before();
           __syncwarp();
@@ -449,6 +457,7 @@ k_fused(const __grid_constant__ CUtensorMap mXh, const __grid_constant__ CUtenso
           if (npieces == 0) release();
         }
       }
+      if (probe) g.dbg[blockIdx.x * 8 + 6] = gtime();
       if (MODE == F_N) {
         epi_bar();                       // xch[2] (colsum exchange) has been read by everybody
         xch[3][ehalf][row] = gsq;
@@ -527,8 +536,29 @@ int fused_launch(const LaunchCtx& c, const StepParams& p, const StepWs& w, int m
   const int mtiles = (g.Rx + kTileM - 1) / kTileM;
   int grid = p.C * mtiles;
   if (grid > c.num_sms) grid = c.num_sms;
+  static const bool timing = getenv("KGE_B200_FUSED_TIMING") != nullptr;
+  unsigned long long* dbg = nullptr;
+  if (timing) { cudaMalloc(&dbg, (size_t)grid * 8 * sizeof(unsigned long long)); cudaMemset(dbg, 0, (size_t)grid * 64); g.dbg = dbg; }
   if (P) KGE_LAUNCH_NAMED(c, "k_fused<P: S=A.Bn^T, loss, GA=V.Bn>", k_fused<F_P>, grid, kThreadsF, smem, mXh, mXl, mYh1, mYl1, mYh2, mYl2, g);
   else KGE_LAUNCH_NAMED(c, "k_fused<N: S^T, G_neg=V^T.A, mean sq>", k_fused<F_N>, grid, kThreadsF, smem, mXh, mXl, mYh1, mYl1, mYh2, mYl2, g);
+  if (timing) {
+    cudaStreamSynchronize(c.stream);
+    unsigned long long* hb = (unsigned long long*)malloc((size_t)grid * 64);
+    cudaMemcpy(hb, dbg, (size_t)grid * 64, cudaMemcpyDeviceToHost);
+    double t[7] = {0, 0, 0, 0, 0, 0, 0};
+    unsigned long long mn = ~0ull, mx = 0;
+    for (int i = 0; i < grid; ++i) {
+      const unsigned long long* r = hb + (size_t)i * 8;
+      for (int k = 1; k < 7; ++k) t[k] += (double)(r[k] - r[0]);
+      if (r[0] < mn) mn = r[0];
+      if (r[6] > mx) mx = r[6];
+    }
+    fprintf(stderr, "[fused timing] mode %c ctas=%d tiles=%d (first tile, us since CTA start) first_stage=%.2f gemm1_done=%.2f softmax_done=%.2f "
+            "gemm2_chunk0=%.2f gemm2_last=%.2f tile_end=%.2f span=%.2f  (nS1=%d nS2=%d Wc=%d N1=%d)\n", P ? 'P' : 'N', grid, p.C * mtiles,
+            t[1] / grid / 1e3, t[2] / grid / 1e3, t[3] / grid / 1e3, t[4] / grid / 1e3, t[5] / grid / 1e3, t[6] / grid / 1e3,
+            (double)(mx - mn) / 1e3, g.nS1, g.nS2, g.Wc, g.N1);
+    free(hb); cudaFree(dbg);
+  }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { snprintf(err, errlen, "k_fused launch: %s", cudaGetErrorString(e)); return KGE_ERR_CUDA; }
   return KGE_OK;

@@ -33,6 +33,12 @@ CASES.append(("TransE_l2_impts", "TransE_l2", dict(adv=True, impts=True)))
 # regularisation off / L2 regulariser
 CASES.append(("DistMult_noreg", "DistMult", dict(adv=False, reg_coef=0.0)))
 CASES.append(("ComplEx_reg2", "ComplEx", dict(adv=True, reg_norm=2, reg_coef=1e-3)))
+# tensor-core shapes (D >= 32, chunk / neg multiples of 8): the tcgen05 kernels are pinned against the reference directly
+CASES.append(("tc_TransE_l2_adv", "TransE_l2", dict(adv=True, hidden=32, batch=16, chunk=8, neg=8, n_ent=60)))
+CASES.append(("tc_TransE_l2_ragged_impts", "TransE_l2", dict(adv=True, hidden=40, batch=32, chunk=16, neg=8, n_ent=60, impts=True)))
+CASES.append(("tc_DistMult_uni", "DistMult", dict(adv=False, hidden=32, batch=16, chunk=8, neg=16, n_ent=60)))
+CASES.append(("tc_ComplEx_adv", "ComplEx", dict(adv=True, hidden=32, batch=16, chunk=8, neg=8, n_ent=60)))
+CASES.append(("tc_RESCAL_adv", "RESCAL", dict(adv=True, hidden=32, batch=16, chunk=8, neg=8, n_ent=60, n_rel=3)))
 
 
 def one_case(name, model, o):
@@ -95,6 +101,9 @@ def one_case(name, model, o):
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    only = sys.argv[1:]                  # optional: generate just the named cases / prefixes
     for name, model, o in CASES:
+        if only and not any(name.startswith(x) for x in only):
+            continue
         meta = one_case(name, model, o)
         print("wrote", name, meta["model"], "B", meta["batch"], "Cs", meta["chunk_size"], "Ns", meta["neg_sample_size"])

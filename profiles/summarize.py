@@ -1,10 +1,18 @@
-"""Turns the ncu artefacts a gpurun call brought back (gpurun_out/) into the tracked summaries under
-profiles/:   python profiles/summarize.py <round tag> <launches.csv> <full.ncu-rep> [workload]
+"""Turns the ncu artefacts a gpurun call brought back (gpurun_out/) into the tracked summaries under profiles/:
+
+    python profiles/summarize.py <tag> <launches.csv> <full.ncu-rep> <traffic key> [launches per step]
+
   <tag>_launches.md   per-kernel launch count / avg device time / share of the step (gpu__time_duration pass)
   <tag>_kernels.md    per-kernel metrics of the --set full capture (DRAM bytes, throughput %, tensor pipe %, ...)
-  <tag>_traffic.json  dram__bytes_read+write summed over the kernels of ONE step (bench.py's roofline.traffic)"""
+  <tag>_traffic.json  {<traffic key>: dram__bytes_read+write of ONE step, <key>_detail: per kernel, <key>_missing: [...]}
+
+bench.py reads <tag>_traffic.json and reports roofline.traffic only for the exact key (workload | batch | schedule) the
+capture was taken on -- null otherwise.  The traffic of a step is the sum over the kernels of the launch list of
+(average bytes per captured launch) x (launches of that kernel per step); a kernel of the launch list without a full
+capture is listed under <key>_missing and makes the total null (a partial sum would under-report)."""
 import csv
 import json
+import re
 import subprocess
 import sys
 
@@ -20,31 +28,46 @@ def launches(path):
             continue
         v = float(r[vi].replace(",", ""))
         v = v / 1e3 if r[ui] == "ns" else (v * 1e3 if r[ui] == "ms" else v)
-        agg.setdefault(r[ki], []).append(v)
+        agg.setdefault(short(r[ki]), []).append(v)
     return agg
 
 
 def short(name):
-    name = name.replace("kge::<unnamed>::", "").replace("kge::", "").replace("void ", "")
-    return name.split("(")[0][:60]
+    """Canonical kernel label: namespaces (kge::, the anonymous namespace in either spelling) and the argument list
+    dropped, template arguments kept (k_fused<0> and k_fused<1> are different kernels)."""
+    name = re.sub(r"\(anonymous namespace\)::|<unnamed>::|kge::|^void ", "", name)
+    depth, out = 0, []
+    for ch in name:                      # cut at the first '(' outside template brackets
+        if ch == "<":
+            depth += 1
+        elif ch == ">":
+            depth -= 1
+        elif ch == "(" and depth == 0:
+            break
+        out.append(ch)
+    return "".join(out).strip()[:80]
 
 
 def main():
-    tag, lcsv, rep = sys.argv[1], sys.argv[2], sys.argv[3]
-    workload = sys.argv[4] if len(sys.argv) > 4 else "fb15k_transe_l2"
+    tag, lcsv, rep, key = sys.argv[1], sys.argv[2], sys.argv[3], sys.argv[4]
     agg = launches(lcsv)
+    steps = int(sys.argv[5]) if len(sys.argv) > 5 else 0
+    if not steps:   # every step runs k_chain (or the RESCAL backward) exactly once
+        steps = max(1, min([len(v) for n, v in agg.items() if n.startswith("k_chain") or n.startswith("k_rescal_bwd")] or [1]))
     tot = sum(sum(v) for v in agg.values())
     with open("profiles/%s_launches.md" % tag, "w") as f:
         f.write("# %s: every launch with its device time (ncu --metrics gpu__time_duration.sum --clock-control none)\n\n" % tag)
-        f.write("Cold-cache, serialised launches: compare SHARES, not absolutes.\n\n| kernel | launches | avg us | share |\n|---|---|---|---|\n")
+        f.write("Cold-cache, serialised launches: compare SHARES, not absolutes.  %d steps in the list.\n\n" % steps)
+        f.write("| kernel | launches | per step | avg us | share |\n|---|---|---|---|---|\n")
         for n, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
-            f.write("| `%s` | %d | %.2f | %.3f |\n" % (short(n), len(v), sum(v) / len(v), sum(v) / tot))
+            f.write("| `%s` | %d | %.2f | %.2f | %.3f |\n" % (n, len(v), len(v) / steps, sum(v) / len(v), sum(v) / tot))
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     h = rows[0]
     want = [("gpu__time_duration.sum", "us"), ("dram__bytes_read.sum", "dram rd"), ("dram__bytes_write.sum", "dram wr"),
             ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram %"),
             ("lts__t_sector_hit_rate.pct", "L2 hit %"),
+            ("lts__t_bytes.sum", "L2 bytes"),
             ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor %"),
             ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "SM %"),
             ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps %"),
@@ -60,30 +83,29 @@ def main():
         for r in rows[2:]:
             f.write("| `%s` | " % short(r[ki]) + " | ".join(r[i] for i, _ in idx) + " |\n")
             try:
-                rd, wr = float(r[h.index("dram__bytes_read.sum")]), float(r[h.index("dram__bytes_write.sum")])
-                u = units[h.index("dram__bytes_read.sum")]
-                mul = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
-                per_kernel.setdefault(short(r[ki]), []).append((rd + wr) * mul)
+                rd, wr = float(r[h.index("dram__bytes_read.sum")].replace(",", "")), float(r[h.index("dram__bytes_write.sum")].replace(",", ""))
+                mul = lambda col: {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(units[h.index(col)], 1)
+                per_kernel.setdefault(short(r[ki]), []).append(rd * mul("dram__bytes_read.sum") + wr * mul("dram__bytes_write.sum"))
             except Exception:
                 pass
-    # traffic of one step = sum over kernels of (avg bytes per launch) x (launches per step in the launch list)
-    steps = max(1, min(len(v) for n, v in agg.items() if "k_chain" in n or "k_rescal_bwd" in n)) if agg else 1
-    per_step = 0.0
-    detail = {}
+    detail, missing = {}, []
     for n, v in agg.items():
-        s = short(n)
-        if s in per_kernel:
-            b = sum(per_kernel[s]) / len(per_kernel[s]) * (len(v) / steps)
-            per_step += b
-            detail[s] = b
+        if n in per_kernel:
+            detail[n] = sum(per_kernel[n]) / len(per_kernel[n]) * (len(v) / steps)
+        else:
+            missing.append(n)
+    total = None if missing else sum(detail.values())
+    assert total is None or abs(total - sum(detail.values())) < 1e-6
     try:
         cur = json.load(open("profiles/%s_traffic.json" % tag))
     except Exception:
         cur = {}
-    cur[workload] = per_step
-    cur[workload + "_detail"] = detail
+    cur[key] = total
+    cur[key + "_detail"] = detail
+    cur[key + "_missing"] = missing
     json.dump(cur, open("profiles/%s_traffic.json" % tag, "w"), indent=1)
-    print("wrote profiles/%s_{launches,kernels}.md, traffic %.1f MB/step" % (tag, per_step / 1e6))
+    print("wrote profiles/%s_{launches,kernels}.md; traffic[%s] = %s MB/step (%d kernels, missing from the full capture: %s)"
+          % (tag, key, "%.1f" % (total / 1e6) if total is not None else "null", len(detail), missing))
 
 
 if __name__ == "__main__":

@@ -21,7 +21,7 @@ SHAPES = [  # (model, hidden, gamma, n_ent, n_rel, B, Cs, Ns, adv)
     ("TransE_l2", 64, 10.0, 977, 13, 256, 64, 64, False),            # one 64-row tile, wide GEMM2 chunk, uniform weights
     ("TransE_l2", 96, 10.0, 977, 13, 320, 160, 72, True),            # ragged: Cs != Ns, two row tiles, D = 3 slab blocks
     ("DistMult", 40, 5.0, 500, 7, 96, 48, 24, True),                 # D not a multiple of 32
-    ("TransE_l2", 400, 19.9, 14951, 1345, 5920, 200, 200, True),     # 60 tiles per pass: several CTAs, TMEM reuse across tiles? (grid 60 < 148)
+    ("TransE_l2", 400, 19.9, 14951, 1345, 6000, 200, 200, True),     # 60 tiles per pass
     ("DistMult", 128, 12.0, 3000, 20, 48000, 240, 240, True),        # 400 tiles > 148 SMs: persistent loop, ring hand-over between tiles
 ]
 
