@@ -60,6 +60,8 @@ struct kge_context {
   float* red_partial = nullptr;      // k_reduce_log partials + ticket + k_update barrier counters (persistent, zero-initialised once)
   float* rel_dense = nullptr;        // [n_rel * Dr | n_rel] per-relation gradient sums of the fused step (zero between steps)
   size_t rel_dense_floats = 0;
+  float* ext_rg = nullptr;           // deferred relation mode: caller-owned dense buffers [n_rel * Dr], [n_rel] that k_chain sums
+  float* ext_rgs = nullptr;          //   the relation gradients into (all-reduced by the caller, kge_set_relation_buffers)
   float* dump_v = nullptr;           // test hook (kge_debug_set_dump): coefficient matrices of the fused kernel
   int fused_mode = -1;               // -1 default (fused kernel whenever the shape allows), 0 off
   size_t stage_bytes = 0;
@@ -150,6 +152,8 @@ int make_params(const kge_step_cfg_t* cfg, long long n_nodes, StepParams* p, boo
   p->Nn = (long long)p->C * p->Ns;
   p->U = n_nodes;
   p->rel_deferred = 0; p->rel_dense = 0; p->use_nc = 1; p->fused = 0;
+  static const int split_trunc = getenv("KGE_B200_SPLIT_TRUNC") ? atoi(getenv("KGE_B200_SPLIT_TRUNC")) : 0;
+  p->split_trunc = split_trunc;
   (void)need_tables;
   return KGE_OK;
 }
@@ -543,13 +547,14 @@ static int forward_backward_impl(kge_handle_t h, const kge_step_cfg_t* cfg, cons
   // fused step on one GPU: nothing can change a table row between its gather and the node update, so the gathered
   // copy NC is skipped; relation gradients are summed per relation (<= 256 MB of sums) instead of stored per edge
   p.use_nc = (fused_step && ve.n_shards == 1) ? 0 : 1;
-  p.rel_dense = (fused_step && !p.rel_deferred && p.model != KGE_RESCAL &&
-                 (size_t)vr.num_rows * (size_t)vr.dim <= ((size_t)64 << 20)) ? 1 : 0;
+  p.rel_dense = (fused_step && p.model != KGE_RESCAL &&
+                 (p.rel_deferred ? (h->ext_rg != nullptr) : ((size_t)vr.num_rows * (size_t)vr.dim <= ((size_t)64 << 20)))) ? 1 : 0;
   StepWs w{};
   CarveOpt opt;
   opt.want_scores = !fused_step;
   if ((rc = carve(h, p, &w, (cudaStream_t)stream, opt))) return rc;
-  if (p.rel_dense && (rc = ensure_rel_dense(h, vr, &w, (cudaStream_t)stream))) return rc;
+  if (p.rel_dense && p.rel_deferred) { w.rg = h->ext_rg; w.rgs = h->ext_rgs; }
+  else if (p.rel_dense && (rc = ensure_rel_dense(h, vr, &w, (cudaStream_t)stream))) return rc;
   LaunchCtx c = lctx(h, stream);
   BatchView b = bview(batch);
   ensure_ng_zero(h, p, w, c, false);
@@ -620,6 +625,19 @@ static int update_impl(kge_handle_t h, const kge_step_cfg_t* cfg, const kge_tabl
 KGE_API int kge_update(kge_handle_t h, const kge_step_cfg_t* cfg, const kge_table_t* ent, const kge_table_t* rel,
                const kge_batch_t* batch, void* stream) {
   return update_impl(h, cfg, ent, rel, batch, nullptr, stream);
+}
+
+// The two halves of kge_step_fused, for callers that put a collective between them (multi-GPU: all-reduce of the
+// relation gradient sums while the entity update runs).
+KGE_API int kge_step_fused_begin(kge_handle_t h, const kge_step_cfg_t* cfg, const kge_table_t* ent, const kge_table_t* rel,
+                         const kge_batch_t* batch, void* stream) {
+  if (!h) return fail(KGE_ERR_INVALID_ARG, "handle is null");
+  return forward_backward_impl(h, cfg, ent, rel, batch, nullptr, stream, true);
+}
+KGE_API int kge_step_fused_end(kge_handle_t h, const kge_step_cfg_t* cfg, const kge_table_t* ent, const kge_table_t* rel,
+                       const kge_batch_t* batch, float* log4, void* stream) {
+  if (!h) return fail(KGE_ERR_INVALID_ARG, "handle is null");
+  return update_impl(h, cfg, ent, rel, batch, log4 ? log4 : h->dev_log4, stream);
 }
 
 // Fused schedule (one GPU, supported shape): k_prep -> k_fused<P> -> k_fused<N> -> k_chain -> k_update = 5 launches.
@@ -747,6 +765,14 @@ KGE_API int kge_debug_read(kge_handle_t h, int which, float* out, int64_t n_floa
 KGE_API int kge_set_relation_mode(kge_handle_t h, int deferred) {
   if (!h) return fail(KGE_ERR_INVALID_ARG, "handle is null");
   h->rel_deferred = deferred ? 1 : 0;
+  return KGE_OK;
+}
+
+KGE_API int kge_set_relation_buffers(kge_handle_t h, float* rg, float* rgs) {
+  if (!h) return fail(KGE_ERR_INVALID_ARG, "handle is null");
+  if ((rg == nullptr) != (rgs == nullptr)) return fail(KGE_ERR_INVALID_ARG, "rg and rgs must both be given or both be null");
+  h->ext_rg = rg;
+  h->ext_rgs = rgs;
   return KGE_OK;
 }
 

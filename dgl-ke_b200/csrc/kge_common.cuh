@@ -52,6 +52,7 @@ struct StepParams {
   int rel_dense;     // 1: k_chain sums relation gradients per relation into ws.rg / ws.rgs (fused single-GPU step)
   int use_nc;        // 1: head/tail rows are read from the gathered copy NC (3-call API, sharded tables); 0: from the table
   int fused;         // 1: contraction by the fused tcgen05 kernel (kge_fused.cu): operands exist only as TF32 hi/lo slabs
+  int split_trunc;   // experiment: operands' hi part is the raw fp32 value (see RowOut::trunc)
 };
 
 // Device workspace of one step (all pointers into the handle's arena).
@@ -193,11 +194,29 @@ struct RowOut {
   float* lo;
   long long chunk;
   int nblk, R, row;
+  int trunc;         // experiment (KGE_B200_SPLIT_TRUNC): hi = the raw fp32 value (the tensor core drops the low 13
+                     // mantissa bits itself), lo = rna_tf32(x - trunc_tf32(x))
 };
+// experiment: which rounding does the tensor core apply to a raw fp32 operand of kind::tf32?
+//   mode 1: truncation, 2: round to nearest, ties away (cvt.rna), 3: round to nearest even (cvt.rn)
+__device__ __forceinline__ void split_tf32_trunc(float x, float& hi, float& lo, int mode) {
+  float ht;
+  if (mode == 1) ht = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+  else if (mode == 2) { uint32_t b; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(b) : "f"(x)); ht = __uint_as_float(b); }
+  else { uint32_t b; asm("cvt.rn.tf32.f32 %0, %1;" : "=r"(b) : "f"(x)); ht = __uint_as_float(b); }
+  uint32_t lb;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(x - ht));
+  hi = x;
+  lo = __uint_as_float(lb);
+}
 __device__ __forceinline__ void row_store4(const RowOut& o, int col, float4 v) {
   if (o.f32) *reinterpret_cast<float4*>(o.f32 + col) = v;
   if (o.hi) {
     float4 h, l;
+    if (o.trunc) {
+      split_tf32_trunc(v.x, h.x, l.x, o.trunc); split_tf32_trunc(v.y, h.y, l.y, o.trunc);
+      split_tf32_trunc(v.z, h.z, l.z, o.trunc); split_tf32_trunc(v.w, h.w, l.w, o.trunc);
+    } else
     split_tf32_4(v, h, l);
     const long long off = slab_off(o.chunk, o.nblk, o.R, o.row, col);
     *reinterpret_cast<float4*>(o.hi + off) = h;

@@ -37,7 +37,9 @@ namespace {
 constexpr int kTileM = 128;
 constexpr int kThreadsF = 320;
 constexpr int kMaxS1 = 4, kMaxS2 = 8;
-constexpr uint32_t kRingBytes = 216 * 1024;
+constexpr uint32_t kRingBytes = 192 * 1024;
+constexpr int kStagePitch = 20;                      // floats per row of an epilogue staging tile (16 + 4 pad, 16-byte aligned rows)
+constexpr uint32_t kEpiStageBytes = 8 * 32 * kStagePitch * 4;   // one 32 x 16 tile per epilogue warp
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
@@ -85,9 +87,11 @@ k_fused(const __grid_constant__ CUtensorMap mXh, const __grid_constant__ CUtenso
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(16) float colA[256], colB[256], colC[256];
   __shared__ float xch[4][2][kTileM];
+  __shared__ float rowscal[kTileM];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* ring = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  float* epi_stage = reinterpret_cast<float*>(ring + kRingBytes);
 
   const int mtiles = (g.Rx + kTileM - 1) / kTileM;
   const int ntiles = g.C * mtiles;
@@ -117,112 +121,124 @@ k_fused(const __grid_constant__ CUtensorMap mXh, const __grid_constant__ CUtenso
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
-  if (g.dbg && threadIdx.x == 0) g.dbg[blockIdx.x * 8 + 0] = gtime();
+  if (g.dbg && threadIdx.x == 0) g.dbg[blockIdx.x * 16 + 0] = gtime();
 
+  // Roles.  The producer and MMA warps run their loops with all 32 lanes (warp-uniform control flow and operands, so the
+  // address / descriptor arithmetic stays on the uniform datapath) and one elected lane issues the TMA / tcgen05 ops.
   if (warp == 0) {
     // ================================ TMA producer ================================
-    if (lane == 0) {
-      uint32_t n1 = 0, n2 = 0;      // stage fills issued so far (GEMM1 / GEMM2)
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int c = tile / mtiles, m0 = (tile % mtiles) * kTileM;
-        // the ring is about to be re-used with the GEMM1 layout: every GEMM2 stage of the previous tile must be consumed
-        for (uint32_t k = (n2 > (uint32_t)g.nS2 ? n2 - g.nS2 : 0); k < n2; ++k) mbar_wait(&empty2[k % g.nS2], (k / g.nS2) & 1);
-        for (int kb = 0; kb < nkb1; ++kb, ++n1) {
-          const uint32_t s = n1 % g.nS1;
-          mbar_wait(&empty1[s], ((n1 / g.nS1) & 1) ^ 1);
-          uint8_t* st = ring + (size_t)s * g.stage1Bytes;
+    uint32_t n1 = 0, n2 = 0;      // stage fills issued so far (GEMM1 / GEMM2)
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int c = tile / mtiles, m0 = (tile % mtiles) * kTileM;
+      // the ring is about to be re-used with the GEMM1 layout: every GEMM2 stage of the previous tile must be consumed
+      for (uint32_t k = (n2 > (uint32_t)g.nS2 ? n2 - g.nS2 : 0); k < n2; ++k) mbar_wait(&empty2[k % g.nS2], (k / g.nS2) & 1);
+      for (int kb = 0; kb < nkb1; ++kb, ++n1) {
+        const uint32_t s = n1 % g.nS1;
+        mbar_wait(&empty1[s], ((n1 / g.nS1) & 1) ^ 1);
+        uint8_t* st = ring + (size_t)s * g.stage1Bytes;
+        // slab layout: TMA row of (chunk c, 32-column block kb, row r) = (c * nblkD + kb) * R + r
+        const int yx = (c * g.nblkD + kb) * g.Rx + m0;
+        const int yy = (c * g.nblkD + kb) * g.Ry;
+        if (elect_one()) {
           mbar_expect_tx(&full1[s], 2u * 16384u + 2u * yBytes1);
-          // slab layout: TMA row of (chunk c, 32-column block kb, row r) = (c * nblkD + kb) * R + r
-          const int yx = (c * g.nblkD + kb) * g.Rx + m0;
-          const int yy = (c * g.nblkD + kb) * g.Ry;
           tma_load_2d(st, &mXh, &full1[s], 0, yx);
           tma_load_2d(st + 16384, &mXl, &full1[s], 0, yx);
           tma_load_2d(st + 32768, &mYh1, &full1[s], 0, yy);
           tma_load_2d(st + 32768 + yBytes1, &mYl1, &full1[s], 0, yy);
         }
-        // GEMM2 stages overlay the GEMM1 stages: wait until the tensor core has consumed all of them
-        for (uint32_t k = (n1 > (uint32_t)g.nS1 ? n1 - g.nS1 : 0); k < n1; ++k) mbar_wait(&empty1[k % g.nS1], (k / g.nS1) & 1);
-        for (int ch = 0; ch < nchunks; ++ch) {
-          const int d0 = ch * g.Wc;
-          int nb = (g.D - d0 + 31) >> 5;
-          if (nb > (g.Wc >> 5)) nb = g.Wc >> 5;
-          for (int kb = 0; kb < nkb2; ++kb, ++n2) {
-            const uint32_t s = n2 % g.nS2;
-            mbar_wait(&empty2[s], ((n2 / g.nS2) & 1) ^ 1);
-            uint8_t* st = ring + (size_t)s * g.stage2Bytes;
+        __syncwarp();
+      }
+      // GEMM2 stages overlay the GEMM1 stages: wait until the tensor core has consumed all of them
+      for (uint32_t k = (n1 > (uint32_t)g.nS1 ? n1 - g.nS1 : 0); k < n1; ++k) mbar_wait(&empty1[k % g.nS1], (k / g.nS1) & 1);
+      for (int ch = 0; ch < nchunks; ++ch) {
+        const int d0 = ch * g.Wc;
+        int nb = (g.D - d0 + 31) >> 5;
+        if (nb > (g.Wc >> 5)) nb = g.Wc >> 5;
+        for (int kb = 0; kb < nkb2; ++kb, ++n2) {
+          const uint32_t s = n2 % g.nS2;
+          mbar_wait(&empty2[s], ((n2 / g.nS2) & 1) ^ 1);
+          uint8_t* st = ring + (size_t)s * g.stage2Bytes;
+          const int yy0 = (c * g.nblkD + (d0 >> 5)) * g.Ry + kb * 32;
+          if (elect_one()) {
             mbar_expect_tx(&full2[s], 2u * (uint32_t)nb * 4096u);
             for (int b = 0; b < nb; ++b) {
-              const int yy = (c * g.nblkD + (d0 >> 5) + b) * g.Ry + kb * 32;
-              tma_load_2d(st + b * 4096, &mYh2, &full2[s], 0, yy);
-              tma_load_2d(st + yBytes2 + b * 4096, &mYl2, &full2[s], 0, yy);
+              tma_load_2d(st + b * 4096, &mYh2, &full2[s], 0, yy0 + b * g.Ry);
+              tma_load_2d(st + yBytes2 + b * 4096, &mYl2, &full2[s], 0, yy0 + b * g.Ry);
             }
           }
+          __syncwarp();
         }
       }
     }
   } else if (warp == 1) {
-    // ================================ MMA issuer (one thread) ================================
-    if (lane == 0) {
-      uint32_t n1 = 0, n2 = 0, nacc = 0, it = 0;
-      const uint32_t idesc1 = make_idesc(kTileM, g.N1, false, false);
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-        // ---- GEMM1: S = X . Y^T, K = D ----
-        uint32_t accumulate = 0;
-        for (int kb = 0; kb < nkb1; ++kb, ++n1) {
-          const uint32_t s = n1 % g.nS1;
-          mbar_wait(&full1[s], (n1 / g.nS1) & 1);
-          if (g.dbg && n1 == 0) g.dbg[blockIdx.x * 8 + 1] = gtime();
-          tc_fence_after();
-          const uint32_t st = smem_u32(ring + (size_t)s * g.stage1Bytes);
-          const uint32_t sXh = st, sXl = st + 16384, sYh = st + 32768, sYl = st + 32768 + yBytes1;
-          const int kleft = g.D - kb * 32;
-          const int ksteps = kleft >= 32 ? 4 : (kleft >> 3);
-          for (int ks = 0; ks < ksteps; ++ks) {
-            const uint32_t off = ks * 32u;     // K-major: +32 bytes per k-step inside the 128-byte swizzle span
-            const uint64_t dXh = make_desc(sXh + off, 16, 1024), dXl = make_desc(sXl + off, 16, 1024);
-            const uint64_t dYh = make_desc(sYh + off, 16, 1024), dYl = make_desc(sYl + off, 16, 1024);
-            umma_tf32(tmem_base, dXh, dYh, idesc1, accumulate);
-            umma_tf32(tmem_base, dXh, dYl, idesc1, 1u);
-            umma_tf32(tmem_base, dXl, dYh, idesc1, 1u);
-            accumulate = 1u;
+    // ================================ MMA issuer ================================
+    uint32_t n1 = 0, n2 = 0, nacc = 0, it = 0;
+    const uint32_t idesc1 = make_idesc(kTileM, g.N1, false, false);
+    // descriptor = constant fields | (shared address >> 4): a k-step advances the address field only
+    const uint64_t descK = make_desc(0, 16, 1024), descMN = make_desc(0, 4096, 512, 1);
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      // ---- GEMM1: S = X . Y^T, K = D ----
+      for (int kb = 0; kb < nkb1; ++kb, ++n1) {
+        const uint32_t s = n1 % g.nS1;
+        mbar_wait(&full1[s], (n1 / g.nS1) & 1);
+        if (g.dbg && n1 == 0 && lane == 0) g.dbg[blockIdx.x * 16 + 1] = gtime();
+        tc_fence_after();
+        const uint32_t st = smem_u32(ring + (size_t)s * g.stage1Bytes);
+        const uint64_t dXh = descK | (uint64_t)(st >> 4), dXl = descK | (uint64_t)((st + 16384u) >> 4);
+        const uint64_t dYh = descK | (uint64_t)((st + 32768u) >> 4), dYl = descK | (uint64_t)((st + 32768u + yBytes1) >> 4);
+        const int kleft = g.D - kb * 32;
+        const int ksteps = kleft >= 32 ? 4 : (kleft >> 3);
+        if (elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            if (ks < ksteps) {
+              const uint64_t o = (uint64_t)(ks * 2);     // K-major: +32 bytes per k-step inside the 128-byte swizzle span
+              umma_tf32(tmem_base, dXh + o, dYh + o, idesc1, (kb | ks) ? 1u : 0u);
+              umma_tf32(tmem_base, dXh + o, dYl + o, idesc1, 1u);
+              umma_tf32(tmem_base, dXl + o, dYh + o, idesc1, 1u);
+            }
           }
           umma_commit(&empty1[s]);
+          if (kb == nkb1 - 1) umma_commit(&s_full);
         }
-        umma_commit(&s_full);
-        // ---- the epilogue warps turn S into V (hi | lo) in TMEM ----
-        mbar_wait(&v_ready, it & 1);
+        __syncwarp();
+      }
+      // ---- the epilogue warps turn S into V (hi | lo) in TMEM ----
+      mbar_wait(&v_ready, it & 1);
+      tc_fence_after();
+      // ---- GEMM2: G[:, chunk] = V . Y[:, chunk], K = Ry, A operand from TMEM ----
+      for (int ch = 0; ch < nchunks; ++ch, ++nacc) {
+        const int d0 = ch * g.Wc;
+        int nb = (g.D - d0 + 31) >> 5;
+        if (nb > (g.Wc >> 5)) nb = g.Wc >> 5;
+        const uint32_t idesc2 = make_idesc(kTileM, nb * 32, false, true);
+        mbar_wait(&acc_empty, (nacc & 1) ^ 1);
         tc_fence_after();
-        // ---- GEMM2: G[:, chunk] = V . Y[:, chunk], K = Ry, A operand from TMEM ----
-        for (int ch = 0; ch < nchunks; ++ch, ++nacc) {
-          const int d0 = ch * g.Wc;
-          int nb = (g.D - d0 + 31) >> 5;
-          if (nb > (g.Wc >> 5)) nb = g.Wc >> 5;
-          const uint32_t idesc2 = make_idesc(kTileM, nb * 32, false, true);
-          mbar_wait(&acc_empty, (nacc & 1) ^ 1);
+        for (int kb = 0; kb < nkb2; ++kb, ++n2) {
+          const uint32_t s = n2 % g.nS2;
+          mbar_wait(&full2[s], (n2 / g.nS2) & 1);
           tc_fence_after();
-          uint32_t acc2 = 0;
-          for (int kb = 0; kb < nkb2; ++kb, ++n2) {
-            const uint32_t s = n2 % g.nS2;
-            mbar_wait(&full2[s], (n2 / g.nS2) & 1);
-            tc_fence_after();
-            const uint32_t st = smem_u32(ring + (size_t)s * g.stage2Bytes);
-            const int kleft = g.Ry - kb * 32;
-            const int ksteps = kleft >= 32 ? 4 : (kleft >> 3);
-            for (int ks = 0; ks < ksteps; ++ks) {
-              // MN-major B (128B swizzle, 32B atoms): k-atoms of 4 rows (512 B, SBO), one k-step = 2 atoms = 1024 B,
-              // LBO = 4096 between the 32-wide column blocks
-              const uint64_t dYh = make_desc(st + ks * 1024u, 4096, 512, 1);
-              const uint64_t dYl = make_desc(st + yBytes2 + ks * 1024u, 4096, 512, 1);
-              const uint32_t aHi = tmem_base + (uint32_t)(kb * 32 + ks * 8);
-              const uint32_t aLo = aHi + colR2;
-              umma_tf32_ts(tmem_base + colAcc, aHi, dYh, idesc2, acc2);
-              umma_tf32_ts(tmem_base + colAcc, aHi, dYl, idesc2, 1u);
-              umma_tf32_ts(tmem_base + colAcc, aLo, dYh, idesc2, 1u);
-              acc2 = 1u;
+          const uint32_t st = smem_u32(ring + (size_t)s * g.stage2Bytes);
+          const uint64_t dYh = descMN | (uint64_t)(st >> 4), dYl = descMN | (uint64_t)((st + yBytes2) >> 4);
+          const uint32_t aHi = tmem_base + (uint32_t)(kb * 32), aLo = aHi + colR2;
+          const int kleft = g.Ry - kb * 32;
+          const int ksteps = kleft >= 32 ? 4 : (kleft >> 3);
+          if (elect_one()) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              if (ks < ksteps) {
+                // MN-major B (128B swizzle, 32B atoms): k-atoms of 4 rows (512 B, SBO), one k-step = 2 atoms = 1024 B,
+                // LBO = 4096 between the 32-wide column blocks
+                const uint64_t o = (uint64_t)(ks * 64);
+                umma_tf32_ts(tmem_base + colAcc, aHi + ks * 8, dYh + o, idesc2, (kb | ks) ? 1u : 0u);
+                umma_tf32_ts(tmem_base + colAcc, aHi + ks * 8, dYl + o, idesc2, 1u);
+                umma_tf32_ts(tmem_base + colAcc, aLo + ks * 8, dYh + o, idesc2, 1u);
+              }
             }
             umma_commit(&empty2[s]);
+            if (kb == nkb2 - 1) umma_commit(&acc_full);
           }
-          umma_commit(&acc_full);
+          __syncwarp();
         }
       }
     }
@@ -254,78 +270,73 @@ k_fused(const __grid_constant__ CUtensorMap mXh, const __grid_constant__ CUtenso
       mbar_wait(&s_full, it & 1);
       tc_fence_after();
       const bool probe = g.dbg && it == 0 && threadIdx.x == 64;
-      if (probe) g.dbg[blockIdx.x * 8 + 2] = gtime();
+      if (probe) g.dbg[blockIdx.x * 16 + 2] = gtime();
 
+      float rscale = 1.f;          // mode P: 1 / softmax denominator, applied to the rows of GA in the GEMM2 epilogue
       if (MODE == F_P) {
         const float w_i = (g.wt && row_ok) ? g.wt[gx] : 1.f;
         const float kw = w_i * g.inv2B;
-        // ---- pass A: scores (distance epilogue for TransE_l2), running max ----
+        // ---- pass A: scores (distance epilogue for TransE_l2), running max; 1/dist parked in TMEM region 2 ----
         float mxl = -INFINITY;
-        for (int col = cb; col < ce; col += 16) {
-          float v[16], dd[16];
-          tmem_ld16(trow + col, v);
+        if (l2 || g.adversarial || g.dumpS) {
+          for (int col = cb; col < ce; col += 16) {
+            float v[16], rr[16];
+            tmem_ld16(trow + col, v);
 #pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            float s = v[e];
-            if (l2) {
-              // batched_l2_dist (score_fun.py:26-34): (|b|^2 - 2 a.b) + |a|^2, clamp 1e-30, sqrt
-              const float sq = fmaf(-2.f, v[e], colA[col + e]) + x2v;
-              dd[e] = sqrta(fmaxf(sq, 1e-30f));
-              s = g.gamma - dd[e];
-              v[e] = s;
+            for (int e = 0; e < 16; ++e) {
+              float s = v[e];
+              if (l2) {
+                // batched_l2_dist (score_fun.py:26-34): (|b|^2 - 2 a.b) + |a|^2, clamp 1e-30, sqrt
+                const float sq = fmaf(-2.f, v[e], colA[col + e]) + x2v;
+                const float sqc = fmaxf(sq, 1e-30f);
+                const float r = rsqrta(sqc);
+                s = g.gamma - sqc * r;
+                rr[e] = (sq > 1e-30f) ? r : 0.f;        // clamped distance: zero gradient (clamp_min_), dist ~ 0
+                v[e] = s;
+              }
+              if (col + e < g.Ry) mxl = fmaxf(mxl, s * g.Tl2e);
             }
-            if (col + e < g.Ry) mxl = fmaxf(mxl, s * g.Tl2e);
-          }
-          if (g.dumpS && row_ok) {
+            if (g.dumpS && row_ok) {
 #pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4)
-              if (col + q4 * 4 < g.Ry) st4(g.dumpS + gx * g.Ry + col + q4 * 4, make_float4(v[q4 * 4], v[q4 * 4 + 1], v[q4 * 4 + 2], v[q4 * 4 + 3]));
+              for (int q4 = 0; q4 < 4; ++q4)
+                if (col + q4 * 4 < g.Ry) st4(g.dumpS + gx * g.Ry + col + q4 * 4, make_float4(v[q4 * 4], v[q4 * 4 + 1], v[q4 * 4 + 2], v[q4 * 4 + 3]));
+            }
+            if (l2) tmem_st16(trow + colR2 + col, rr);
           }
-          if (l2) tmem_st16(trow + colR2 + col, dd);
+          if (l2) tmem_wait_st();
         }
-        if (l2) tmem_wait_st();
-        float rden = g.uni;
         if (g.adversarial) {
           xch[0][ehalf][row] = mxl;
           epi_bar();
           mxl = fmaxf(mxl, xch[0][ehalf ^ 1][row]);
-          // ---- pass B: softmax denominator ----
-          float den = 0.f;
-          for (int col = cb; col < ce; col += 16) {
-            float v[16];
-            tmem_ld16(trow + (l2 ? colR2 : 0u) + col, v);
-#pragma unroll
-            for (int e = 0; e < 16; ++e) {
-              const float s = l2 ? g.gamma - v[e] : v[e];
-              if (col + e < g.Ry) den += ex2a(fmaf(s, g.Tl2e, -mxl));
-            }
-          }
-          xch[1][ehalf][row] = den;
-          epi_bar();
-          den += xch[1][ehalf ^ 1][row];
-          rden = 1.f / den;
         } else {
           mxl = 0.f;
         }
-        // ---- pass C: loss terms + backward coefficients, written back to TMEM as TF32 hi | lo ----
-        float nls = 0.f, rs = 0.f;
+        // ---- pass C: softmax numerators, loss terms and (unnormalised) backward coefficients -> TMEM as TF32 hi | lo.
+        //      The 1/denominator of the row is a per-row scalar: it is applied to the loss sums here and to the row of
+        //      GA in the GEMM2 epilogue, so no separate denominator pass over TMEM is needed.
+        float nls = 0.f, rs = 0.f, den = 0.f;
         for (int col = cb; col < ce; col += 16) {
-          float v[16], hi[16], lo[16];
-          tmem_ld16(trow + (l2 ? colR2 : 0u) + col, v);
+          float v[16], rr[16], hi[16], lo[16];
+          tmem_ld16(trow + col, v);
+          if (l2) tmem_ld16(trow + colR2 + col, rr);
 #pragma unroll
           for (int e = 0; e < 16; ++e) {
-            const float d = v[e];
-            const float s = l2 ? g.gamma - d : d;
-            const float p = g.adversarial ? ex2a(fmaf(s, g.Tl2e, -mxl)) * rden : g.uni;
+            float s = v[e], rinv = 1.f;
+            if (l2) {
+              const float sqc = fmaxf(fmaf(-2.f, v[e], colA[col + e]) + x2v, 1e-30f);
+              rinv = rr[e];
+              s = g.gamma - sqc * rinv;
+            }
+            const float pe = g.adversarial ? ex2a(fmaf(s, g.Tl2e, -mxl)) : 1.f;
             const float t = ex2a(-fabsf(s) * kLog2e);
-            const float r1 = rcpa(1.f + t);
-            const float sig = (s >= 0.f) ? r1 : t * r1;                       // sigmoid(s)
-            const float sp = fmaxf(s, 0.f) + kLn2 * lg2a(1.f + t);           // -logsigmoid(-s)
-            float coef = p * sig * kw;                                        // dL/dneg_ij
-            if (l2) coef = (d > 1.5e-15f) ? coef * rcpa(d) : 0.f;             // clamped distance: zero gradient (clamp_min_)
+            const float u = 1.f + t;
+            const float r1 = rcpa(u);
+            const float sig = (s >= 0.f) ? r1 : t * r1;                     // sigmoid(s)
+            const float sp = fmaf(kLn2, lg2a(u), fmaxf(s, 0.f));            // -logsigmoid(-s)
             const bool ok = row_ok && (col + e < g.Ry);
-            if (!ok) coef = 0.f;
-            if (ok) nls += p * sp;
+            float coef = ok ? pe * sig * kw * rinv : 0.f;                    // dL/dneg_ij (/ dist) * denominator
+            if (ok) { nls = fmaf(pe, sp, nls); den += pe; }
             rs += coef;
             split_tf32(coef, hi[e], lo[e]);
             v[e] = coef;
@@ -338,20 +349,29 @@ k_fused(const __grid_constant__ CUtensorMap mXh, const __grid_constant__ CUtenso
           tmem_st16(trow + col, hi);
           tmem_st16(trow + colR2 + col, lo);
         }
+        xch[1][ehalf][row] = den;
         xch[2][ehalf][row] = nls;
         xch[3][ehalf][row] = rs;
         epi_bar();
+        den += xch[1][ehalf ^ 1][row];
+        rscale = g.adversarial ? (row_ok ? 1.f / den : 0.f) : g.uni;
+        if (g.dumpV && row_ok) {        // test hook: the dump shows the normalised coefficients
+          for (int col = cb; col < ce && col < g.Ry; col += 4) {
+            float4 x = ld4(g.dumpV + gx * g.Ry + col);
+            st4(g.dumpV + gx * g.Ry + col, f4_scale(x, rscale));
+          }
+        }
         if (ehalf == 0 && row_ok) {
           nls += xch[2][1][row];
           rs += xch[3][1][row];
           const float ps = g.pos[gx];
           const float wb = g.wt ? *g.wbar : 1.f;        // loss.py:75,82: [B] * [B,1] -> mean(pl) * mean(w)
           g.pl[gx] = softplusf(-ps);
-          g.nl[gx] = nls * w_i;
+          g.nl[gx] = nls * rscale * w_i;
           g.gpos[gx] = -sigmoidf(-ps) * wb * g.inv2B;
-          if (l2) g.rowsum[gx] = rs;
+          if (l2) g.rowsum[gx] = rs * rscale;
           g.stat_m[gx] = mxl;
-          g.stat_k[gx] = kw * rden;
+          g.stat_k[gx] = kw * rscale;
         }
       } else {
         // ---- mode N: one pass, the softmax statistics of every column (positive) come from mode P ----
@@ -361,18 +381,19 @@ k_fused(const __grid_constant__ CUtensorMap mXh, const __grid_constant__ CUtenso
           tmem_ld16(trow + col, v);
 #pragma unroll
           for (int e = 0; e < 16; ++e) {
-            float s = v[e], d = 1.f;
+            float s = v[e], rinv = 1.f;
             if (l2) {
               const float sq = fmaf(-2.f, v[e], x2v) + colA[col + e];
-              d = sqrta(fmaxf(sq, 1e-30f));
-              s = g.gamma - d;
+              const float sqc = fmaxf(sq, 1e-30f);
+              const float r = rsqrta(sqc);
+              s = g.gamma - sqc * r;
+              rinv = (sq > 1e-30f) ? r : 0.f;
             }
             const float pe = g.adversarial ? ex2a(fmaf(s, g.Tl2e, -colB[col + e])) : 1.f;
             const float t = ex2a(-fabsf(s) * kLog2e);
             const float r1 = rcpa(1.f + t);
             const float sig = (s >= 0.f) ? r1 : t * r1;
-            float coef = pe * colC[col + e] * sig;
-            if (l2) coef = (d > 1.5e-15f) ? coef * rcpa(d) : 0.f;
+            float coef = pe * colC[col + e] * sig * rinv;
             if (!(row_ok && (col + e < g.Ry))) coef = 0.f;
             cs += coef;
             split_tf32(coef, hi[e], lo[e]);
@@ -395,11 +416,23 @@ k_fused(const __grid_constant__ CUtensorMap mXh, const __grid_constant__ CUtenso
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&v_ready);
-      if (probe) g.dbg[blockIdx.x * 8 + 3] = gtime();
+      if (probe) g.dbg[blockIdx.x * 16 + 3] = gtime();
 
       // ---- GEMM2 epilogue, one output-column chunk at a time ----
-      float gsq = 0.f;
-      float* orow = g.out + gx * (long long)g.D;
+      // TMEM hands every thread one accumulator ROW; writing rows from 32 lanes touches 32 cache lines per
+      // instruction (L1 is a few KB next to the 200+ KB of shared memory, so nothing merges).  Each warp therefore
+      // transposes its 32 x 16 pieces through a private shared-memory tile: afterwards a lane owns 4 consecutive
+      // columns of 4 rows (lane / 4 + 8 * it) and a warp instruction covers 8 rows x 64 contiguous bytes.
+      float* stile = epi_stage + (warp - 2) * (32 * kStagePitch);
+      const int tr = lane >> 2, tc4 = (lane & 3) * 4;                 // transposed mapping: rows tr + 8*it, columns tc4..tc4+3
+      const int mrow0 = m0 + q * 32;                                  // first lane-side row of this warp
+      // per-row scalars of this tile in the transposed mapping
+      if (ehalf == 0) rowscal[row] = (MODE == F_P) ? rscale : colsum;
+      epi_bar();
+      float rsc[4];
+#pragma unroll
+      for (int it = 0; it < 4; ++it) rsc[it] = rowscal[q * 32 + tr + 8 * it];
+      float gsq[4] = {0.f, 0.f, 0.f, 0.f};
       for (int ch = 0; ch < nchunks; ++ch, ++nacc) {
         const int d0 = ch * g.Wc;
         int nb = (g.D - d0 + 31) >> 5;
@@ -408,31 +441,57 @@ k_fused(const __grid_constant__ CUtensorMap mXh, const __grid_constant__ CUtenso
         const int hc = ((Nc >> 1) + 15) & ~15;
         const int cb2 = ehalf ? hc : 0, ce2 = ehalf ? Nc : hc;
         const int npieces = (ce2 - cb2 + 15) >> 4;
+        // mode N: the rows' own values b (for -colsum*b and the regulariser) do not depend on the accumulator:
+        // issue their loads before waiting for the tensor core, so that they overlap this chunk's MMAs
+        float4 bq[12];
+        if (MODE == F_N && npieces <= 3) {
+#pragma unroll
+          for (int i = 0; i < 12; ++i) {
+            const int pc = i >> 2, it = i & 3;
+            const int k = d0 + cb2 + pc * 16 + tc4, mr = mrow0 + tr + 8 * it;
+            if (pc < npieces && k < g.D && mr < g.Rx) {
+              const long long so = slab_off(c, g.nblkD, g.Rx, mr, k);
+              bq[i] = f4_add(ld4(g.Xhi + so), ld4(g.Xlo + so));
+            } else {
+              bq[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+        }
+        if (probe && ch == 1) g.dbg[blockIdx.x * 16 + 8] = gtime();          // b loads issued (and summed)
         mbar_wait(&acc_full, nacc & 1);
         tc_fence_after();
-        if (probe && ch == 0) g.dbg[blockIdx.x * 8 + 4] = gtime();
-        if (probe && ch == nchunks - 1) g.dbg[blockIdx.x * 8 + 5] = gtime();
+        if (probe && ch == 1) g.dbg[blockIdx.x * 16 + 9] = gtime();          // accumulator of chunk 1 ready
+        if (probe && ch == 0) g.dbg[blockIdx.x * 16 + 4] = gtime();
+        if (probe && ch == nchunks - 1) g.dbg[blockIdx.x * 16 + 5] = gtime();
         auto release = [&]() {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty);
         };
-        auto process = [&](const uint32_t* r, int col) {
-          if (!row_ok) return;
+        // one 32-row x 16-column piece: registers (row per lane) -> tile -> (4 columns of 4 rows per lane) -> global
+        auto process = [&](const uint32_t* r, int col, const float4* bpre) {
+          __syncwarp();                                              // the previous piece has been read out of the tile
 #pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
-            const int k = d0 + col + q4 * 4;
-            if (k >= g.D) continue;
-            float4 o = make_float4(__uint_as_float(r[q4 * 4]), __uint_as_float(r[q4 * 4 + 1]),
-                                   __uint_as_float(r[q4 * 4 + 2]), __uint_as_float(r[q4 * 4 + 3]));
+          for (int q4 = 0; q4 < 4; ++q4)
+            *reinterpret_cast<float4*>(stile + lane * kStagePitch + q4 * 4) =
+                make_float4(__uint_as_float(r[q4 * 4]), __uint_as_float(r[q4 * 4 + 1]), __uint_as_float(r[q4 * 4 + 2]), __uint_as_float(r[q4 * 4 + 3]));
+          __syncwarp();
+          const int k = d0 + col + tc4;
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int mr = mrow0 + tr + 8 * it;
+            if (k >= g.D || mr >= g.Rx) continue;
+            float4 o = *reinterpret_cast<const float4*>(stile + (tr + 8 * it) * kStagePitch + tc4);
+            if (MODE == F_P) o = f4_scale(o, rsc[it]);            // 1 / softmax denominator of the row
             if (MODE == F_N) {
-              const long long so = slab_off(c, g.nblkD, g.Rx, m, k);
-              const float4 b = f4_add(ld4(g.Xhi + so), ld4(g.Xlo + so));
-              if (l2) o = f4_fma(b, -colsum, o);                 // sum_i V_ij a_i - (sum_i V_ij) b_j
+              float4 b;
+              if (bpre) b = bpre[it];
+              else { const long long so = slab_off(c, g.nblkD, g.Rx, mr, k); b = f4_add(ld4(g.Xhi + so), ld4(g.Xlo + so)); }
+              if (l2) o = f4_fma(b, -rsc[it], o);                   // sum_i V_ij a_i - (sum_i V_ij) b_j
               o = f4_add(o, reg_grad4(b, g.reg_norm, g.reg_coef));
-              gsq += f4_dot(o, o);
+              gsq[it] += f4_dot(o, o);
             }
-            st4(orow + k, o);
+            st4(g.out + ((long long)c * g.Rx + mr) * (long long)g.D + k, o);
           }
         };
         if (npieces <= 3) {
@@ -443,26 +502,35 @@ k_fused(const __grid_constant__ CUtensorMap mXh, const __grid_constant__ CUtenso
             if (pc < npieces) tmem_ld16_nowait(trow + colAcc + cb2 + pc * 16, r + pc * 16);
           tmem_wait_ld();
           release();
+          if (probe && ch == 1) g.dbg[blockIdx.x * 16 + 10] = gtime();       // TMEM read, accumulator released
 #pragma unroll
           for (int pc = 0; pc < 3; ++pc)
-            if (pc < npieces) process(r + pc * 16, cb2 + pc * 16);
+            if (pc < npieces) process(r + pc * 16, cb2 + pc * 16, bq + pc * 4);
+          if (probe && ch == 1) g.dbg[blockIdx.x * 16 + 11] = gtime();       // chunk 1 stored
+          if (probe && ch == 0) g.dbg[blockIdx.x * 16 + 7] = gtime();        // chunk 0 stored
         } else {
           for (int pc = 0; pc < npieces; ++pc) {
             uint32_t r[16];
             tmem_ld16_nowait(trow + colAcc + cb2 + pc * 16, r);
             tmem_wait_ld();
             if (pc == npieces - 1) release();
-            process(r, cb2 + pc * 16);
+            process(r, cb2 + pc * 16, nullptr);
           }
           if (npieces == 0) release();
         }
       }
-      if (probe) g.dbg[blockIdx.x * 8 + 6] = gtime();
+      if (probe) g.dbg[blockIdx.x * 16 + 6] = gtime();
       if (MODE == F_N) {
-        epi_bar();                       // xch[2] (colsum exchange) has been read by everybody
-        xch[3][ehalf][row] = gsq;
+        // mean(G_neg^2) per row: the 4 lanes that share a row, then the two warps that share the quarter
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          float v = gsq[it];
+          v += __shfl_xor_sync(0xffffffffu, v, 1);
+          v += __shfl_xor_sync(0xffffffffu, v, 2);
+          if ((lane & 3) == 0) xch[3][ehalf][q * 32 + tr + 8 * it] = v;
+        }
         epi_bar();
-        if (ehalf == 0 && row_ok) g.gsn[gx] = (gsq + xch[3][1][row]) / (float)g.D;
+        if (ehalf == 0 && row_ok) g.gsn[gx] = (xch[3][0][row] + xch[3][1][row]) / (float)g.D;
       }
     }
     tc_fence_before();
@@ -523,7 +591,7 @@ int fused_launch(const LaunchCtx& c, const StepParams& p, const StepWs& w, int m
       !tc_make_map(&mYh1, Yh, rowsY, 32, g.N1, err, errlen) || !tc_make_map(&mYl1, Yl, rowsY, 32, g.N1, err, errlen) ||
       !tc_make_map(&mYh2, Yh, rowsY, 32, 32, err, errlen, true) || !tc_make_map(&mYl2, Yl, rowsY, 32, 32, err, errlen, true))
     return KGE_ERR_CUDA;
-  const size_t smem = kRingBytes + 1024;
+  const size_t smem = kRingBytes + kEpiStageBytes + 1024;
   static bool attr_set[2][64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -538,25 +606,28 @@ int fused_launch(const LaunchCtx& c, const StepParams& p, const StepWs& w, int m
   if (grid > c.num_sms) grid = c.num_sms;
   static const bool timing = getenv("KGE_B200_FUSED_TIMING") != nullptr;
   unsigned long long* dbg = nullptr;
-  if (timing) { cudaMalloc(&dbg, (size_t)grid * 8 * sizeof(unsigned long long)); cudaMemset(dbg, 0, (size_t)grid * 64); g.dbg = dbg; }
+  if (timing) { cudaMalloc(&dbg, (size_t)grid * 16 * sizeof(unsigned long long)); cudaMemset(dbg, 0, (size_t)grid * 128); g.dbg = dbg; }
   if (P) KGE_LAUNCH_NAMED(c, "k_fused<P: S=A.Bn^T, loss, GA=V.Bn>", k_fused<F_P>, grid, kThreadsF, smem, mXh, mXl, mYh1, mYl1, mYh2, mYl2, g);
   else KGE_LAUNCH_NAMED(c, "k_fused<N: S^T, G_neg=V^T.A, mean sq>", k_fused<F_N>, grid, kThreadsF, smem, mXh, mXl, mYh1, mYl1, mYh2, mYl2, g);
   if (timing) {
     cudaStreamSynchronize(c.stream);
-    unsigned long long* hb = (unsigned long long*)malloc((size_t)grid * 64);
-    cudaMemcpy(hb, dbg, (size_t)grid * 64, cudaMemcpyDeviceToHost);
-    double t[7] = {0, 0, 0, 0, 0, 0, 0};
+    unsigned long long* hb = (unsigned long long*)malloc((size_t)grid * 128);
+    cudaMemcpy(hb, dbg, (size_t)grid * 128, cudaMemcpyDeviceToHost);
+    double t[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     unsigned long long mn = ~0ull, mx = 0;
     for (int i = 0; i < grid; ++i) {
-      const unsigned long long* r = hb + (size_t)i * 8;
-      for (int k = 1; k < 7; ++k) t[k] += (double)(r[k] - r[0]);
+      const unsigned long long* r = hb + (size_t)i * 16;
+      for (int k = 1; k < 12; ++k) t[k] += (double)(r[k] - r[0]);
       if (r[0] < mn) mn = r[0];
       if (r[6] > mx) mx = r[6];
     }
     fprintf(stderr, "[fused timing] mode %c ctas=%d tiles=%d (first tile, us since CTA start) first_stage=%.2f gemm1_done=%.2f softmax_done=%.2f "
-            "gemm2_chunk0=%.2f gemm2_last=%.2f tile_end=%.2f span=%.2f  (nS1=%d nS2=%d Wc=%d N1=%d)\n", P ? 'P' : 'N', grid, p.C * mtiles,
+            "gemm2_chunk0=%.2f gemm2_last=%.2f tile_end=%.2f span=%.2f  (nS1=%d nS2=%d Wc=%d N1=%d)\n"
+            "               epilogue warp 2: chunk0 stored=%.2f | chunk1: b loaded=%.2f acc ready=%.2f released=%.2f stored=%.2f\n",
+            P ? 'P' : 'N', grid, p.C * mtiles,
             t[1] / grid / 1e3, t[2] / grid / 1e3, t[3] / grid / 1e3, t[4] / grid / 1e3, t[5] / grid / 1e3, t[6] / grid / 1e3,
-            (double)(mx - mn) / 1e3, g.nS1, g.nS2, g.Wc, g.N1);
+            (double)(mx - mn) / 1e3, g.nS1, g.nS2, g.Wc, g.N1,
+            t[7] / grid / 1e3, t[8] / grid / 1e3, t[9] / grid / 1e3, t[10] / grid / 1e3, t[11] / grid / 1e3);
     free(hb); cudaFree(dbg);
   }
   cudaError_t e = cudaGetLastError();

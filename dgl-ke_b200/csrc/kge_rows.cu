@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(kRowBlock) k_prep(StepParams p, TableView ent,
     float pos, a2, reg, nrm;
     const long long ro = job * (long long)p.D;
     // tcgen05 engine: A is only consumed as hi/lo operands; fp32 tiles: plain fp32
-    const RowOut ao{w.Ahi ? nullptr : w.A + ro, w.Ahi, w.Alo, job / p.Cs, slab_blocks(p.D), p.Cs, (int)(job % p.Cs)};
+    const RowOut ao{w.Ahi ? nullptr : w.A + ro, w.Ahi, w.Alo, job / p.Cs, slab_blocks(p.D), p.Cs, (int)(job % p.Cs), p.split_trunc};
     edge_forward<MODEL, KIT>(p, h, r, t, ao, lane, pos, a2, reg, nrm, true);
     if (lane == 0) {
       w.pos[job] = pos;
@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(kRowBlock) k_prep(StepParams p, TableView ent,
     const float* src = row_ptr(ent, b.neg_ids[job]);
     const long long ro = job * (long long)p.D;
     // fused contraction: the negatives exist only as TF32 hi/lo slabs (Bn receives their gradient later)
-    const RowOut bo{p.fused ? nullptr : w.Bn + ro, w.Bhi, w.Blo, job / p.Ns, slab_blocks(p.D), p.Ns, (int)(job % p.Ns)};
+    const RowOut bo{p.fused ? nullptr : w.Bn + ro, w.Bhi, w.Blo, job / p.Ns, slab_blocks(p.D), p.Ns, (int)(job % p.Ns), p.split_trunc};
     float b2 = 0.f, reg = 0.f;
     const int nv = p.D >> 2;
     for (int v0 = 0; v0 < nv; v0 += kWarp * KIT) {
@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(kRowBlock) k_prep_dense(StepParams p, const fl
     if (!want_pos) { if (p.neg_head) hrow = trow; else trow = hrow; }
     const long long ro = job * (long long)p.D;
     const RowOut ao{(want_a && !w.Ahi) ? w.A + ro : nullptr, want_a ? w.Ahi : nullptr, want_a ? w.Alo : nullptr,
-                    job / p.Cs, slab_blocks(p.D), p.Cs, (int)(job % p.Cs)};
+                    job / p.Cs, slab_blocks(p.D), p.Cs, (int)(job % p.Cs), 0};
     edge_forward<MODEL, 1>(p, hrow, relr + job * (long long)p.Dr, trow, ao, lane, pos, a2, reg, nrm, want_a);
     if (lane == 0) {
       if (want_pos) w.pos[job] = pos;
@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(kRowBlock) k_prep_dense(StepParams p, const fl
   if (job < p.Nn && negrows != nullptr) {
     const float* src = negrows + job * (long long)p.D;
     const long long ro = job * (long long)p.D;
-    const RowOut bo{nullptr, w.Bhi, w.Blo, job / p.Ns, slab_blocks(p.D), p.Ns, (int)(job % p.Ns)};
+    const RowOut bo{nullptr, w.Bhi, w.Blo, job / p.Ns, slab_blocks(p.D), p.Ns, (int)(job % p.Ns), 0};
     float b2 = 0.f;
     for (int v = lane; v < (p.D >> 2); v += kWarp) {
       float4 x = ld4(src + 4 * v);
@@ -774,6 +774,51 @@ __device__ __forceinline__ void upd_node(const StepParams& p, const TableView& e
   const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
   const bool sharded = ent.n_shards > 1;
   const bool reg_on = (p.reg_coef > 0.f && p.reg_norm > 0);
+  float* st = state_ptr(ent, id);
+  if (nv <= 4 * kWarp) {
+    // row in registers (D <= 512): one read of NG and of the traced copy, no second pass through memory
+    float4 x[4], gq[4];
+    float gs = 0.f, reg = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int v = lane + kWarp * q;
+      x[q] = (v < nv) ? ld4(nc + 4 * v) : z;
+      gq[q] = (v < nv) ? ld4(ng + 4 * v) : z;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int v = lane + kWarp * q;
+      if (v < nv) {
+        gq[q] = f4_add(gq[q], reg_grad4(x[q], p.reg_norm, p.reg_coef));
+        gs += f4_dot(gq[q], gq[q]);
+        if (reg_on && !p.use_nc) reg += abs_pow4_sum(x[q], p.reg_norm);
+      }
+    }
+    gs = warp_sum(gs) / (float)p.D;
+    if (!p.use_nc) {            // no k_gather_nodes ran: this node's share of the regulariser is produced here
+      reg = warp_sum(reg);
+      if (lane == 0) w.regp[p.B + p.Nn + u] = reg;
+    }
+    float s_new = 0.f;
+    if (lane == 0) {
+      if (sharded) s_new = atomicAdd_system(st, gs) + gs;   // remote-safe: other GPUs may add to the same state
+      else { s_new = *st + gs; *st = s_new; }
+    }
+    s_new = __shfl_sync(0xffffffffu, s_new, 0);
+    const float stdv = sqrtf(s_new) + 1e-10f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int v = lane + kWarp * q;
+      if (v < nv) {
+        const float4 g = gq[q];
+        float4 tmp = make_float4((-p.lr * g.x) / stdv, (-p.lr * g.y) / stdv, (-p.lr * g.z) / stdv, (-p.lr * g.w) / stdv);
+        if (sharded) red_add4_sys(row + 4 * v, tmp);
+        else st4(row + 4 * v, f4_add(x[q], tmp));
+        st4(ng + 4 * v, z);
+      }
+    }
+    return;
+  }
   // pass 1: g = NG + reg'(x), mean(g^2)
   float gs = 0.f, reg = 0.f;
   for (int v = lane; v < nv; v += kWarp) {
@@ -787,7 +832,6 @@ __device__ __forceinline__ void upd_node(const StepParams& p, const TableView& e
     reg = warp_sum(reg);
     if (lane == 0) w.regp[p.B + p.Nn + u] = reg;
   }
-  float* st = state_ptr(ent, id);
   float s_new = 0.f;
   if (lane == 0) {
     if (sharded) s_new = atomicAdd_system(st, gs) + gs;   // remote-safe: other GPUs may add to the same state
@@ -851,7 +895,7 @@ __global__ void __launch_bounds__(kRowBlock) k_update(UpdArgs a) {
   const bool rel_edge = !p.rel_deferred && !p.rel_dense;      // relation entry handled per edge, here
   for (int phase = a.phase_lo; phase <= a.phase_hi; ++phase) {
     if (phase == 1) {
-      const long long nrel = p.rel_dense ? a.rel.num_rows : 0;
+      const long long nrel = (p.rel_dense && !p.rel_deferred) ? a.rel.num_rows : 0;
       for (long long j = warp0; j < p.U + nrel; j += nwarps) {
         if (j < p.U) upd_node(p, a.ent, a.b, w, j, lane);
         else upd_rel_dense(a.rel, w.rg, w.rgs, j - p.U, p.lr, lane);
@@ -907,7 +951,7 @@ int launch_update(const LaunchCtx& c, const StepParams& p, const TableView& ent,
                   const BatchView& b, const StepWs& w, float* log4, const float* wt) {
   UpdArgs a{p, ent, rel, b, w, log4, wt, 1, 3};
   // job counts per phase (warps): nodes (+ relations), negatives (+ edges), negatives + edges
-  const long long nrel = p.rel_dense ? rel.num_rows : 0;
+  const long long nrel = (p.rel_dense && !p.rel_deferred) ? rel.num_rows : 0;
   const long long nr = (!p.rel_deferred && !p.rel_dense) ? p.B : 0;
   long long jobs = p.U + nrel;
   if (p.Nn + nr > jobs) jobs = p.Nn + nr;
@@ -920,7 +964,10 @@ int launch_update(const LaunchCtx& c, const StepParams& p, const TableView& ent,
     occ[dev] = n;
   }
   static const bool no_coop = getenv("KGE_B200_NO_COOP") != nullptr;
-  const int max_resident = c.num_sms * (dev >= 0 && dev < 64 ? occ[dev] : 1);
+  // multi-GPU: the NCCL all-reduce of the relation sums runs beside this kernel; leave it a few SMs so that the
+  // all-or-nothing cooperative launch does not have to wait for it (or it for us)
+  const int sms = (p.rel_deferred && c.num_sms > 32) ? c.num_sms - 16 : c.num_sms;
+  const int max_resident = sms * (dev >= 0 && dev < 64 ? occ[dev] : 1);
   int grid = ceil_div(jobs, kWarpsPerBlock);
   if (!no_coop) {
     if (grid > max_resident) grid = max_resident;

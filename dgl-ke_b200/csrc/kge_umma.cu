@@ -99,8 +99,8 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CU
   if (g.dbg && threadIdx.x == 0) { g.dbg[cta_lin * 6 + 4] = t_entry; g.dbg[cta_lin * 6 + 0] = gtime(); }
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (all lanes run the loop, one elected lane issues) =====================
+    {
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % kStages;
         const uint32_t ph = (kb / kStages) & 1;
@@ -110,6 +110,7 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CU
         uint8_t* sBh = st + 2 * kABytes; uint8_t* sBl = sBh + bBytesAligned;
         const int k0 = kb * kBlockK;
         uint32_t tx = 2 * kABytes + 2 * bBytes;
+        if (elect_one()) {
         mbar_expect_tx(&full_bar[s], tx);
         // slab layout: row coordinate of (chunk c, 32-column block blk, row r) = (c * nblk + blk) * R + r; x = 0
         if (!A_MN) {
@@ -137,23 +138,26 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CU
             tma_load_2d(sBl + b * 4096, &tmBl, &full_bar[s], 0, yb);
           }
         }
+        }   // elect_one
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
+    {
       const uint32_t idesc = make_idesc(kTileM, Nt, A_MN, B_MN);
       uint32_t accumulate = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % kStages;
         const uint32_t ph = (kb / kStages) & 1;
         mbar_wait(&full_bar[s], ph);
-        if (g.dbg && kb == 0) g.dbg[cta_lin * 6 + 1] = gtime();
+        if (g.dbg && kb == 0 && lane == 0) g.dbg[cta_lin * 6 + 1] = gtime();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t st = smem_u32(smem + (size_t)s * stageBytes);
         const uint32_t sAh = st, sAl = st + kABytes, sBh = st + 2 * kABytes, sBl = sBh + bBytesAligned;
         const int kleft = K - kb * kBlockK;
         const int ksteps = kleft >= kBlockK ? kBlockK / kUmmaK : kleft / kUmmaK;   // K % 8 == 0 guaranteed
+        if (elect_one()) {
         for (int ks = 0; ks < ksteps; ++ks) {
           // K-major: +32 bytes per k-step inside the 128-byte swizzle span; SBO = 1024 (8-row groups)
           // MN-major (128B swizzle, 32B atoms): k-atoms of 4 rows (512 B, SBO), one k-step = 2 atoms = 1024 B;
@@ -164,14 +168,16 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CU
           const uint64_t dAl = A_MN ? make_desc(sAl + aoff, 4096, 512, 1) : make_desc(sAl + aoff, 16, 1024);
           const uint64_t dBh = B_MN ? make_desc(sBh + boff, 4096, 512, 1) : make_desc(sBh + boff, 16, 1024);
           const uint64_t dBl = B_MN ? make_desc(sBl + boff, 4096, 512, 1) : make_desc(sBl + boff, 16, 1024);
-          umma_tf32(tmem_base, dAh, dBh, idesc, accumulate);
+          umma_tf32(tmem_base, dAh, dBh, idesc, (accumulate | (uint32_t)ks) ? 1u : 0u);
           umma_tf32(tmem_base, dAh, dBl, idesc, 1u);
           umma_tf32(tmem_base, dAl, dBh, idesc, 1u);
-          accumulate = 1u;
         }
         umma_commit(&empty_bar[s]);          // frees the smem stage when these MMAs retire
+        if (kb == num_kb - 1) umma_commit(&tmem_full_bar);           // accumulator complete
+        }   // elect_one
+        accumulate = 1u;
+        __syncwarp();
       }
-      umma_commit(&tmem_full_bar);           // accumulator complete
     }
   } else {
     // ===================== epilogue: warps 2..9, TMEM lane quarter = warp % 4 =====================

@@ -17,8 +17,8 @@ BUF_POS_SCORE, BUF_NEG_SCORE, BUF_NODE_GRAD, BUF_NEG_GRAD, BUF_REL_GRAD = range(
 
 EXPORTS = ["kge_abi_version", "kge_last_error", "kge_create", "kge_destroy", "kge_gather", "kge_score_pos",
            "kge_score_neg", "kge_loss_grad", "kge_adagrad", "kge_forward_backward", "kge_update",
-           "kge_step_fused", "kge_step_fused_host", "kge_sync", "kge_debug_read", "kge_launch_count",
-           "kge_set_engine", "kge_set_fused", "kge_debug_set_dump", "kge_profile_enable", "kge_profile_read", "kge_set_relation_mode",
+           "kge_step_fused", "kge_step_fused_begin", "kge_step_fused_end", "kge_step_fused_host", "kge_sync", "kge_debug_read", "kge_launch_count",
+           "kge_set_engine", "kge_set_fused", "kge_debug_set_dump", "kge_profile_enable", "kge_profile_read", "kge_set_relation_mode", "kge_set_relation_buffers",
            "kge_rel_grad_dense", "kge_rel_apply_dense", "kge_device_alloc", "kge_device_free", "kge_ipc_export",
            "kge_ipc_open"]
 
@@ -77,6 +77,8 @@ def load_library():
     lib.kge_forward_backward.argtypes = [vp, P(StepCfg), P(Table), P(Table), P(Batch), vp, vp]
     lib.kge_update.argtypes = [vp, P(StepCfg), P(Table), P(Table), P(Batch), vp]
     lib.kge_step_fused.argtypes = [vp, P(StepCfg), P(Table), P(Table), P(Batch), vp, vp]
+    lib.kge_step_fused_begin.argtypes = [vp, P(StepCfg), P(Table), P(Table), P(Batch), vp]
+    lib.kge_step_fused_end.argtypes = [vp, P(StepCfg), P(Table), P(Table), P(Batch), vp, vp]
     lib.kge_step_fused_host.argtypes = [vp, P(StepCfg), P(Table), P(Table), P(Batch), vp, vp]
     lib.kge_sync.argtypes = [vp, vp]
     lib.kge_debug_read.argtypes = [vp, C.c_int, vp, i64, vp]
@@ -88,6 +90,7 @@ def load_library():
     lib.kge_profile_enable.argtypes = [vp, C.c_int]
     lib.kge_profile_read.argtypes = [vp, C.c_char_p, C.c_int, P(f32), C.c_int]
     lib.kge_set_relation_mode.argtypes = [vp, C.c_int]
+    lib.kge_set_relation_buffers.argtypes = [vp, vp, vp]
     lib.kge_rel_grad_dense.argtypes = [vp, vp, vp, vp]
     lib.kge_rel_apply_dense.argtypes = [vp, P(Table), vp, vp, f32, vp]
     lib.kge_device_alloc.argtypes = [vp, i64, P(vp)]

@@ -102,6 +102,8 @@ class ShardedTrainer:
         self.rbuf = torch.zeros(n_rel * Dr + n_rel, dtype=torch.float32, device=device)
         self.rg, self.rgs = self.rbuf[:n_rel * Dr], self.rbuf[n_rel * Dr:]
         _lib.check(lib.kge_set_relation_mode(self.h.raw, 1))
+        # the fused step sums the relation gradients straight into the all-reduce buffer
+        _lib.check(lib.kge_set_relation_buffers(self.h.raw, self.rg.data_ptr(), self.rgs.data_ptr()))
         self.eng = StepEngine(hp, self.ent, self.rel, device.index)
         self.log4 = self.eng.log4
         self._log_host = torch.zeros(4, dtype=torch.float32).pin_memory()
@@ -109,14 +111,18 @@ class ShardedTrainer:
 
     # -- one training step: forward/backward, entity Adagrad over NVLink, relation all-reduce + apply
     def step(self, node_ids, head_local, tail_local, rel_ids, neg_ids, chunk_size, neg_sample_size, neg_head,
-             edge_weight=None, log4=None):
+             edge_weight=None, log4=None, sync_between=False):
+        """sync_between (tests): a cross-rank barrier between the gradient half and the update half, so that every
+        rank's gradients come from the same table snapshot."""
         lib, h = self.h.lib, self.h
-        out = self.eng.forward_backward(node_ids, head_local, tail_local, rel_ids, neg_ids, chunk_size,
-                                        neg_sample_size, neg_head, edge_weight, log4)
-        _lib.check(lib.kge_rel_grad_dense(h.raw, self.rg.data_ptr(), self.rgs.data_ptr(), h.stream()))
-        # the relation all-reduce (NCCL stream) overlaps the entity Adagrad kernels, which do not touch rbuf
+        # gather (peer loads) .. k_chain: per-relation gradient sums land in rbuf
+        self.eng.step_begin(node_ids, head_local, tail_local, rel_ids, neg_ids, chunk_size, neg_sample_size, neg_head,
+                            edge_weight)
+        # the relation all-reduce (NCCL stream) overlaps the entity Adagrad kernel, which does not touch rbuf
+        if sync_between:
+            self.barrier()
         work = dist.all_reduce(self.rbuf, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
-        self.eng.update()
+        out = self.eng.step_end(log4)
         work.wait()
         _lib.check(lib.kge_rel_apply_dense(h.raw, self.rel.ref(), self.rg.data_ptr(), self.rgs.data_ptr(),
                                            float(self.hp.lr), h.stream()))

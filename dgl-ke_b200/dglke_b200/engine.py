@@ -109,6 +109,27 @@ class StepEngine:
                                            out.data_ptr(), self.h.stream()))
         return out
 
+    def step_begin(self, node_ids, head_local, tail_local, rel_ids, neg_ids, chunk_size, neg_sample_size, neg_head,
+                   edge_weight=None):
+        """first half of step(): everything up to the gradients (kge_step_fused_begin)"""
+        cfg = self.cfg(head_local.numel(), chunk_size, neg_sample_size, neg_head)
+        b, keep = _lib.make_batch(node_ids, head_local, tail_local, rel_ids, neg_ids, edge_weight)
+        _lib.check(self.lib.kge_step_fused_begin(self.h.raw, C.byref(cfg), self.ent.ref(), self.rel.ref(), C.byref(b),
+                                                 self.h.stream()))
+        self._last = (cfg, b, keep)
+
+    def step_end(self, log4=None):
+        """second half of step(): the Adagrad update + log scalars (kge_step_fused_end)"""
+        if self._last is None:
+            raise _lib.KgeError("step_end() without step_begin()")
+        cfg, b, keep = self._last
+        cfg.lr = self.hp.lr
+        out = self.log4 if log4 is None else log4
+        _lib.check(self.lib.kge_step_fused_end(self.h.raw, C.byref(cfg), self.ent.ref(), self.rel.ref(), C.byref(b),
+                                               out.data_ptr(), self.h.stream()))
+        self._last = None
+        return out
+
     def step_host(self, node_ids, head_local, tail_local, rel_ids, neg_ids, chunk_size, neg_sample_size, neg_head,
                   edge_weight=None):
         """Index tensors are CPU tensors (as a sampler produces them); returns the pinned host

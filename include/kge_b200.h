@@ -174,6 +174,13 @@ KGE_API int kge_update(kge_handle_t h, const kge_step_cfg_t* cfg, const kge_tabl
 KGE_API int kge_step_fused(kge_handle_t h, const kge_step_cfg_t* cfg, const kge_table_t* ent,
                    const kge_table_t* rel, const kge_batch_t* batch, float* log4, void* stream);
 
+/* kge_step_fused in two halves, for callers that put a collective between them (multi-GPU: the relation all-reduce
+ * overlaps the entity update): begin = gather .. k_chain, end = k_update (+ log scalars into log4). */
+KGE_API int kge_step_fused_begin(kge_handle_t h, const kge_step_cfg_t* cfg, const kge_table_t* ent,
+                         const kge_table_t* rel, const kge_batch_t* batch, void* stream);
+KGE_API int kge_step_fused_end(kge_handle_t h, const kge_step_cfg_t* cfg, const kge_table_t* ent,
+                       const kge_table_t* rel, const kge_batch_t* batch, float* log4, void* stream);
+
 /* Same as kge_step_fused but the batch index arrays (and edge weights) are HOST memory, as they
  * come out of the sampler.  Pageable arrays are staged through the handle's pinned buffer (they may be
  * reused as soon as the call returns); page-locked arrays (cudaHostAlloc / torch pin_memory) are DMA'd
@@ -228,6 +235,10 @@ KGE_API int kge_debug_set_dump(kge_handle_t h, float* coef_dump);
  * (sum of mean(g^2)), the host all-reduces both with NCCL, and kge_rel_apply_dense applies the same
  * Adagrad update on every replica and zeroes the buffers. */
 KGE_API int kge_set_relation_mode(kge_handle_t h, int deferred);
+/* Deferred mode, fused step: caller-owned dense buffers rg [num_rel, D_r] and rgs [num_rel] (zero between steps) that
+ * kge_step_fused_begin sums the per-relation gradients / mean squares into directly (no per-edge rows, no
+ * kge_rel_grad_dense); the caller all-reduces them and calls kge_rel_apply_dense.  NULL, NULL = off. */
+KGE_API int kge_set_relation_buffers(kge_handle_t h, float* rg, float* rgs);
 KGE_API int kge_rel_grad_dense(kge_handle_t h, float* rg, float* rgs, void* stream);
 KGE_API int kge_rel_apply_dense(kge_handle_t h, const kge_table_t* rel, float* rg, float* rgs, float lr, void* stream);
 KGE_API int kge_device_alloc(kge_handle_t h, int64_t bytes, void** out);

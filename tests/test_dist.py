@@ -11,18 +11,23 @@ import torch as th
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _torchrun(nproc, script, *args, timeout=600):
+def _torchrun(nproc, script, *args, timeout=600, env=None):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc),
            "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 2000), script, *args]
-    return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT)
+    e = dict(os.environ)
+    e.update(env or {})
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT, env=e)
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["disjoint", "overlap"])
 @pytest.mark.parametrize("model", ["TransE_l2", "ComplEx"])
-def test_sharded_trainer_matches_oracle(model):
-    if th.cuda.device_count() < 2:
-        pytest.skip("needs >= 2 GPUs")
-    out = _torchrun(2, os.path.join(ROOT, "tests", "dist_check.py"), model)
+def test_sharded_trainer_matches_oracle(model, mode):
+    """2 ranks: on 2 GPUs over NCCL/NVLink when the box has them, else both ranks on cuda:0 (gloo for the relation
+    all-reduce): the sharded TableView, the IPC mapping, the system-scope atomics and the fused multi-GPU schedule run
+    either way.  `overlap` = every rank updates the SAME rows (cross-GPU Hogwild)."""
+    env = {} if th.cuda.device_count() >= 2 else {"DIST_SAME_GPU": "1"}
+    out = _torchrun(2, os.path.join(ROOT, "tests", "dist_check.py"), model, mode, env=env)
     assert "DIST_CHECK_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
 
 
