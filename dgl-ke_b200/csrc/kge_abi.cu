@@ -150,7 +150,8 @@ int make_params(const kge_step_cfg_t* cfg, long long n_nodes, StepParams* p, boo
   p->B = cfg->batch; p->Cs = cfg->chunk_size; p->Ns = cfg->neg_sample_size;
   p->C = (int)(cfg->batch / cfg->chunk_size);
   p->Nn = (long long)p->C * p->Ns;
-  p->U = n_nodes;
+  p->U = n_nodes >= 0 ? n_nodes : 2 * p->B;      // capacity when only the device knows the count
+  p->U_dev = nullptr;
   p->rel_deferred = 0; p->rel_dense = 0; p->use_nc = 1; p->fused = 0;
   static const int split_trunc = getenv("KGE_B200_SPLIT_TRUNC") ? atoi(getenv("KGE_B200_SPLIT_TRUNC")) : 0;
   p->split_trunc = split_trunc;
@@ -271,6 +272,7 @@ int check_batch(const kge_batch_t* b, const StepParams& p) {
   if (!b) return fail(KGE_ERR_INVALID_ARG, "batch is null");
   if (!b->node_ids || !b->head_local || !b->tail_local || !b->rel_ids || !b->neg_ids)
     return fail(KGE_ERR_INVALID_ARG, "batch has null index arrays");
+  if (b->n_nodes < 0 && b->n_nodes_dev) return KGE_OK;      // device-side count (kge_sampler_sample)
   if (b->n_nodes <= 0 || b->n_nodes > 2 * p.B) return fail(KGE_ERR_INVALID_ARG, "n_nodes=%lld out of (0, 2*batch]", (long long)b->n_nodes);
   return KGE_OK;
 }
@@ -297,7 +299,7 @@ int umma_grad(const LaunchCtx&, const StepParams&, const StepWs&, bool side_b, c
 // fused contraction (kge_fused.cu): mode 0 = P (scores, loss, GA), mode 1 = N (G_neg, mean squares)
 bool fused_supported(const StepParams&);
 int fused_launch(const LaunchCtx&, const StepParams&, const StepWs&, int mode, const float* wt, float* dumpS, float* dumpV,
-                 char* err, size_t errlen);
+                 const TableView* ent, const long long* neg_ids, char* err, size_t errlen);
 }  // namespace kge
 
 extern "C" {
@@ -536,6 +538,7 @@ static int forward_backward_impl(kge_handle_t h, const kge_step_cfg_t* cfg, cons
   if (rc) return rc;
   rc = check_batch(batch, p);
   if (rc) return rc;
+  if (batch->n_nodes < 0) p.U_dev = (const long long*)batch->n_nodes_dev;
   p.rel_deferred = h->rel_deferred;
   TableView ve, vr;
   if ((rc = make_view(ent, &ve, "entity"))) return rc;
@@ -564,9 +567,9 @@ static int forward_backward_impl(kge_handle_t h, const kge_step_cfg_t* cfg, cons
   float* logdst = log4 ? log4 : h->dev_log4;
   if (p.fused) {
     launch_wbar(c, p, b.edge_weight, w);
-    if ((rc = fused_launch(c, p, w, 0, b.edge_weight, fused_step ? nullptr : w.S, h->dump_v, g_err, sizeof(g_err)))) return rc;
+    if ((rc = fused_launch(c, p, w, 0, b.edge_weight, fused_step ? nullptr : w.S, h->dump_v, &ve, b.neg_ids, g_err, sizeof(g_err)))) return rc;
     if ((rc = fused_launch(c, p, w, 1, b.edge_weight, nullptr,
-                           h->dump_v ? h->dump_v + (size_t)p.B * p.Ns : nullptr, g_err, sizeof(g_err)))) return rc;
+                           h->dump_v ? h->dump_v + (size_t)p.B * p.Ns : nullptr, &ve, b.neg_ids, g_err, sizeof(g_err)))) return rc;
   } else {
     if ((rc = run_score(h, c, p, w))) return rc;
     launch_wbar(c, p, b.edge_weight, w);
@@ -758,6 +761,85 @@ KGE_API int kge_debug_read(kge_handle_t h, int which, float* out, int64_t n_floa
   }
   if (n_floats != n) return fail(KGE_ERR_INVALID_ARG, "expected %lld floats, got %lld", n, (long long)n_floats);
   KGE_CUDA_OK(cudaMemcpyAsync(out, src, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return KGE_OK;
+}
+
+// ---- device-side sampler ----------------------------------------------------------------------
+struct kge_sampler {
+  kge_context* h = nullptr;
+  kge::SamplerParams base{};
+  char* mem = nullptr;           // [2 buffers of index arrays | hash table]
+  size_t buf_stride = 0;         // bytes between the two index buffers
+  int32_t neg_sample_size = 0;
+};
+
+KGE_API int kge_sampler_create(kge_handle_t h, const int64_t* heads, const int64_t* rels, const int64_t* tails, int64_t n_edges,
+                       int64_t n_entities, int64_t batch, int32_t neg_sample_size, uint64_t seed, kge_sampler_t* out) {
+  if (!h || !out) return fail(KGE_ERR_INVALID_ARG, "null argument");
+  *out = nullptr;
+  if (!heads || !rels || !tails) return fail(KGE_ERR_INVALID_ARG, "edge arrays are null");
+  if (batch <= 0 || neg_sample_size <= 0 || n_entities <= 0) return fail(KGE_ERR_INVALID_ARG, "batch / neg_sample_size / n_entities must be positive");
+  if (batch % neg_sample_size != 0 && batch >= neg_sample_size)
+    return fail(KGE_ERR_INVALID_ARG, "batch %lld is not a multiple of neg_sample_size %d (utils.get_compatible_batch_size)", (long long)batch, neg_sample_size);
+  if (n_edges < batch) return fail(KGE_ERR_INVALID_ARG, "fewer edges (%lld) than batch (%lld)", (long long)n_edges, (long long)batch);
+  if (2 * batch >= (1ll << 30)) return fail(KGE_ERR_UNSUPPORTED, "batch too large for the sampler's hash table");
+  DeviceGuard g(h->device);
+  kge_sampler* s = new (std::nothrow) kge_sampler();
+  if (!s) return fail(KGE_ERR_NOMEM, "out of host memory");
+  s->h = h;
+  s->neg_sample_size = neg_sample_size;
+  const long long B = batch, C = batch >= neg_sample_size ? batch / neg_sample_size : 1, Nn = C * neg_sample_size;
+  int hb = 1;
+  while ((1ull << (2 * hb)) < (unsigned long long)n_edges) ++hb;
+  long long H = 1;
+  while (H < 4 * B) H <<= 1;
+  // per buffer: head, rel, tail [B] | neg [Nn] | nodes [2B] | hl, tl [B] | n_nodes [1 (+pad)]
+  const size_t per_buf = align_up((size_t)(7 * B + Nn + 2) * 8);
+  const size_t table = align_up((size_t)H * 8) + 2 * align_up((size_t)H * 4) + align_up((size_t)2 * B * 4);
+  if (cudaMalloc(&s->mem, 2 * per_buf + table) != cudaSuccess) { cudaGetLastError(); delete s; return fail(KGE_ERR_NOMEM, "cudaMalloc for the sampler failed"); }
+  s->buf_stride = per_buf;
+  kge::SamplerParams& p = s->base;
+  p.heads = (const long long*)heads; p.rels = (const long long*)rels; p.tails = (const long long*)tails;
+  p.n_edges = n_edges; p.n_entities = n_entities; p.B = B; p.Nn = Nn; p.seed = seed; p.half_bits = hb;
+  char* t = s->mem + 2 * per_buf;
+  p.tkey = (unsigned long long*)t; t += align_up((size_t)H * 8);
+  p.tpos = (int*)t; t += align_up((size_t)H * 4);
+  p.tloc = (int*)t; t += align_up((size_t)H * 4);
+  p.flags = (int*)t;
+  p.hmask = (int)(H - 1);
+  // empty table: keys ~0, positions INT_MAX (k_sample_reset restores this after every step)
+  if (cudaMemset(p.tkey, 0xff, (size_t)H * 8) != cudaSuccess || cudaMemset(p.tpos, 0x7f, (size_t)H * 4) != cudaSuccess) {
+    cudaGetLastError(); cudaFree(s->mem); delete s; return fail(KGE_ERR_CUDA, "cudaMemset failed");
+  }
+  // 0x7f7f7f7f is what the memset leaves in tpos: larger than any position (< 2^30), like the INT_MAX the reset writes
+  *out = s;
+  return KGE_OK;
+}
+
+KGE_API int kge_sampler_destroy(kge_sampler_t s) {
+  if (!s) return KGE_OK;
+  DeviceGuard g(s->h->device);
+  cudaDeviceSynchronize();
+  if (s->mem) cudaFree(s->mem);
+  delete s;
+  return KGE_OK;
+}
+
+KGE_API int kge_sampler_sample(kge_sampler_t s, int64_t step, kge_batch_t* out, int32_t* neg_head_out, void* stream) {
+  if (!s || !out) return fail(KGE_ERR_INVALID_ARG, "null argument");
+  if (step < 0) return fail(KGE_ERR_INVALID_ARG, "step < 0");
+  DeviceGuard g(s->h->device);
+  kge::SamplerParams p = s->base;
+  long long* b = (long long*)(s->mem + (size_t)(step & 1) * s->buf_stride);
+  p.o_head = b; p.o_rel = b + p.B; p.o_tail = b + 2 * p.B; p.o_neg = b + 3 * p.B;
+  p.o_nodes = b + 3 * p.B + p.Nn; p.o_hl = p.o_nodes + 2 * p.B; p.o_tl = p.o_hl + p.B; p.o_n_nodes = p.o_tl + p.B;
+  launch_sampler(lctx(s->h, stream), p, (long long)step);
+  KGE_CUDA_OK(cudaGetLastError());
+  memset(out, 0, sizeof(*out));
+  out->node_ids = (const int64_t*)p.o_nodes; out->n_nodes = -1; out->n_nodes_dev = (const int64_t*)p.o_n_nodes;
+  out->head_local = (const int64_t*)p.o_hl; out->tail_local = (const int64_t*)p.o_tl;
+  out->rel_ids = (const int64_t*)p.o_rel; out->neg_ids = (const int64_t*)p.o_neg; out->edge_weight = nullptr;
+  if (neg_head_out) *neg_head_out = (int32_t)(step & 1);
   return KGE_OK;
 }
 

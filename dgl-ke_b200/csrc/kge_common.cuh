@@ -47,7 +47,8 @@ struct StepParams {
   long long B;  // positives
   int C, Cs, Ns;
   long long Nn; // C * Ns negative rows
-  long long U;  // unique positive nodes
+  long long U;  // unique positive nodes (capacity 2B when only the device knows the count: U_dev)
+  const long long* U_dev;   // device-side node count (device sampler) or null
   int rel_deferred;  // 1: relation Adagrad is applied later from dense all-reduced buffers (multi-GPU)
   int rel_dense;     // 1: k_chain sums relation gradients per relation into ws.rg / ws.rgs (fused single-GPU step)
   int use_nc;        // 1: head/tail rows are read from the gathered copy NC (3-call API, sharded tables); 0: from the table
@@ -101,6 +102,8 @@ struct BatchView {
   const long long* neg_ids;
   const float* edge_weight;
 };
+
+__device__ __forceinline__ long long node_count(const StepParams& p) { return p.U_dev ? *p.U_dev : p.U; }
 
 // row of the positive graph's local node `loc` (pos_g.ndata['emb'][loc], general_models.py:548): the gathered copy,
 // or the table row itself when nothing can have changed it since the gather (single-GPU fused step)
@@ -306,6 +309,28 @@ inline void prof_end(const LaunchCtx& c) {
     prof_end((ctx));                                                            \
     if ((ctx).launch_counter) ++*(ctx).launch_counter;                          \
   } while (0)
+
+// device-side sampler (kge_sampler.cu)
+struct SamplerParams {
+  const long long *heads, *rels, *tails;   // the partition's edges (device)
+  long long n_edges, n_entities;
+  long long B, Nn;
+  unsigned long long seed;
+  int half_bits;                            // Feistel half width: 2^(2*half_bits) >= n_edges
+  // outputs
+  long long *o_head, *o_rel, *o_tail;       // [B] global ids of the sampled positives
+  long long *o_neg;                         // [Nn]
+  long long *o_nodes, *o_hl, *o_tl;         // [2B], [B], [B]
+  long long* o_n_nodes;                     // [1]
+  // hash table of the batch's distinct entity ids
+  unsigned long long* tkey;                 // [H], ~0 = empty
+  int* tpos;                                // [H] smallest position of the key in [heads | tails]
+  int* tloc;                                // [H] local id of the key
+  int hmask;                                // H - 1
+  int* flags;                               // [2B] 1 = first occurrence
+};
+
+void launch_sampler(const LaunchCtx&, const SamplerParams&, long long step);
 
 void launch_gather(const LaunchCtx&, const TableView& t, const long long* idx, long long n, float* out);
 void launch_gather_nodes(const LaunchCtx&, const StepParams&, const TableView& ent, const BatchView&, const StepWs&);

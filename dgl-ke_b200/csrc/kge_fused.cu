@@ -17,8 +17,8 @@
 // trip of S and V (and the k_loss / k_colsum / k_state_add launches).  fp32 fidelity: operands are TF32 hi/lo pairs
 // and every k-step issues hi*hi + hi*lo + lo*hi (3xTF32, fp32 accumulation in TMEM).
 //
-// CTA = 320 threads: warp 0 TMA producer, warp 1 TMEM allocator + single-thread tcgen05.mma issuer, warps 2-9
-// epilogue (two warps per TMEM lane quarter, splitting the columns).  Persistent over (chunk, 128-row tile) work
+// CTA = 384 threads: warps 0-7 epilogue (two warps per TMEM lane quarter, splitting the columns), warp 8 TMA producer,
+// warp 9 TMEM allocator + tcgen05.mma issuer (one elected lane), warps 10-11 idle (they only give their registers away).  Persistent over (chunk, 128-row tile) work
 // items.  TMEM columns: [0,N1) S -> V_hi | [N1,2N1) distances -> V_lo | [2N1, 2N1+Wc) accumulator of GEMM2, which is
 // processed in Wc-wide column chunks of the output (Wc = 96 at Ns = 200).  Shared memory: one 216 KB ring used as
 // nS1 stages {X_hi,X_lo,Y_hi,Y_lo} by GEMM1 and as nS2 stages {Y_hi,Y_lo} (MN-major) by GEMM2.
@@ -35,7 +35,8 @@ using namespace tc;
 namespace {
 
 constexpr int kTileM = 128;
-constexpr int kThreadsF = 320;
+constexpr int kThreadsF = 384;                    // warps 0-7 epilogue (two warpgroups), 8 TMA producer, 9 MMA issuer, 10-11 idle
+constexpr int kProducerWarp = 8, kMmaWarp = 9;
 constexpr int kMaxS1 = 4, kMaxS2 = 8;
 constexpr uint32_t kRingBytes = 192 * 1024;
 constexpr int kStagePitch = 20;                      // floats per row of an epilogue staging tile (16 + 4 pad, 16-byte aligned rows)
@@ -69,9 +70,13 @@ struct FusedArgs {
   const float* cstat_m;  // per positive: softmax shift (log2 domain)
   const float* cstat_k;  // per positive: w_i / (2B den_i)  (or w_i / (2B Ns))
   const float *Xhi, *Xlo;  // slabs of the lane-side rows (negatives): b = hi + lo in the epilogue
+  const long long* xids;   // mode N, one GPU: entity ids of the lane-side rows -- b is then read from the table itself
+  TableView xtab;          //   (one fp32 load instead of hi + lo; nothing updates the table before k_update)
   float* gsn;            // [C*Rx] mean(G_neg^2)
   float* out;            // P: GA [C*Rx, D]; N: G_neg [C*Rx, D]
   unsigned long long* dbg;   // optional per-CTA timestamps of the first tile (KGE_B200_FUSED_TIMING=1)
+  int exp_halfload;          // experiment (KGE_B200_FUSED_HALFLOAD): skip the TMA loads of the lo tiles (WRONG results;
+                             // shows how much of the GEMM time is operand traffic)
 };
 
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
@@ -109,11 +114,11 @@ k_fused(const __grid_constant__ CUtensorMap mXh, const __grid_constant__ CUtenso
     mbar_init(&s_full, 1); mbar_init(&v_ready, 8); mbar_init(&acc_full, 1); mbar_init(&acc_empty, 8);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0 && lane == 0) {
+  if (warp == kProducerWarp && lane == 0) {
     tma_prefetch_desc(&mXh); tma_prefetch_desc(&mXl); tma_prefetch_desc(&mYh1);
     tma_prefetch_desc(&mYl1); tma_prefetch_desc(&mYh2); tma_prefetch_desc(&mYl2);
   }
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
@@ -122,10 +127,16 @@ k_fused(const __grid_constant__ CUtensorMap mXh, const __grid_constant__ CUtenso
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
   if (g.dbg && threadIdx.x == 0) g.dbg[blockIdx.x * 16 + 0] = gtime();
+  (void)0;
 
   // Roles.  The producer and MMA warps run their loops with all 32 lanes (warp-uniform control flow and operands, so the
   // address / descriptor arithmetic stays on the uniform datapath) and one elected lane issues the TMA / tcgen05 ops.
-  if (warp == 0) {
+  // Registers: a 12-warp CTA is capped at 168 per thread; the third warpgroup (producer, MMA issuer, two idle warps)
+  // hands most of its share to the two epilogue warpgroups, which keep whole accumulator chunks and two chunks' worth of
+  // prefetched rows in registers.
+  if (warp >= 8) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+  if (warp == kProducerWarp) {
     // ================================ TMA producer ================================
     uint32_t n1 = 0, n2 = 0;      // stage fills issued so far (GEMM1 / GEMM2)
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -140,11 +151,17 @@ k_fused(const __grid_constant__ CUtensorMap mXh, const __grid_constant__ CUtenso
         const int yx = (c * g.nblkD + kb) * g.Rx + m0;
         const int yy = (c * g.nblkD + kb) * g.Ry;
         if (elect_one()) {
+          if (g.exp_halfload) {
+            mbar_expect_tx(&full1[s], 16384u + yBytes1);
+            tma_load_2d(st, &mXh, &full1[s], 0, yx);
+            tma_load_2d(st + 32768, &mYh1, &full1[s], 0, yy);
+          } else {
           mbar_expect_tx(&full1[s], 2u * 16384u + 2u * yBytes1);
           tma_load_2d(st, &mXh, &full1[s], 0, yx);
           tma_load_2d(st + 16384, &mXl, &full1[s], 0, yx);
           tma_load_2d(st + 32768, &mYh1, &full1[s], 0, yy);
           tma_load_2d(st + 32768 + yBytes1, &mYl1, &full1[s], 0, yy);
+          }
         }
         __syncwarp();
       }
@@ -160,17 +177,17 @@ k_fused(const __grid_constant__ CUtensorMap mXh, const __grid_constant__ CUtenso
           uint8_t* st = ring + (size_t)s * g.stage2Bytes;
           const int yy0 = (c * g.nblkD + (d0 >> 5)) * g.Ry + kb * 32;
           if (elect_one()) {
-            mbar_expect_tx(&full2[s], 2u * (uint32_t)nb * 4096u);
+            mbar_expect_tx(&full2[s], (g.exp_halfload ? 1u : 2u) * (uint32_t)nb * 4096u);
             for (int b = 0; b < nb; ++b) {
               tma_load_2d(st + b * 4096, &mYh2, &full2[s], 0, yy0 + b * g.Ry);
-              tma_load_2d(st + yBytes2 + b * 4096, &mYl2, &full2[s], 0, yy0 + b * g.Ry);
+              if (!g.exp_halfload) tma_load_2d(st + yBytes2 + b * 4096, &mYl2, &full2[s], 0, yy0 + b * g.Ry);
             }
           }
           __syncwarp();
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kMmaWarp) {
     // ================================ MMA issuer ================================
     uint32_t n1 = 0, n2 = 0, nacc = 0, it = 0;
     const uint32_t idesc1 = make_idesc(kTileM, g.N1, false, false);
@@ -189,13 +206,20 @@ k_fused(const __grid_constant__ CUtensorMap mXh, const __grid_constant__ CUtenso
         const int kleft = g.D - kb * 32;
         const int ksteps = kleft >= 32 ? 4 : (kleft >> 3);
         if (elect_one()) {
+          // Two accumulators (TMEM regions 1 and 2, summed by the epilogue): even k-steps -> region 1, odd -> region 2,
+          // issued term-major so that consecutive MMAs never accumulate into the same tile back to back.
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            if (ks < ksteps) {
-              const uint64_t o = (uint64_t)(ks * 2);     // K-major: +32 bytes per k-step inside the 128-byte swizzle span
-              umma_tf32(tmem_base, dXh + o, dYh + o, idesc1, (kb | ks) ? 1u : 0u);
-              umma_tf32(tmem_base, dXh + o, dYl + o, idesc1, 1u);
-              umma_tf32(tmem_base, dXl + o, dYh + o, idesc1, 1u);
+          for (int term = 0; term < 3; ++term) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              if (ks < ksteps) {
+                const uint64_t o = (uint64_t)(ks * 2);   // K-major: +32 bytes per k-step inside the 128-byte swizzle span
+                const uint32_t dst = tmem_base + ((ks & 1) ? colR2 : 0u);
+                const uint32_t acc = (kb == 0 && ks < 2 && term == 0) ? 0u : 1u;
+                if (term == 0) umma_tf32(dst, dXh + o, dYh + o, idesc1, acc);
+                else if (term == 1) umma_tf32(dst, dXh + o, dYl + o, idesc1, 1u);
+                else umma_tf32(dst, dXl + o, dYh + o, idesc1, 1u);
+              }
             }
           }
           umma_commit(&empty1[s]);
@@ -242,12 +266,14 @@ k_fused(const __grid_constant__ CUtensorMap mXh, const __grid_constant__ CUtenso
         }
       }
     }
+  }
   } else {
-    // ================================ epilogue warps 2..9 ================================
+    // ================================ epilogue warps 0..7 ================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
-    const int ehalf = (warp - 2) >> 2;            // two warps share a quarter and split the columns
+    const int ehalf = warp >> 2;                  // two warps share a quarter and split the columns
     const int row = q * 32 + lane;                // accumulator row = lane-side row inside the tile
-    const int et = threadIdx.x - 64;              // 0..255
+    const int et = threadIdx.x;                   // 0..255
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
     const int h0 = ((g.N1 >> 1) + 15) & ~15;
     const int cb = ehalf ? h0 : 0, ce = ehalf ? g.N1 : h0;
@@ -267,9 +293,19 @@ k_fused(const __grid_constant__ CUtensorMap mXh, const __grid_constant__ CUtenso
       epi_bar();
       const float x2v = (l2 && row_ok) ? g.x2[gx] : 0.f;
       float colsum = 0.f;
+      // mode N, one GPU: table rows of the 4 lane-side rows this lane handles in the transposed epilogue mapping
+      // (ids fetched now, while GEMM1 runs: the epilogue's row loads then depend on nothing)
+      const float* brow[4] = {nullptr, nullptr, nullptr, nullptr};
+      if (MODE == F_N && g.xids) {
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int mr = m0 + q * 32 + (lane >> 2) + 8 * it;
+          brow[it] = row_ptr(g.xtab, mr < g.Rx ? g.xids[(long long)c * g.Rx + mr] : 0);
+        }
+      }
       mbar_wait(&s_full, it & 1);
       tc_fence_after();
-      const bool probe = g.dbg && it == 0 && threadIdx.x == 64;
+      const bool probe = g.dbg && it == 0 && threadIdx.x == 0;
       if (probe) g.dbg[blockIdx.x * 16 + 2] = gtime();
 
       float rscale = 1.f;          // mode P: 1 / softmax denominator, applied to the rows of GA in the GEMM2 epilogue
@@ -282,6 +318,10 @@ k_fused(const __grid_constant__ CUtensorMap mXh, const __grid_constant__ CUtenso
           for (int col = cb; col < ce; col += 16) {
             float v[16], rr[16];
             tmem_ld16(trow + col, v);
+            tmem_ld16(trow + colR2 + col, rr);
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[e] += rr[e];               // the two GEMM1 accumulators
+            tmem_st16(trow + col, v);                                   // region 1 <- their sum (pass C reads it)
 #pragma unroll
             for (int e = 0; e < 16; ++e) {
               float s = v[e];
@@ -303,8 +343,9 @@ k_fused(const __grid_constant__ CUtensorMap mXh, const __grid_constant__ CUtenso
             }
             if (l2) tmem_st16(trow + colR2 + col, rr);
           }
-          if (l2) tmem_wait_st();
+          tmem_wait_st();
         }
+        const bool summed = l2 || g.adversarial || g.dumpS;      // pass A ran: region 1 holds the summed accumulator
         if (g.adversarial) {
           xch[0][ehalf][row] = mxl;
           epi_bar();
@@ -319,7 +360,11 @@ k_fused(const __grid_constant__ CUtensorMap mXh, const __grid_constant__ CUtenso
         for (int col = cb; col < ce; col += 16) {
           float v[16], rr[16], hi[16], lo[16];
           tmem_ld16(trow + col, v);
-          if (l2) tmem_ld16(trow + colR2 + col, rr);
+          if (l2 || !summed) tmem_ld16(trow + colR2 + col, rr);
+          if (!summed) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[e] += rr[e];
+          }
 #pragma unroll
           for (int e = 0; e < 16; ++e) {
             float s = v[e], rinv = 1.f;
@@ -379,6 +424,9 @@ k_fused(const __grid_constant__ CUtensorMap mXh, const __grid_constant__ CUtenso
         for (int col = cb; col < ce; col += 16) {
           float v[16], hi[16], lo[16];
           tmem_ld16(trow + col, v);
+          tmem_ld16(trow + colR2 + col, hi);
+#pragma unroll
+          for (int e = 0; e < 16; ++e) v[e] += hi[e];                 // the two GEMM1 accumulators
 #pragma unroll
           for (int e = 0; e < 16; ++e) {
             float s = v[e], rinv = 1.f;
@@ -417,15 +465,42 @@ k_fused(const __grid_constant__ CUtensorMap mXh, const __grid_constant__ CUtenso
       __syncwarp();
       if (lane == 0) mbar_arrive(&v_ready);
       if (probe) g.dbg[blockIdx.x * 16 + 3] = gtime();
+      const int tr = lane >> 2, tc4 = (lane & 3) * 4;                 // transposed mapping: rows tr + 8*it, columns tc4..tc4+3
+      const int mrow0 = m0 + q * 32;                                  // first lane-side row of this warp
+      float4 bnext[12];
+      // b values of chunk `chn` in the transposed mapping: piece pc = i / 4, rows tr + 8 * (i % 4), columns tc4..tc4+3
+      auto load_b = [&](int chn) {
+        const int d0n = chn * g.Wc;
+        int nbn = (g.D - d0n + 31) >> 5;
+        if (nbn > (g.Wc >> 5)) nbn = g.Wc >> 5;
+        const int Ncn = nbn * 32;
+        const int hcn = ((Ncn >> 1) + 15) & ~15;
+        const int cbn = ehalf ? hcn : 0, cen = ehalf ? Ncn : hcn;
+        const int npn = (cen - cbn + 15) >> 4;
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+          const int pc = i >> 2, it = i & 3;
+          const int k = d0n + cbn + pc * 16 + tc4, mr = mrow0 + tr + 8 * it;
+          if (chn < nchunks && pc < npn && k < g.D && mr < g.Rx) {
+            if (g.xids) {
+              bnext[i] = ld4(brow[it] + k);
+            } else {
+              const long long so = slab_off(c, g.nblkD, g.Rx, mr, k);
+              bnext[i] = f4_add(ld4(g.Xhi + so), ld4(g.Xlo + so));
+            }
+          } else {
+            bnext[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+      };
+      if (MODE == F_N) load_b(0);                                     // chunk 0's rows: in flight during its MMAs
 
       // ---- GEMM2 epilogue, one output-column chunk at a time ----
       // TMEM hands every thread one accumulator ROW; writing rows from 32 lanes touches 32 cache lines per
       // instruction (L1 is a few KB next to the 200+ KB of shared memory, so nothing merges).  Each warp therefore
       // transposes its 32 x 16 pieces through a private shared-memory tile: afterwards a lane owns 4 consecutive
       // columns of 4 rows (lane / 4 + 8 * it) and a warp instruction covers 8 rows x 64 contiguous bytes.
-      float* stile = epi_stage + (warp - 2) * (32 * kStagePitch);
-      const int tr = lane >> 2, tc4 = (lane & 3) * 4;                 // transposed mapping: rows tr + 8*it, columns tc4..tc4+3
-      const int mrow0 = m0 + q * 32;                                  // first lane-side row of this warp
+      float* stile = epi_stage + warp * (32 * kStagePitch);
       // per-row scalars of this tile in the transposed mapping
       if (ehalf == 0) rowscal[row] = (MODE == F_P) ? rscale : colsum;
       epi_bar();
@@ -441,21 +516,14 @@ k_fused(const __grid_constant__ CUtensorMap mXh, const __grid_constant__ CUtenso
         const int hc = ((Nc >> 1) + 15) & ~15;
         const int cb2 = ehalf ? hc : 0, ce2 = ehalf ? Nc : hc;
         const int npieces = (ce2 - cb2 + 15) >> 4;
-        // mode N: the rows' own values b (for -colsum*b and the regulariser) do not depend on the accumulator:
-        // issue their loads before waiting for the tensor core, so that they overlap this chunk's MMAs
+        // mode N: the rows' own values b (for -colsum*b and the regulariser) do not depend on the accumulator.  Their
+        // loads are software-pipelined one chunk ahead (issued right after the previous chunk's accumulator was read out
+        // of TMEM), so that their latency -- microseconds while the TMA stream saturates the L2 path -- hides behind
+        // this chunk's MMAs.
         float4 bq[12];
         if (MODE == F_N && npieces <= 3) {
 #pragma unroll
-          for (int i = 0; i < 12; ++i) {
-            const int pc = i >> 2, it = i & 3;
-            const int k = d0 + cb2 + pc * 16 + tc4, mr = mrow0 + tr + 8 * it;
-            if (pc < npieces && k < g.D && mr < g.Rx) {
-              const long long so = slab_off(c, g.nblkD, g.Rx, mr, k);
-              bq[i] = f4_add(ld4(g.Xhi + so), ld4(g.Xlo + so));
-            } else {
-              bq[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-          }
+          for (int i = 0; i < 12; ++i) bq[i] = bnext[i];
         }
         if (probe && ch == 1) g.dbg[blockIdx.x * 16 + 8] = gtime();          // b loads issued (and summed)
         mbar_wait(&acc_full, nacc & 1);
@@ -469,7 +537,7 @@ k_fused(const __grid_constant__ CUtensorMap mXh, const __grid_constant__ CUtenso
           if (lane == 0) mbar_arrive(&acc_empty);
         };
         // one 32-row x 16-column piece: registers (row per lane) -> tile -> (4 columns of 4 rows per lane) -> global
-        auto process = [&](const uint32_t* r, int col, const float4* bpre) {
+        auto process_pre = [&](const uint32_t* r, int col, const int bidx) {      // rows' own values prefetched into bq[bidx..bidx+3]
           __syncwarp();                                              // the previous piece has been read out of the tile
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4)
@@ -485,7 +553,31 @@ k_fused(const __grid_constant__ CUtensorMap mXh, const __grid_constant__ CUtenso
             if (MODE == F_P) o = f4_scale(o, rsc[it]);            // 1 / softmax denominator of the row
             if (MODE == F_N) {
               float4 b;
-              if (bpre) b = bpre[it];
+              b = bq[bidx + it];
+              if (l2) o = f4_fma(b, -rsc[it], o);                   // sum_i V_ij a_i - (sum_i V_ij) b_j
+              o = f4_add(o, reg_grad4(b, g.reg_norm, g.reg_coef));
+              gsq[it] += f4_dot(o, o);
+            }
+            st4(g.out + ((long long)c * g.Rx + mr) * (long long)g.D + k, o);
+          }
+        };
+        auto process_ld = [&](const uint32_t* r, int col) {                      // wide chunks: the rows' own values are loaded here
+          __syncwarp();                                              // the previous piece has been read out of the tile
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4)
+            *reinterpret_cast<float4*>(stile + lane * kStagePitch + q4 * 4) =
+                make_float4(__uint_as_float(r[q4 * 4]), __uint_as_float(r[q4 * 4 + 1]), __uint_as_float(r[q4 * 4 + 2]), __uint_as_float(r[q4 * 4 + 3]));
+          __syncwarp();
+          const int k = d0 + col + tc4;
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int mr = mrow0 + tr + 8 * it;
+            if (k >= g.D || mr >= g.Rx) continue;
+            float4 o = *reinterpret_cast<const float4*>(stile + (tr + 8 * it) * kStagePitch + tc4);
+            if (MODE == F_P) o = f4_scale(o, rsc[it]);            // 1 / softmax denominator of the row
+            if (MODE == F_N) {
+              float4 b;
+              if (g.xids) b = ld4(brow[it] + k);
               else { const long long so = slab_off(c, g.nblkD, g.Rx, mr, k); b = f4_add(ld4(g.Xhi + so), ld4(g.Xlo + so)); }
               if (l2) o = f4_fma(b, -rsc[it], o);                   // sum_i V_ij a_i - (sum_i V_ij) b_j
               o = f4_add(o, reg_grad4(b, g.reg_norm, g.reg_coef));
@@ -502,10 +594,11 @@ k_fused(const __grid_constant__ CUtensorMap mXh, const __grid_constant__ CUtenso
             if (pc < npieces) tmem_ld16_nowait(trow + colAcc + cb2 + pc * 16, r + pc * 16);
           tmem_wait_ld();
           release();
+          if (MODE == F_N) load_b(ch + 1);                            // next chunk's rows, one chunk ahead
           if (probe && ch == 1) g.dbg[blockIdx.x * 16 + 10] = gtime();       // TMEM read, accumulator released
 #pragma unroll
           for (int pc = 0; pc < 3; ++pc)
-            if (pc < npieces) process(r + pc * 16, cb2 + pc * 16, bq + pc * 4);
+            if (pc < npieces) process_pre(r + pc * 16, cb2 + pc * 16, pc * 4);
           if (probe && ch == 1) g.dbg[blockIdx.x * 16 + 11] = gtime();       // chunk 1 stored
           if (probe && ch == 0) g.dbg[blockIdx.x * 16 + 7] = gtime();        // chunk 0 stored
         } else {
@@ -514,7 +607,7 @@ k_fused(const __grid_constant__ CUtensorMap mXh, const __grid_constant__ CUtenso
             tmem_ld16_nowait(trow + colAcc + cb2 + pc * 16, r);
             tmem_wait_ld();
             if (pc == npieces - 1) release();
-            process(r, cb2 + pc * 16, nullptr);
+            process_ld(r, cb2 + pc * 16);
           }
           if (npieces == 0) release();
         }
@@ -536,7 +629,7 @@ k_fused(const __grid_constant__ CUtensorMap mXh, const __grid_constant__ CUtenso
     tc_fence_before();
   }
   __syncthreads();
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
   }
@@ -557,7 +650,7 @@ bool fused_supported(const StepParams& p) {
 
 // mode 0 (P): S = A.Bn^T -> loss, coefficients -> GA;  mode 1 (N): S^T -> coefficients -> G_neg (+ mean square)
 int fused_launch(const LaunchCtx& c, const StepParams& p, const StepWs& w, int mode, const float* wt, float* dumpS,
-                 float* dumpV, char* err, size_t errlen) {
+                 float* dumpV, const TableView* ent, const long long* neg_ids, char* err, size_t errlen) {
   FusedArgs g{};
   g.model = p.model; g.adversarial = p.adversarial;
   g.gamma = p.gamma; g.Tl2e = p.adv_temperature * kLog2e; g.inv2B = 0.5f / (float)p.B; g.uni = 1.f / (float)p.Ns;
@@ -583,6 +676,9 @@ int fused_launch(const LaunchCtx& c, const StepParams& p, const StepWs& w, int m
   g.dumpS = P ? dumpS : nullptr; g.dumpV = dumpV;
   g.cstat_m = w.stat_m; g.cstat_k = w.stat_k;
   g.Xhi = Xh; g.Xlo = Xl;
+  // one GPU: the negatives' own rows come straight from the table (exact fp32, one load); sharded tables would make
+  // that a remote read per row, so they use the local hi + lo slabs
+  if (!P && ent && ent->n_shards == 1 && neg_ids) { g.xids = neg_ids; g.xtab = *ent; }
   g.gsn = w.gsn;
   g.out = P ? w.GA : w.Bn;
   const long long rowsX = (long long)p.C * g.Rx * g.nblkD, rowsY = (long long)p.C * g.Ry * g.nblkD;
@@ -605,6 +701,8 @@ int fused_launch(const LaunchCtx& c, const StepParams& p, const StepWs& w, int m
   int grid = p.C * mtiles;
   if (grid > c.num_sms) grid = c.num_sms;
   static const bool timing = getenv("KGE_B200_FUSED_TIMING") != nullptr;
+  static const bool halfload = getenv("KGE_B200_FUSED_HALFLOAD") != nullptr;
+  g.exp_halfload = halfload ? 1 : 0;
   unsigned long long* dbg = nullptr;
   if (timing) { cudaMalloc(&dbg, (size_t)grid * 16 * sizeof(unsigned long long)); cudaMemset(dbg, 0, (size_t)grid * 128); g.dbg = dbg; }
   if (P) KGE_LAUNCH_NAMED(c, "k_fused<P: S=A.Bn^T, loss, GA=V.Bn>", k_fused<F_P>, grid, kThreadsF, smem, mXh, mXl, mYh1, mYl1, mYh2, mYl2, g);

@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(kRowBlock) k_prep(StepParams p, TableView ent,
 template <int KIT>
 __global__ void __launch_bounds__(kRowBlock) k_gather_nodes(StepParams p, TableView ent, BatchView b, StepWs w) {
   const long long u = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-  if (u >= p.U) return;
+  if (u >= node_count(p)) return;
   const int lane = threadIdx.x & 31;
   const bool reg_on = (p.reg_coef > 0.f && p.reg_norm > 0);
   const float* src = row_ptr(ent, b.node_ids[u]);
@@ -539,6 +539,7 @@ __device__ void reduce_log_part(const StepParams& p, const StepWs& w, long long 
 // the CTA that finishes last (ticket counter) adds the partials in index order => deterministic.
 __global__ void __launch_bounds__(256) k_reduce_log(StepParams p, StepWs w, long long nreg, const float* __restrict__ wbar,
                                                      float* __restrict__ log4) {
+  if (nreg > 0 && p.U_dev) nreg = p.B + p.Nn + *p.U_dev;
   reduce_log_part(p, w, nreg, wbar, log4, blockIdx.x, gridDim.x);
 }
 
@@ -775,50 +776,6 @@ __device__ __forceinline__ void upd_node(const StepParams& p, const TableView& e
   const bool sharded = ent.n_shards > 1;
   const bool reg_on = (p.reg_coef > 0.f && p.reg_norm > 0);
   float* st = state_ptr(ent, id);
-  if (nv <= 4 * kWarp) {
-    // row in registers (D <= 512): one read of NG and of the traced copy, no second pass through memory
-    float4 x[4], gq[4];
-    float gs = 0.f, reg = 0.f;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int v = lane + kWarp * q;
-      x[q] = (v < nv) ? ld4(nc + 4 * v) : z;
-      gq[q] = (v < nv) ? ld4(ng + 4 * v) : z;
-    }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int v = lane + kWarp * q;
-      if (v < nv) {
-        gq[q] = f4_add(gq[q], reg_grad4(x[q], p.reg_norm, p.reg_coef));
-        gs += f4_dot(gq[q], gq[q]);
-        if (reg_on && !p.use_nc) reg += abs_pow4_sum(x[q], p.reg_norm);
-      }
-    }
-    gs = warp_sum(gs) / (float)p.D;
-    if (!p.use_nc) {            // no k_gather_nodes ran: this node's share of the regulariser is produced here
-      reg = warp_sum(reg);
-      if (lane == 0) w.regp[p.B + p.Nn + u] = reg;
-    }
-    float s_new = 0.f;
-    if (lane == 0) {
-      if (sharded) s_new = atomicAdd_system(st, gs) + gs;   // remote-safe: other GPUs may add to the same state
-      else { s_new = *st + gs; *st = s_new; }
-    }
-    s_new = __shfl_sync(0xffffffffu, s_new, 0);
-    const float stdv = sqrtf(s_new) + 1e-10f;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int v = lane + kWarp * q;
-      if (v < nv) {
-        const float4 g = gq[q];
-        float4 tmp = make_float4((-p.lr * g.x) / stdv, (-p.lr * g.y) / stdv, (-p.lr * g.z) / stdv, (-p.lr * g.w) / stdv);
-        if (sharded) red_add4_sys(row + 4 * v, tmp);
-        else st4(row + 4 * v, f4_add(x[q], tmp));
-        st4(ng + 4 * v, z);
-      }
-    }
-    return;
-  }
   // pass 1: g = NG + reg'(x), mean(g^2)
   float gs = 0.f, reg = 0.f;
   for (int v = lane; v < nv; v += kWarp) {
@@ -896,9 +853,10 @@ __global__ void __launch_bounds__(kRowBlock) k_update(UpdArgs a) {
   for (int phase = a.phase_lo; phase <= a.phase_hi; ++phase) {
     if (phase == 1) {
       const long long nrel = (p.rel_dense && !p.rel_deferred) ? a.rel.num_rows : 0;
-      for (long long j = warp0; j < p.U + nrel; j += nwarps) {
-        if (j < p.U) upd_node(p, a.ent, a.b, w, j, lane);
-        else upd_rel_dense(a.rel, w.rg, w.rgs, j - p.U, p.lr, lane);
+      const long long U = node_count(p);
+      for (long long j = warp0; j < U + nrel; j += nwarps) {
+        if (j < U) upd_node(p, a.ent, a.b, w, j, lane);
+        else upd_rel_dense(a.rel, w.rg, w.rgs, j - U, p.lr, lane);
       }
     } else if (phase == 2) {
       if (p.fused) {
@@ -928,7 +886,7 @@ __global__ void __launch_bounds__(kRowBlock) k_update(UpdArgs a) {
         const int nb = gridDim.x < 64 ? gridDim.x : 64;
         const bool reg_on = (p.reg_coef > 0.f && p.reg_norm > 0);
         if ((int)blockIdx.x < nb)
-          reduce_log_part(p, w, reg_on ? (p.B + p.Nn + p.U) : 0, a.wt ? w.wbar : nullptr, a.log4, blockIdx.x, nb);
+          reduce_log_part(p, w, reg_on ? (p.B + p.Nn + node_count(p)) : 0, a.wt ? w.wbar : nullptr, a.log4, blockIdx.x, nb);
       }
     }
     if (phase < a.phase_hi) grid_barrier(w.sync_ctr + (phase - 1));
@@ -1064,7 +1022,7 @@ void launch_adagrad(const LaunchCtx& c, const TableView& t, const long long* idx
 __global__ void __launch_bounds__(kRowBlock) k_node_grad_reg(StepParams p, TableView ent, BatchView b, StepWs w,
                                                               float* __restrict__ out) {
   const long long u = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-  if (u >= p.U) return;
+  if (u >= node_count(p)) return;
   const int lane = threadIdx.x & 31;
   const float* row = node_row(p, ent, b, w, u);
   for (int v = lane; v < (p.D >> 2); v += kWarp)

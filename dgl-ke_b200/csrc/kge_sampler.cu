@@ -24,25 +24,6 @@ __host__ __device__ __forceinline__ unsigned long long mix64(unsigned long long 
   return z ^ (z >> 31);
 }
 
-struct SamplerParams {
-  const long long *heads, *rels, *tails;   // the partition's edges (device)
-  long long n_edges, n_entities;
-  long long B, Nn;
-  unsigned long long seed;
-  int half_bits;                            // Feistel half width: 2^(2*half_bits) >= n_edges
-  // outputs
-  long long *o_head, *o_rel, *o_tail;       // [B] global ids of the sampled positives
-  long long *o_neg;                         // [Nn]
-  long long *o_nodes, *o_hl, *o_tl;         // [2B], [B], [B]
-  long long* o_n_nodes;                     // [1]
-  // hash table of the batch's distinct entity ids
-  unsigned long long* tkey;                 // [H], ~0 = empty
-  int* tpos;                                // [H] smallest position of the key in [heads | tails]
-  int* tloc;                                // [H] local id of the key
-  int hmask;                                // H - 1
-  int* flags;                               // [2B] 1 = first occurrence
-};
-
 __device__ __forceinline__ unsigned long long feistel_perm(unsigned long long x, unsigned long long n, int hb,
                                                            unsigned long long key) {
   const unsigned long long mask = (1ull << hb) - 1ull;

@@ -20,7 +20,7 @@ EXPORTS = ["kge_abi_version", "kge_last_error", "kge_create", "kge_destroy", "kg
            "kge_step_fused", "kge_step_fused_begin", "kge_step_fused_end", "kge_step_fused_host", "kge_sync", "kge_debug_read", "kge_launch_count",
            "kge_set_engine", "kge_set_fused", "kge_debug_set_dump", "kge_profile_enable", "kge_profile_read", "kge_set_relation_mode", "kge_set_relation_buffers",
            "kge_rel_grad_dense", "kge_rel_apply_dense", "kge_device_alloc", "kge_device_free", "kge_ipc_export",
-           "kge_ipc_open"]
+           "kge_ipc_open", "kge_sampler_create", "kge_sampler_destroy", "kge_sampler_sample"]
 
 
 class KgeError(RuntimeError):
@@ -48,7 +48,7 @@ class StepCfg(C.Structure):
 class Batch(C.Structure):
     _fields_ = [("node_ids", C.c_void_p), ("n_nodes", C.c_int64), ("head_local", C.c_void_p),
                 ("tail_local", C.c_void_p), ("rel_ids", C.c_void_p), ("neg_ids", C.c_void_p),
-                ("edge_weight", C.c_void_p)]
+                ("edge_weight", C.c_void_p), ("n_nodes_dev", C.c_void_p)]
 
 
 _lib = None
@@ -97,6 +97,9 @@ def load_library():
     lib.kge_device_free.argtypes = [vp, vp]
     lib.kge_ipc_export.argtypes = [vp, vp, C.c_char_p, P(i64)]
     lib.kge_ipc_open.argtypes = [vp, C.c_char_p, i64, P(vp)]
+    lib.kge_sampler_create.argtypes = [vp, vp, vp, vp, i64, i64, i64, i32, C.c_uint64, P(vp)]
+    lib.kge_sampler_destroy.argtypes = [vp]
+    lib.kge_sampler_sample.argtypes = [vp, i64, P(Batch), P(i32), vp]
     missing = [name for name in EXPORTS if not hasattr(lib, name)]
     if missing:
         raise KgeError("libkge_b200.so at %s lacks symbols %s (stale build?)" % (LIB_PATH, missing))
@@ -216,5 +219,5 @@ def make_batch(node_ids, head_local, tail_local, rel_ids, neg_ids, edge_weight=N
         assert t.dtype == torch.int64 and t.is_contiguous()
     b = Batch(node_ids.data_ptr(), node_ids.numel(), head_local.data_ptr(), tail_local.data_ptr(),
               rel_ids.data_ptr(), neg_ids.data_ptr(),
-              edge_weight.data_ptr() if edge_weight is not None else None)
+              edge_weight.data_ptr() if edge_weight is not None else None, None)
     return b, (node_ids, head_local, tail_local, rel_ids, neg_ids, edge_weight)

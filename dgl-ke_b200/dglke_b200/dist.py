@@ -110,14 +110,15 @@ class ShardedTrainer:
         dist.barrier(group=group)
 
     # -- one training step: forward/backward, entity Adagrad over NVLink, relation all-reduce + apply
-    def step(self, node_ids, head_local, tail_local, rel_ids, neg_ids, chunk_size, neg_sample_size, neg_head,
-             edge_weight=None, log4=None, sync_between=False):
+    def step(self, node_ids, head_local=None, tail_local=None, rel_ids=None, neg_ids=None, chunk_size=None,
+             neg_sample_size=None, neg_head=None, edge_weight=None, log4=None, sync_between=False):
         """sync_between (tests): a cross-rank barrier between the gradient half and the update half, so that every
         rank's gradients come from the same table snapshot."""
         lib, h = self.h.lib, self.h
         # gather (peer loads) .. k_chain: per-relation gradient sums land in rbuf
-        self.eng.step_begin(node_ids, head_local, tail_local, rel_ids, neg_ids, chunk_size, neg_sample_size, neg_head,
-                            edge_weight)
+        # (node_ids may be a sampler.DeviceBatch: the indices then never visit the host)
+        self.eng.step_begin(node_ids, head_local, tail_local, rel_ids, neg_ids, chunk_size=chunk_size,
+                            neg_sample_size=neg_sample_size, neg_head=neg_head, edge_weight=edge_weight)
         # the relation all-reduce (NCCL stream) overlaps the entity Adagrad kernel, which does not touch rbuf
         if sync_between:
             self.barrier()

@@ -109,11 +109,25 @@ class StepEngine:
                                            out.data_ptr(), self.h.stream()))
         return out
 
-    def step_begin(self, node_ids, head_local, tail_local, rel_ids, neg_ids, chunk_size, neg_sample_size, neg_head,
-                   edge_weight=None):
-        """first half of step(): everything up to the gradients (kge_step_fused_begin)"""
-        cfg = self.cfg(head_local.numel(), chunk_size, neg_sample_size, neg_head)
-        b, keep = _lib.make_batch(node_ids, head_local, tail_local, rel_ids, neg_ids, edge_weight)
+    def step_sampled(self, batch, chunk_size, neg_sample_size, log4=None):
+        """fused step on a DeviceBatch (dglke_b200.sampler.DeviceSampler): the indices never leave the GPU"""
+        cfg = self.cfg(batch.B, chunk_size, neg_sample_size, batch.neg_head)
+        out = self.log4 if log4 is None else log4
+        _lib.check(self.lib.kge_step_fused(self.h.raw, C.byref(cfg), self.ent.ref(), self.rel.ref(), C.byref(batch.c),
+                                           out.data_ptr(), self.h.stream()))
+        return out
+
+    def step_begin(self, node_ids, head_local=None, tail_local=None, rel_ids=None, neg_ids=None, chunk_size=None,
+                   neg_sample_size=None, neg_head=None, edge_weight=None):
+        """first half of step(): everything up to the gradients (kge_step_fused_begin).  `node_ids` may be a
+        sampler.DeviceBatch (then only chunk_size / neg_sample_size are read from the other arguments)."""
+        if hasattr(node_ids, "c") and hasattr(node_ids, "neg_head"):        # DeviceBatch
+            batch = node_ids
+            cfg = self.cfg(batch.B, chunk_size, neg_sample_size, batch.neg_head)
+            b, keep = batch.c, batch
+        else:
+            cfg = self.cfg(head_local.numel(), chunk_size, neg_sample_size, neg_head)
+            b, keep = _lib.make_batch(node_ids, head_local, tail_local, rel_ids, neg_ids, edge_weight)
         _lib.check(self.lib.kge_step_fused_begin(self.h.raw, C.byref(cfg), self.ent.ref(), self.rel.ref(), C.byref(b),
                                                  self.h.stream()))
         self._last = (cfg, b, keep)

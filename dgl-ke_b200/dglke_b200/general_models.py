@@ -143,9 +143,20 @@ class KEModel(object):
     # -- the training hot path ----------------------------------------------------------------------
     def forward(self, pos_g, neg_g, gpu_id=-1):
         """gather -> positive + chunked negative scores -> loss -> every gradient, in one stream-ordered
-        sequence of CUDA kernels (kge_forward_backward).  Returns (loss, log) like the reference."""
+        sequence of CUDA kernels (kge_forward_backward).  Returns (loss, log) like the reference.
+
+        A batch that comes from the device sampler (pos_g.device_batch, dglke_b200.sampler) takes the fused
+        schedule: forward = kge_step_fused_begin, update = kge_step_fused_end, 5 kernels per step; the log scalars are
+        produced by the update kernel and read lazily."""
         if getattr(self.args, "neg_deg_sample", False):
             raise NotImplementedError("--neg_deg_sample is not accelerated yet (SURVEY 8f-2)")
+        batch = getattr(pos_g, "device_batch", None)
+        if batch is not None and not self.has_edge_importance:
+            eng = self.engine()
+            eng.step_begin(batch, chunk_size=neg_g.chunk_size, neg_sample_size=neg_g.neg_sample_size)
+            self._fused_pending = True
+            with_reg = self.hyper.reg_coef > 0.0 and self.hyper.reg_norm > 0
+            return FusedLoss(eng.log4, with_reg, lazy=True), LazyLog(eng.log4, has_reg=with_reg, lazy=True)
         dev = self.device
         mv = lambda t: t if t.device == dev else t.to(dev, non_blocking=True)
         head_local, tail_local = pos_g.all_edges(order="eid")
@@ -158,7 +169,11 @@ class KEModel(object):
         return FusedLoss(log4, with_reg), LazyLog(log4, has_reg=with_reg)
 
     def update(self, gpu_id=-1):
-        self.engine().update()
+        if getattr(self, "_fused_pending", False):
+            self.engine().step_end()
+            self._fused_pending = False
+        else:
+            self.engine().update()
         self.score_func.update(gpu_id)
 
     # -- reference API kept for train loops written against it -----------------------------------------

@@ -14,9 +14,12 @@ class LazyLog(dict):
     only when somebody looks (the reference pays 3-4 .item() syncs per step, tensor_models.py:55)."""
     KEYS = ("pos_loss", "neg_loss", "loss", "regularization")
 
-    def __init__(self, log4, has_reg=True):
+    def __init__(self, log4, has_reg=True, lazy=False):
         super().__init__()
-        self._log4 = log4.clone()
+        # lazy: the scalars are written by a kernel that has not been enqueued yet (fused step: the update kernel
+        # reduces them); an event recorded right after that kernel would be ideal, reading on first use after the
+        # caller's update() is what the train loop does
+        self._log4 = log4 if lazy else log4.clone()
         self._keys = self.KEYS if has_reg else self.KEYS[:3]
         self._vals = None
 
@@ -53,7 +56,7 @@ class FusedLoss:
     """What KEModel.forward returns as `loss`: the fused step has already produced every gradient,
     so backward() has nothing left to do (train_pytorch.py:145 keeps working unchanged)."""
 
-    def __init__(self, log4, with_reg):
+    def __init__(self, log4, with_reg, lazy=False):
         self._log4, self._with_reg = log4, with_reg
 
     def backward(self):

@@ -37,7 +37,7 @@ extern "C" {
 #define KGE_API
 #endif
 
-#define KGE_ABI_VERSION 1
+#define KGE_ABI_VERSION 2
 #define KGE_MAX_SHARDS 8
 
 typedef enum {
@@ -114,6 +114,8 @@ typedef struct {
   const int64_t* rel_ids;
   const int64_t* neg_ids;
   const float* edge_weight;
+  const int64_t* n_nodes_dev;  /* device-side node count (kge_sampler_sample): used when n_nodes < 0; node_ids then
+                                  has room for 2*batch entries */
 } kge_batch_t;
 
 typedef struct kge_context* kge_handle_t;
@@ -190,6 +192,22 @@ KGE_API int kge_step_fused_host(kge_handle_t h, const kge_step_cfg_t* cfg, const
                         const kge_table_t* rel, const kge_batch_t* batch_host, float* log4_host,
                         void* stream);
 KGE_API int kge_sync(kge_handle_t h, void* stream);
+
+/* --- device-side sampler (replaces DGL's EdgeSampler on the training path: dataloader/sampler.py:376-419 create_sampler,
+ *     :459-512 chunk layout, :823-876 tail/head alternation) -------------------------------------------------------------
+ * heads/rels/tails: the (partition's) edge list in device memory, owned by the caller.  Step k takes the k-th batch of
+ * the current epoch's random permutation (a fresh one per epoch, ragged tail dropped), draws num_chunks * neg_sample_size
+ * corrupting entities uniformly with replacement, and builds the positive graph's node list (distinct endpoints in order of
+ * first appearance) + local endpoints -- all in device memory, counter based (seed, step): dglke_b200/sampler.py holds
+ * the same integer arithmetic in numpy and produces bit-identical arrays.  Even steps corrupt tails, odd steps heads. */
+typedef struct kge_sampler* kge_sampler_t;
+KGE_API int kge_sampler_create(kge_handle_t h, const int64_t* heads, const int64_t* rels, const int64_t* tails,
+                       int64_t n_edges, int64_t n_entities, int64_t batch, int32_t neg_sample_size, uint64_t seed,
+                       kge_sampler_t* out);
+KGE_API int kge_sampler_destroy(kge_sampler_t s);
+/* Fills *batch_out with device pointers into the sampler's storage (two buffers, alternating with `step`; valid until the
+ * next-but-one call), n_nodes = -1 and n_nodes_dev set; *neg_head_out = step & 1. */
+KGE_API int kge_sampler_sample(kge_sampler_t s, int64_t step, kge_batch_t* batch_out, int32_t* neg_head_out, void* stream);
 
 /* --- introspection (parity tests read the traced gradients the way the reference exposes
  *     `data.grad` of each trace entry, tensor_models.py:318) ---------------------------------- */

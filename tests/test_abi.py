@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), "libkge_b200.so does not export %s" % n
     assert sorted(names) == sorted(_lib.EXPORTS)
-    assert lib.kge_abi_version() == 1
+    assert lib.kge_abi_version() == 2
 
 
 def test_struct_layouts_match_header():
@@ -31,7 +31,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(_lib.Shard) == 40
     assert C.sizeof(_lib.Table) == 32
     assert C.sizeof(_lib.StepCfg) == 64
-    assert C.sizeof(_lib.Batch) == 56
+    assert C.sizeof(_lib.Batch) == 64
     assert _lib.StepCfg.batch.offset == 48 and _lib.StepCfg.neg_sample_size.offset == 60
 
 
