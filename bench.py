@@ -36,6 +36,9 @@ WORKLOADS = {
                          "ComplEx Freebase-shape 86M entities d=400 neg=200 -adv (BASELINE configs[3])"),
     "synth_distmult": ("DistMult", 100000000, 10000, 512, 143.0, 0.08, 2e-6, 1024, False, 4096,
                        "DistMult synthetic 100M entities d=512 neg=1024 -adv (BASELINE configs[4])"),
+    "freebase_transe_l2": ("TransE_l2", 86054151, 14824, 400, 19.9, 0.25, 1e-9, 200, False, 14800,
+                           "TransE_l2 d=400 neg=200 -adv on the Freebase-shaped table (86 M entities, 137.7 GB; 14 824 relations): "
+                           "north_star's multi-GPU scaling shape, HBM-resident"),
     "big_transe_l2": ("TransE_l2", 20000000, 1345, 400, 19.9, 0.25, 1e-9, 200, False, 14800,
                       "TransE_l2 d=400 neg=200 -adv on a 20M-entity (32 GB) table: HBM-resident variant of configs[1]"),
 }
@@ -53,7 +56,10 @@ def parse():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="fb15k_transe_l2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS),
+                    help="default: fb15k_transe_l2 (BASELINE configs[1]) on one GPU, freebase_transe_l2 (the 86 M-entity "
+                         "HBM-resident table north_star's scaling target names) on several; the other one is measured beside it")
+    ap.add_argument("--no-beside", action="store_true", help="skip the second (beside) workload of a default run")
     ap.add_argument("--batch", type=int, default=0, help="edges per step per GPU (0 = workload default)")
     ap.add_argument("--n-ent", type=int, default=0, help="override the entity count (capacity experiments)")
     ap.add_argument("--engine", type=int, default=-1, help="-1 library default, 0 fp32 tiles, 1 tcgen05")
@@ -76,7 +82,7 @@ def run_reference(args):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import cpu_bench
     import kge_oracle as ko
-    model, n_ent, n_rel, hidden, gamma, lr, rc, neg, de, _, desc = WORKLOADS[args.workload]
+    model, n_ent, n_rel, hidden, gamma, lr, rc, neg, de, _, desc = WORKLOADS[args.workload or "fb15k_transe_l2"]
     if args.n_ent:
         n_ent = args.n_ent
     # host RAM bound for the huge shapes: a stated scaled-down entity count
@@ -170,7 +176,7 @@ class ClockSampler:
 
 def cpu_baseline_subprocess(args):
     """Times the CPU oracle on a bounded sample in a fresh process (before CUDA is initialised here)."""
-    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", args.workload,
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", args.workload or "fb15k_transe_l2",
            "--steps", "8", "--warmup", "2", "--cpu-procs", str(args.cpu_procs), "--cpu-impl", args.cpu_impl]
     if args.n_ent:
         cmd += ["--n-ent", str(args.n_ent)]
@@ -209,8 +215,42 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    default_run = args.workload is None
+    primary = args.workload or ("fb15k_transe_l2" if world == 1 else "freebase_transe_l2")
+    beside = None
+    if default_run and not args.no_beside and not args.batch and not args.n_ent:
+        beside = "freebase_transe_l2" if world == 1 else "fb15k_transe_l2"
 
-    model, n_ent, n_rel, hidden, gamma, lr, rc, neg, de, bdef, desc = WORKLOADS[args.workload]
+    line = measure(args, primary, rank, world, local_rank, dev, cpu_base, max(1, args.steps), True)
+    if beside is not None:
+        torch.cuda.empty_cache()
+        other = measure(args, beside, rank, world, local_rank, dev, None, min(max(1, args.steps), 20), False)
+        if rank == 0:
+            line["beside"] = {k: other[k] for k in ("value", "unit", "ms_per_step", "config", "e2e", "roofline")}
+            line["beside"]["note"] = ("the same step on %s, measured in the same process: value(N) of the Freebase-shaped "
+                                      "runs against the Freebase-shaped value at N=1 is the like-for-like scaling ratio"
+                                      % WORKLOADS[beside][10])
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    sys.stdout.flush()
+    if world > 1:
+        # leave without tearing down NCCL / captured graphs / IPC mappings: destroying a process group whose
+        # collectives live inside CUDA graphs has been seen to hang at exit
+        os._exit(0)
+
+
+def measure(args, workload, rank, world, local_rank, dev, cpu_base, K_steps, full):
+    """One workload: device-resident throughput (CUDA graph per step), end-to-end throughput, per-kernel times."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from dglke_b200.engine import StepEngine, DeviceTable, Hyper
+    from dglke_b200.graph import SyntheticSampler
+
+    model, n_ent, n_rel, hidden, gamma, lr, rc, neg, de, bdef, desc = WORKLOADS[workload]
     if args.n_ent:
         n_ent = args.n_ent
     B = (args.batch or bdef) // neg * neg
@@ -243,12 +283,16 @@ def run_ours(args):
         hb = [pg.ndata["id"], pg.all_edges()[0], pg.all_edges()[1], pg.edata["id"], ng.ndata["id"]]
         hb = [t.pin_memory() for t in hb]
         host.append((hb, ng.neg_head))
-        devb.append(([t.to(dev) for t in hb], ng.neg_head))
+        db = [t.to(dev) for t in hb]
+        db += [db[0][db[1]].contiguous(), db[0][db[2]].contiguous()]      # the edges' global endpoint ids (a sampler has them)
+        devb.append((db, ng.neg_head))
     Cs = sampler.chunk_size
     h2d = sum(t.numel() * 8 for t in host[0][0])
 
     def step_dev(k):
         b, nh = devb[k % NB]
+        if world == 1:
+            return eng.step(b[0], b[1], b[2], b[3], b[4], Cs, neg, nh, head_ids=b[5], tail_ids=b[6])
         return eng.step(b[0], b[1], b[2], b[3], b[4], Cs, neg, nh)
 
     def step_host(k):
@@ -267,7 +311,7 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    W, K = max(3, args.warmup), max(1, args.steps)
+    W, K = max(3, args.warmup), K_steps
     for k in range(W):
         step_dev(k)
     torch.cuda.synchronize()
@@ -342,14 +386,12 @@ def run_ours(args):
     kern_ms = sum(prof.values())
     dominant = max(prof.items(), key=lambda kv: kv[1]) if prof else ("", 0.0)
 
+    del graphs
     if world > 1:
         dist.barrier()
         torch.cuda.synchronize()
     if rank != 0:
-        # leave without tearing down NCCL / captured graphs / IPC mappings: destroying a process group whose
-        # collectives live inside CUDA graphs has been seen to hang at exit
-        sys.stdout.flush()
-        os._exit(0)
+        return None
 
     peaks = {}
     try:
@@ -366,7 +408,7 @@ def run_ours(args):
     achieved = B * bpe / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else 0.0
     # DRAM traffic of one step from the committed ncu --set full capture -- only when that capture was taken on exactly
     # this workload / batch / schedule on one GPU (profiles/summarize.py writes the key); null otherwise
-    traffic, traffic_key = None, "%s|B=%d|launches=%d" % (args.workload, B, per_step_launches)
+    traffic, traffic_key = None, "%s|B=%d|launches=%d" % (workload, B, per_step_launches)
     if world == 1:
         try:
             traffic = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json"))).get(traffic_key)
@@ -395,10 +437,7 @@ def run_ours(args):
         "cpu_baseline": cpu_base,
         "clocks": clocks,
     }
-    print(json.dumps(line), flush=True)
-    if world > 1:
-        sys.stdout.flush()
-        os._exit(0)
+    return line
 
 
 if __name__ == "__main__":

@@ -153,8 +153,7 @@ int make_params(const kge_step_cfg_t* cfg, long long n_nodes, StepParams* p, boo
   p->U = n_nodes >= 0 ? n_nodes : 2 * p->B;      // capacity when only the device knows the count
   p->U_dev = nullptr;
   p->rel_deferred = 0; p->rel_dense = 0; p->use_nc = 1; p->fused = 0;
-  static const int split_trunc = getenv("KGE_B200_SPLIT_TRUNC") ? atoi(getenv("KGE_B200_SPLIT_TRUNC")) : 0;
-  p->split_trunc = split_trunc;
+
   (void)need_tables;
   return KGE_OK;
 }
@@ -279,7 +278,8 @@ int check_batch(const kge_batch_t* b, const StepParams& p) {
 
 BatchView bview(const kge_batch_t* b) {
   return BatchView{(const long long*)b->node_ids, (const long long*)b->head_local, (const long long*)b->tail_local,
-                   (const long long*)b->rel_ids, (const long long*)b->neg_ids, b->edge_weight};
+                   (const long long*)b->rel_ids, (const long long*)b->neg_ids, b->edge_weight,
+                   (const long long*)b->head_ids, (const long long*)b->tail_ids};
 }
 
 }  // namespace
@@ -839,6 +839,7 @@ KGE_API int kge_sampler_sample(kge_sampler_t s, int64_t step, kge_batch_t* out, 
   out->node_ids = (const int64_t*)p.o_nodes; out->n_nodes = -1; out->n_nodes_dev = (const int64_t*)p.o_n_nodes;
   out->head_local = (const int64_t*)p.o_hl; out->tail_local = (const int64_t*)p.o_tl;
   out->rel_ids = (const int64_t*)p.o_rel; out->neg_ids = (const int64_t*)p.o_neg; out->edge_weight = nullptr;
+  out->head_ids = (const int64_t*)p.o_head; out->tail_ids = (const int64_t*)p.o_tail;
   if (neg_head_out) *neg_head_out = (int32_t)(step & 1);
   return KGE_OK;
 }

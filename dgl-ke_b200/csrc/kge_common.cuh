@@ -53,7 +53,6 @@ struct StepParams {
   int rel_dense;     // 1: k_chain sums relation gradients per relation into ws.rg / ws.rgs (fused single-GPU step)
   int use_nc;        // 1: head/tail rows are read from the gathered copy NC (3-call API, sharded tables); 0: from the table
   int fused;         // 1: contraction by the fused tcgen05 kernel (kge_fused.cu): operands exist only as TF32 hi/lo slabs
-  int split_trunc;   // experiment: operands' hi part is the raw fp32 value (see RowOut::trunc)
 };
 
 // Device workspace of one step (all pointers into the handle's arena).
@@ -101,6 +100,8 @@ struct BatchView {
   const long long* rel_ids;
   const long long* neg_ids;
   const float* edge_weight;
+  const long long* head_ids;    // optional global ids of the edges' endpoints
+  const long long* tail_ids;
 };
 
 __device__ __forceinline__ long long node_count(const StepParams& p) { return p.U_dev ? *p.U_dev : p.U; }
@@ -110,6 +111,17 @@ __device__ __forceinline__ long long node_count(const StepParams& p) { return p.
 __device__ __forceinline__ const float* node_row(const StepParams& p, const TableView& ent, const BatchView& b,
                                                  const StepWs& w, long long loc) {
   return p.use_nc ? (w.NC + loc * (long long)p.D) : row_ptr(ent, b.node_ids[loc]);
+}
+// head / tail row of edge i: with the edges' global ids at hand the table row needs one index load instead of two
+__device__ __forceinline__ const float* head_row(const StepParams& p, const TableView& ent, const BatchView& b,
+                                                 const StepWs& w, long long i) {
+  if (!p.use_nc && b.head_ids) return row_ptr(ent, b.head_ids[i]);
+  return node_row(p, ent, b, w, b.head_local[i]);
+}
+__device__ __forceinline__ const float* tail_row(const StepParams& p, const TableView& ent, const BatchView& b,
+                                                 const StepWs& w, long long i) {
+  if (!p.use_nc && b.tail_ids) return row_ptr(ent, b.tail_ids[i]);
+  return node_row(p, ent, b, w, b.tail_local[i]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -197,29 +209,11 @@ struct RowOut {
   float* lo;
   long long chunk;
   int nblk, R, row;
-  int trunc;         // experiment (KGE_B200_SPLIT_TRUNC): hi = the raw fp32 value (the tensor core drops the low 13
-                     // mantissa bits itself), lo = rna_tf32(x - trunc_tf32(x))
 };
-// experiment: which rounding does the tensor core apply to a raw fp32 operand of kind::tf32?
-//   mode 1: truncation, 2: round to nearest, ties away (cvt.rna), 3: round to nearest even (cvt.rn)
-__device__ __forceinline__ void split_tf32_trunc(float x, float& hi, float& lo, int mode) {
-  float ht;
-  if (mode == 1) ht = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
-  else if (mode == 2) { uint32_t b; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(b) : "f"(x)); ht = __uint_as_float(b); }
-  else { uint32_t b; asm("cvt.rn.tf32.f32 %0, %1;" : "=r"(b) : "f"(x)); ht = __uint_as_float(b); }
-  uint32_t lb;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(x - ht));
-  hi = x;
-  lo = __uint_as_float(lb);
-}
 __device__ __forceinline__ void row_store4(const RowOut& o, int col, float4 v) {
   if (o.f32) *reinterpret_cast<float4*>(o.f32 + col) = v;
   if (o.hi) {
     float4 h, l;
-    if (o.trunc) {
-      split_tf32_trunc(v.x, h.x, l.x, o.trunc); split_tf32_trunc(v.y, h.y, l.y, o.trunc);
-      split_tf32_trunc(v.z, h.z, l.z, o.trunc); split_tf32_trunc(v.w, h.w, l.w, o.trunc);
-    } else
     split_tf32_4(v, h, l);
     const long long off = slab_off(o.chunk, o.nblk, o.R, o.row, col);
     *reinterpret_cast<float4*>(o.hi + off) = h;
@@ -228,12 +222,19 @@ __device__ __forceinline__ void row_store4(const RowOut& o, int col, float4 v) {
 }
 
 // |x|^p  and  d/dx coef*|x|^p  (general_models.py:572-576: coef * norm(x, p)**p)
+static __device__ __noinline__ float abs_pow_generic(float ax, int p) { return powf(ax, (float)p); }
 __device__ __forceinline__ float abs_pow(float x, int p) {
   float ax = fabsf(x);
   if (p == 3) return ax * ax * ax;
   if (p == 2) return ax * ax;
   if (p == 1) return ax;
-  return powf(ax, (float)p);
+  return abs_pow_generic(ax, p);
+}
+// the powf path is kept out of line: inlined at every call site it multiplied the code size of the kernels that apply
+// the regulariser per element (the fused kernel's negative-side pass went from 4k to 12k instructions and thrashed the
+// instruction cache), and no reference recipe uses a norm other than 1, 2 or 3
+static __device__ __noinline__ float reg_grad_pow(float x, int p, float coef) {
+  return coef * (float)p * powf(fabsf(x), (float)(p - 1)) * sgnf(x);
 }
 __device__ __forceinline__ float reg_grad(float x, int p, float coef) {
   if (coef == 0.f || p <= 0) return 0.f;
@@ -241,7 +242,7 @@ __device__ __forceinline__ float reg_grad(float x, int p, float coef) {
   if (p == 3) return 3.f * coef * ax * x;
   if (p == 2) return 2.f * coef * x;
   if (p == 1) return coef * sgnf(x);
-  return coef * (float)p * powf(ax, (float)(p - 1)) * sgnf(x);
+  return reg_grad_pow(x, p, coef);
 }
 __device__ __forceinline__ float4 reg_grad4(float4 x, int p, float coef) {
   return make_float4(reg_grad(x.x, p, coef), reg_grad(x.y, p, coef), reg_grad(x.z, p, coef), reg_grad(x.w, p, coef));

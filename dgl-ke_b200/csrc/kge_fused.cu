@@ -79,6 +79,17 @@ struct FusedArgs {
                              // shows how much of the GEMM time is operand traffic)
 };
 
+// regulariser gradient in the epilogue: the default norm (3) inline, anything else out of line (code size: the
+// epilogue is instruction-cache sensitive)
+static __device__ __noinline__ float4 reg_grad4_any(float4 b, int norm, float coef) { return reg_grad4(b, norm, coef); }
+__device__ __forceinline__ float4 reg_grad4_fast(float4 b, int norm, float coef) {
+  if (norm == 3) {
+    const float c3 = 3.f * coef;
+    return make_float4(c3 * fabsf(b.x) * b.x, c3 * fabsf(b.y) * b.y, c3 * fabsf(b.z) * b.z, c3 * fabsf(b.w) * b.w);
+  }
+  return reg_grad4_any(b, norm, coef);
+}
+
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 template <int MODE>
@@ -206,20 +217,13 @@ k_fused(const __grid_constant__ CUtensorMap mXh, const __grid_constant__ CUtenso
         const int kleft = g.D - kb * 32;
         const int ksteps = kleft >= 32 ? 4 : (kleft >> 3);
         if (elect_one()) {
-          // Two accumulators (TMEM regions 1 and 2, summed by the epilogue): even k-steps -> region 1, odd -> region 2,
-          // issued term-major so that consecutive MMAs never accumulate into the same tile back to back.
 #pragma unroll
-          for (int term = 0; term < 3; ++term) {
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              if (ks < ksteps) {
-                const uint64_t o = (uint64_t)(ks * 2);   // K-major: +32 bytes per k-step inside the 128-byte swizzle span
-                const uint32_t dst = tmem_base + ((ks & 1) ? colR2 : 0u);
-                const uint32_t acc = (kb == 0 && ks < 2 && term == 0) ? 0u : 1u;
-                if (term == 0) umma_tf32(dst, dXh + o, dYh + o, idesc1, acc);
-                else if (term == 1) umma_tf32(dst, dXh + o, dYl + o, idesc1, 1u);
-                else umma_tf32(dst, dXl + o, dYh + o, idesc1, 1u);
-              }
+          for (int ks = 0; ks < 4; ++ks) {
+            if (ks < ksteps) {
+              const uint64_t o = (uint64_t)(ks * 2);     // K-major: +32 bytes per k-step inside the 128-byte swizzle span
+              umma_tf32(tmem_base, dXh + o, dYh + o, idesc1, (kb | ks) ? 1u : 0u);
+              umma_tf32(tmem_base, dXh + o, dYl + o, idesc1, 1u);
+              umma_tf32(tmem_base, dXl + o, dYh + o, idesc1, 1u);
             }
           }
           umma_commit(&empty1[s]);
@@ -318,10 +322,6 @@ k_fused(const __grid_constant__ CUtensorMap mXh, const __grid_constant__ CUtenso
           for (int col = cb; col < ce; col += 16) {
             float v[16], rr[16];
             tmem_ld16(trow + col, v);
-            tmem_ld16(trow + colR2 + col, rr);
-#pragma unroll
-            for (int e = 0; e < 16; ++e) v[e] += rr[e];               // the two GEMM1 accumulators
-            tmem_st16(trow + col, v);                                   // region 1 <- their sum (pass C reads it)
 #pragma unroll
             for (int e = 0; e < 16; ++e) {
               float s = v[e];
@@ -343,9 +343,8 @@ k_fused(const __grid_constant__ CUtensorMap mXh, const __grid_constant__ CUtenso
             }
             if (l2) tmem_st16(trow + colR2 + col, rr);
           }
-          tmem_wait_st();
+          if (l2) tmem_wait_st();
         }
-        const bool summed = l2 || g.adversarial || g.dumpS;      // pass A ran: region 1 holds the summed accumulator
         if (g.adversarial) {
           xch[0][ehalf][row] = mxl;
           epi_bar();
@@ -360,11 +359,7 @@ k_fused(const __grid_constant__ CUtensorMap mXh, const __grid_constant__ CUtenso
         for (int col = cb; col < ce; col += 16) {
           float v[16], rr[16], hi[16], lo[16];
           tmem_ld16(trow + col, v);
-          if (l2 || !summed) tmem_ld16(trow + colR2 + col, rr);
-          if (!summed) {
-#pragma unroll
-            for (int e = 0; e < 16; ++e) v[e] += rr[e];
-          }
+          if (l2) tmem_ld16(trow + colR2 + col, rr);
 #pragma unroll
           for (int e = 0; e < 16; ++e) {
             float s = v[e], rinv = 1.f;
@@ -424,9 +419,6 @@ k_fused(const __grid_constant__ CUtensorMap mXh, const __grid_constant__ CUtenso
         for (int col = cb; col < ce; col += 16) {
           float v[16], hi[16], lo[16];
           tmem_ld16(trow + col, v);
-          tmem_ld16(trow + colR2 + col, hi);
-#pragma unroll
-          for (int e = 0; e < 16; ++e) v[e] += hi[e];                 // the two GEMM1 accumulators
 #pragma unroll
           for (int e = 0; e < 16; ++e) {
             float s = v[e], rinv = 1.f;
@@ -555,7 +547,7 @@ k_fused(const __grid_constant__ CUtensorMap mXh, const __grid_constant__ CUtenso
               float4 b;
               b = bq[bidx + it];
               if (l2) o = f4_fma(b, -rsc[it], o);                   // sum_i V_ij a_i - (sum_i V_ij) b_j
-              o = f4_add(o, reg_grad4(b, g.reg_norm, g.reg_coef));
+              o = f4_add(o, reg_grad4_fast(b, g.reg_norm, g.reg_coef));
               gsq[it] += f4_dot(o, o);
             }
             st4(g.out + ((long long)c * g.Rx + mr) * (long long)g.D + k, o);
@@ -580,7 +572,7 @@ k_fused(const __grid_constant__ CUtensorMap mXh, const __grid_constant__ CUtenso
               if (g.xids) b = ld4(brow[it] + k);
               else { const long long so = slab_off(c, g.nblkD, g.Rx, mr, k); b = f4_add(ld4(g.Xhi + so), ld4(g.Xlo + so)); }
               if (l2) o = f4_fma(b, -rsc[it], o);                   // sum_i V_ij a_i - (sum_i V_ij) b_j
-              o = f4_add(o, reg_grad4(b, g.reg_norm, g.reg_coef));
+              o = f4_add(o, reg_grad4_fast(b, g.reg_norm, g.reg_coef));
               gsq[it] += f4_dot(o, o);
             }
             st4(g.out + ((long long)c * g.Rx + mr) * (long long)g.D + k, o);

@@ -186,13 +186,13 @@ __global__ void __launch_bounds__(kRowBlock) k_prep(StepParams p, TableView ent,
   const int lane = threadIdx.x & 31;
   const bool reg_on = (p.reg_coef > 0.f && p.reg_norm > 0);
   if (job < p.B) {
-    const float* h = node_row(p, ent, b, w, b.head_local[job]);     // local copies made by k_gather_nodes, or table rows
-    const float* t = node_row(p, ent, b, w, b.tail_local[job]);
+    const float* h = head_row(p, ent, b, w, job);     // local copies made by k_gather_nodes, or table rows
+    const float* t = tail_row(p, ent, b, w, job);
     const float* r = row_ptr(rel, b.rel_ids[job]);
     float pos, a2, reg, nrm;
     const long long ro = job * (long long)p.D;
     // tcgen05 engine: A is only consumed as hi/lo operands; fp32 tiles: plain fp32
-    const RowOut ao{w.Ahi ? nullptr : w.A + ro, w.Ahi, w.Alo, job / p.Cs, slab_blocks(p.D), p.Cs, (int)(job % p.Cs), p.split_trunc};
+    const RowOut ao{w.Ahi ? nullptr : w.A + ro, w.Ahi, w.Alo, job / p.Cs, slab_blocks(p.D), p.Cs, (int)(job % p.Cs)};
     edge_forward<MODEL, KIT>(p, h, r, t, ao, lane, pos, a2, reg, nrm, true);
     if (lane == 0) {
       w.pos[job] = pos;
@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(kRowBlock) k_prep(StepParams p, TableView ent,
     const float* src = row_ptr(ent, b.neg_ids[job]);
     const long long ro = job * (long long)p.D;
     // fused contraction: the negatives exist only as TF32 hi/lo slabs (Bn receives their gradient later)
-    const RowOut bo{p.fused ? nullptr : w.Bn + ro, w.Bhi, w.Blo, job / p.Ns, slab_blocks(p.D), p.Ns, (int)(job % p.Ns), p.split_trunc};
+    const RowOut bo{p.fused ? nullptr : w.Bn + ro, w.Bhi, w.Blo, job / p.Ns, slab_blocks(p.D), p.Ns, (int)(job % p.Ns)};
     float b2 = 0.f, reg = 0.f;
     const int nv = p.D >> 2;
     for (int v0 = 0; v0 < nv; v0 += kWarp * KIT) {
@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(kRowBlock) k_prep_dense(StepParams p, const fl
     if (!want_pos) { if (p.neg_head) hrow = trow; else trow = hrow; }
     const long long ro = job * (long long)p.D;
     const RowOut ao{(want_a && !w.Ahi) ? w.A + ro : nullptr, want_a ? w.Ahi : nullptr, want_a ? w.Alo : nullptr,
-                    job / p.Cs, slab_blocks(p.D), p.Cs, (int)(job % p.Cs), 0};
+                    job / p.Cs, slab_blocks(p.D), p.Cs, (int)(job % p.Cs)};
     edge_forward<MODEL, 1>(p, hrow, relr + job * (long long)p.Dr, trow, ao, lane, pos, a2, reg, nrm, want_a);
     if (lane == 0) {
       if (want_pos) w.pos[job] = pos;
@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(kRowBlock) k_prep_dense(StepParams p, const fl
   if (job < p.Nn && negrows != nullptr) {
     const float* src = negrows + job * (long long)p.D;
     const long long ro = job * (long long)p.D;
-    const RowOut bo{nullptr, w.Bhi, w.Blo, job / p.Ns, slab_blocks(p.D), p.Ns, (int)(job % p.Ns), 0};
+    const RowOut bo{nullptr, w.Bhi, w.Blo, job / p.Ns, slab_blocks(p.D), p.Ns, (int)(job % p.Ns)};
     float b2 = 0.f;
     for (int v = lane; v < (p.D >> 2); v += kWarp) {
       float4 x = ld4(src + 4 * v);
@@ -583,8 +583,8 @@ __global__ void __launch_bounds__(kRowBlock) k_chain(StepParams p, TableView ent
   if (i >= p.B) return;
   const int lane = threadIdx.x & 31;
   const long long hl = b.head_local[i], tl = b.tail_local[i], rid = b.rel_ids[i];
-  const float* h = node_row(p, ent, b, w, hl);
-  const float* t = node_row(p, ent, b, w, tl);
+  const float* h = head_row(p, ent, b, w, i);
+  const float* t = tail_row(p, ent, b, w, i);
   const float* r = row_ptr(rel, rid);
   const float* ga = w.GA + i * (long long)p.D;
   float* ngh = w.NG + hl * (long long)p.D;
@@ -796,12 +796,13 @@ __device__ __forceinline__ void upd_node(const StepParams& p, const TableView& e
   }
   s_new = __shfl_sync(0xffffffffu, s_new, 0);
   const float stdv = sqrtf(s_new) + 1e-10f;
+  const float nlr_std = -p.lr / stdv;
   // pass 2: emb[id] += -lr * g / std.  Indices are unique, so on one GPU the new row is (traced copy + step);
   // across GPUs the step is a system-scope red.add (atomic w.r.t. peers).
   for (int v = lane; v < nv; v += kWarp) {
     float4 x = ld4(nc + 4 * v);
     float4 g = f4_add(ld4(ng + 4 * v), reg_grad4(x, p.reg_norm, p.reg_coef));
-    float4 tmp = make_float4((-p.lr * g.x) / stdv, (-p.lr * g.y) / stdv, (-p.lr * g.z) / stdv, (-p.lr * g.w) / stdv);
+    const float4 tmp = f4_scale(g, nlr_std);       // (-lr * g) / std up to one rounding: one division per row, not per element
     if (sharded) red_add4_sys(row + 4 * v, tmp);
     else st4(row + 4 * v, f4_add(x, tmp));
     st4(ng + 4 * v, z);
@@ -825,17 +826,18 @@ __device__ __forceinline__ void upd_rel_dense(const TableView& rel, float* rg, f
   const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int v = lane; v < (rel.dim >> 2); v += kWarp) {
     float4 x = ld4(g + 4 * v), e = ld4(row + 4 * v);
-    st4(row + 4 * v, f4_add(e, make_float4((-lr * x.x) / stdv, (-lr * x.y) / stdv, (-lr * x.z) / stdv, (-lr * x.w) / stdv)));
+    st4(row + 4 * v, f4_fma(x, -lr / stdv, e));
     st4(g + 4 * v, z);
   }
 }
 
 __device__ __forceinline__ void apply_row(const TableView& t, long long id, const float* g, int dim, float lr, int lane) {
   const float stdv = sqrtf(*state_ptr(t, id)) + 1e-10f;
+  const float nlr_std = -lr / stdv;               // one division per row: (-lr * g) / std up to one rounding
   float* row = row_ptr(t, id);
   for (int v = lane; v < (dim >> 2); v += kWarp) {
     float4 x = ld4(g + 4 * v);
-    table_red_add4(t, row + 4 * v, make_float4((-lr * x.x) / stdv, (-lr * x.y) / stdv, (-lr * x.z) / stdv, (-lr * x.w) / stdv));
+    table_red_add4(t, row + 4 * v, f4_scale(x, nlr_std));
   }
   for (int k = ((dim >> 2) << 2) + lane; k < dim; k += kWarp) atomicAdd(row + k, (-lr * g[k]) / stdv);
 }
@@ -998,7 +1000,7 @@ __global__ void __launch_bounds__(kRowBlock) k_rel_apply_dense(TableView rel, fl
   const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int v = lane; v < (rel.dim >> 2); v += kWarp) {
     float4 x = ld4(g + 4 * v), e = ld4(row + 4 * v);
-    st4(row + 4 * v, f4_add(e, make_float4((-lr * x.x) / stdv, (-lr * x.y) / stdv, (-lr * x.z) / stdv, (-lr * x.w) / stdv)));
+    st4(row + 4 * v, f4_fma(x, -lr / stdv, e));
     st4(g + 4 * v, z);
   }
 }

@@ -48,7 +48,8 @@ class StepCfg(C.Structure):
 class Batch(C.Structure):
     _fields_ = [("node_ids", C.c_void_p), ("n_nodes", C.c_int64), ("head_local", C.c_void_p),
                 ("tail_local", C.c_void_p), ("rel_ids", C.c_void_p), ("neg_ids", C.c_void_p),
-                ("edge_weight", C.c_void_p), ("n_nodes_dev", C.c_void_p)]
+                ("edge_weight", C.c_void_p), ("n_nodes_dev", C.c_void_p), ("head_ids", C.c_void_p),
+                ("tail_ids", C.c_void_p)]
 
 
 _lib = None
@@ -213,11 +214,12 @@ def make_cfg(model, entity_dim, relation_dim, gamma, emb_init, lr, reg_coef, reg
                    neg_sample_size)
 
 
-def make_batch(node_ids, head_local, tail_local, rel_ids, neg_ids, edge_weight=None):
-    """Index tensors may be CUDA tensors (device ABI) or CPU tensors (host ABI); int64, contiguous."""
+def make_batch(node_ids, head_local, tail_local, rel_ids, neg_ids, edge_weight=None, head_ids=None, tail_ids=None):
+    """Index tensors may be CUDA tensors (device ABI) or CPU tensors (host ABI); int64, contiguous.
+    head_ids / tail_ids (optional, = node_ids[head_local], node_ids[tail_local]) save the kernels an index hop."""
     for t in (node_ids, head_local, tail_local, rel_ids, neg_ids):
         assert t.dtype == torch.int64 and t.is_contiguous()
+    ptr = lambda t: t.data_ptr() if t is not None else None
     b = Batch(node_ids.data_ptr(), node_ids.numel(), head_local.data_ptr(), tail_local.data_ptr(),
-              rel_ids.data_ptr(), neg_ids.data_ptr(),
-              edge_weight.data_ptr() if edge_weight is not None else None, None)
-    return b, (node_ids, head_local, tail_local, rel_ids, neg_ids, edge_weight)
+              rel_ids.data_ptr(), neg_ids.data_ptr(), ptr(edge_weight), None, ptr(head_ids), ptr(tail_ids))
+    return b, (node_ids, head_local, tail_local, rel_ids, neg_ids, edge_weight, head_ids, tail_ids)

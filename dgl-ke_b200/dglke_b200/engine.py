@@ -101,9 +101,9 @@ class StepEngine:
 
     # ---- fused ------------------------------------------------------------------------------
     def step(self, node_ids, head_local, tail_local, rel_ids, neg_ids, chunk_size, neg_sample_size, neg_head,
-             edge_weight=None, log4=None):
+             edge_weight=None, log4=None, head_ids=None, tail_ids=None):
         cfg = self.cfg(head_local.numel(), chunk_size, neg_sample_size, neg_head)
-        b, keep = _lib.make_batch(node_ids, head_local, tail_local, rel_ids, neg_ids, edge_weight)
+        b, keep = _lib.make_batch(node_ids, head_local, tail_local, rel_ids, neg_ids, edge_weight, head_ids, tail_ids)
         out = self.log4 if log4 is None else log4
         _lib.check(self.lib.kge_step_fused(self.h.raw, C.byref(cfg), self.ent.ref(), self.rel.ref(), C.byref(b),
                                            out.data_ptr(), self.h.stream()))

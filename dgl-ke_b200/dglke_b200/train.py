@@ -7,10 +7,12 @@ All reference flags parse.  What differs, and why:
   * data: there is no network in this environment, so built-in dataset names select the dataset's SHAPE
     (entities / relations / training edges) and triples are drawn synthetically unless --data_files
     points at udd_hrt-style integer triple files (entity_file relation_file train_file [valid] [test]);
-  * --gpu is required (no CPU path).  This CLI drives ONE GPU; the multi-GPU path (entity table row-sharded over the
-    GPUs instead of --mix_cpu_gpu's host table, one process per GPU under torchrun) is the
-    dglke_b200.dist.ShardedTrainer API that bench.py --gpus N uses -- wiring it into this CLI is on the next list;
-  * sampling is numpy-based (DGL's C++ sampler is out of scope).
+  * --gpu is required (no CPU path).  One GPU id: one process, KEModel over the fused 5-kernel step.  Several ids
+    (`--gpu 0 1 2 3`, the reference's multi-GPU spelling, train.py:290-317): one process per GPU is spawned, the entity
+    table is row-sharded over the GPUs' HBM (replacing --mix_cpu_gpu's host table) and trained through
+    dglke_b200.dist.ShardedTrainer (peer loads / red.add over NVLink, NCCL all-reduce of the relation gradients);
+  * sampling runs on the GPU (dglke_b200.sampler.DeviceSampler replaces DGL's C++ EdgeSampler; --host_sampler selects
+    the numpy samplers of dglke_b200.graph instead).
 """
 import os
 import sys
@@ -21,7 +23,8 @@ import torch as th
 
 from .utils import ArgParser, get_compatible_batch_size, save_model, prepare_save_path
 from .general_models import KEModel
-from .graph import SyntheticSampler, TripleSampler, eval_batches
+from .graph import SyntheticSampler, TripleSampler, eval_batches, NegGraph
+from .sampler import DeviceSampler
 
 # (entities, relations, training edges): docs/source/benchmarks.rst dataset table
 BUILTIN_SHAPES = {
@@ -51,6 +54,42 @@ def _read_udd(args):
     valid = triples(files[3]) if len(files) > 3 else None
     test = triples(files[4]) if len(files) > 4 else None
     return n_ent, n_rel, train, valid, test
+
+
+class _DevicePosGraph:
+    """What KEModel.forward needs from a device-sampled batch: the kge_batch_t itself."""
+
+    def __init__(self, batch):
+        self.device_batch = batch
+        self.ndata, self.edata = {}, {}
+
+    def number_of_edges(self):
+        return self.device_batch.B
+
+
+class DeviceGraphSampler:
+    """Iterator of (pos_g, neg_g) over dglke_b200.sampler.DeviceSampler (same protocol as the numpy samplers)."""
+
+    def __init__(self, heads, rels, tails, n_entities, batch_size, neg_sample_size, seed=0, device=0):
+        self.s = DeviceSampler(heads, rels, tails, n_entities, batch_size, neg_sample_size, seed=seed, device=device)
+        self.k = 0
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        b = self.s.sample(self.k)
+        self.k += 1
+        dummy = th.empty(0, dtype=th.int64)
+        ng = NegGraph(dummy, self.s.num_chunks, self.s.chunk_size, self.s.Ns, b.neg_head)
+        return _DevicePosGraph(b), ng
+
+
+def synthetic_edges(n_ent, n_rel, n_edges, seed=0):
+    """A synthetic training graph of a built-in dataset's shape (there is no network to download the real one)."""
+    rng = np.random.default_rng(seed)
+    n_edges = int(min(n_edges, 20_000_000))
+    return rng.integers(0, n_ent, n_edges), rng.integers(0, n_rel, n_edges), rng.integers(0, n_ent, n_edges)
 
 
 def train(args, model, train_sampler, valid_batches=None, rank=0, barrier=None):
@@ -128,13 +167,20 @@ def main(argv=None):
         print("NOTE: no network -- training on a synthetic graph of %s's shape (%d entities, %d relations)" % (
             args.dataset, n_ent, n_rel))
         tr = va = te = None
+    if len(args.gpu) > 1:
+        return train_multi_gpu(args, n_ent, n_rel, tr if tr is not None else synthetic_edges(n_ent, n_rel, n_edges))
     th.cuda.set_device(args.gpu[0])
     model = KEModel(args, args.model_name, n_ent, n_rel, args.hidden_dim, args.gamma,
                     double_entity_emb=args.double_ent, double_relation_emb=args.double_rel)
-    if tr is None:
+    host = getattr(args, "host_sampler", False) or args.has_edge_importance
+    if host and tr is None:
         sampler = SyntheticSampler(n_ent, n_rel, args.batch_size, args.neg_sample_size, seed=0)
-    else:
+    elif host:
         sampler = TripleSampler(tr[0], tr[1], tr[2], n_ent, n_rel, args.batch_size, args.neg_sample_size, seed=0)
+    else:
+        edges = tr if tr is not None else synthetic_edges(n_ent, n_rel, n_edges)
+        sampler = DeviceGraphSampler(edges[0], edges[1], edges[2], n_ent, args.batch_size, args.neg_sample_size, seed=0,
+                                     device=args.gpu[0])
 
     def split_batches(split):
         def gen():
@@ -147,6 +193,62 @@ def main(argv=None):
     if args.test and te is not None:
         test(args, model, split_batches(te)())
     return model
+
+
+def _multi_gpu_worker(rank, world, args, n_ent, n_rel, edges, port):
+    """One process per GPU (reference: train.py:298-317 forks one process per GPU over a shared host table)."""
+    import torch.distributed as dist
+    from .dist import ShardedTrainer
+    from .engine import Hyper
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    dev = th.device("cuda", args.gpu[rank])
+    th.cuda.set_device(dev)
+    dist.init_process_group("nccl", device_id=dev)
+    hp = Hyper(model=args.model_name, hidden_dim=args.hidden_dim, gamma=args.gamma, lr=args.lr,
+               reg_coef=args.regularization_coef, reg_norm=args.regularization_norm,
+               adversarial=args.neg_adversarial_sampling, adv_temperature=args.adversarial_temperature,
+               double_ent=args.double_ent, double_rel=args.double_rel)
+    trainer = ShardedTrainer(hp, n_ent, n_rel, dev, seed=0)
+    # RandomPartition (dataloader/sampler.py:256-290): a fixed random split of the edges over the ranks
+    perm = np.random.default_rng(0).permutation(len(edges[0]))[rank::world]
+    sampler = DeviceSampler(edges[0][perm], edges[1][perm], edges[2][perm], n_ent, args.batch_size, args.neg_sample_size,
+                            seed=1000 + rank, device=dev.index)
+    start = t0 = time.time()
+    logs = []
+    for step in range(args.max_step):
+        b = sampler.sample(step)
+        log4 = trainer.step(b, chunk_size=sampler.chunk_size, neg_sample_size=args.neg_sample_size)
+        if (step + 1) % args.log_interval == 0:
+            v = log4.cpu().tolist()
+            print("[proc {}][Train]({}/{}) average loss: {} (pos {}, neg {}, reg {})".format(rank, step + 1, args.max_step, v[2],
+                                                                                      v[0], v[1], v[3]))
+            print("[proc {}][Train] {} steps take {:.3f} seconds".format(rank, args.log_interval, time.time() - start))
+            start = time.time()
+        if args.force_sync_interval > 0 and (step + 1) % args.force_sync_interval == 0:
+            trainer.barrier()                       # train_pytorch.py:157-159
+    trainer.barrier()
+    print("proc {} takes {:.3f} seconds".format(rank, time.time() - t0))
+    if not args.no_save_emb:
+        ent = trainer.gather_entity_table()
+        if rank == 0:
+            os.makedirs(args.save_path, exist_ok=True)
+            name = args.dataset + "_" + args.model_name
+            np.save(os.path.join(args.save_path, name + "_entity.npy"), ent.cpu().numpy())
+            np.save(os.path.join(args.save_path, name + "_relation.npy"), trainer.rel_emb.cpu().numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def train_multi_gpu(args, n_ent, n_rel, edges):
+    import torch.multiprocessing as mp
+    world = len(args.gpu)
+    if args.has_edge_importance:
+        raise SystemExit("--has_edge_importance is single-GPU only here")
+    port = 29400 + os.getpid() % 1000
+    edges = tuple(np.ascontiguousarray(e, dtype=np.int64) for e in edges)
+    mp.spawn(_multi_gpu_worker, args=(world, args, n_ent, n_rel, edges, port), nprocs=world, join=True)
+    return None
 
 
 if __name__ == "__main__":

@@ -116,6 +116,8 @@ typedef struct {
   const float* edge_weight;
   const int64_t* n_nodes_dev;  /* device-side node count (kge_sampler_sample): used when n_nodes < 0; node_ids then
                                   has room for 2*batch entries */
+  const int64_t* head_ids;     /* optional: global entity ids of the edges' endpoints (= node_ids[head_local],   */
+  const int64_t* tail_ids;     /*   node_ids[tail_local]); saves the kernels one dependent index load per row     */
 } kge_batch_t;
 
 typedef struct kge_context* kge_handle_t;

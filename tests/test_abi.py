@@ -31,7 +31,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(_lib.Shard) == 40
     assert C.sizeof(_lib.Table) == 32
     assert C.sizeof(_lib.StepCfg) == 64
-    assert C.sizeof(_lib.Batch) == 64
+    assert C.sizeof(_lib.Batch) == 80
     assert _lib.StepCfg.batch.offset == 48 and _lib.StepCfg.neg_sample_size.offset == 60
 
 

@@ -129,6 +129,36 @@ def test_fused_step_five_launches_matches_oracle(cfg):
     assert per_step[-1] <= 5, per_step
 
 
+@pytest.mark.parametrize("model,hidden,de", [("TransE_l1", 64, False), ("RotatE", 32, True), ("RESCAL", 32, False),
+                                             ("DistMult", 20, False)])
+def test_step_fused_schedule_with_the_tile_kernels(model, hidden, de):
+    """kge_step_fused on shapes / models the tcgen05 kernel does not take (L1, RotatE, RESCAL, D < 32): same fused-step
+    schedule (no node cache, dense relation sums, log scalars from the update kernel) over the fp32 tile kernels."""
+    hp = ko.Hyper(model=model, hidden_dim=hidden, gamma=8.0, lr=0.1, reg_coef=1e-6, reg_norm=3, adversarial=True,
+                  double_ent=de)
+    n_ent, n_rel, B, Cs, Ns = 700, 9, 96, 32, 24
+    ent, es, rel, rs = ko.init_tables(hp, n_ent, n_rel, seed=6)
+    es.uniform_(0.0, 1e-3)
+    rs.uniform_(0.0, 1e-3)
+    eng, (e, e_s, r, r_s) = _engine(hp, ent, es, rel, rs)
+    o = [x.clone() for x in (ent, es, rel, rs)]
+    for step in range(2):
+        neg_head = step % 2 == 1
+        si, C = _random_step(hp, n_ent, n_rel, B, Cs, Ns, neg_head, seed=300 + step)
+        fb = ko.train_step(hp, o[0], o[1], o[2], o[3], si["node_ids"], si["head_local"], si["tail_local"],
+                           si["rel_ids"], si["neg_ids"], C, Cs, Ns, neg_head)
+        d = lambda t: t.to(eng.device)
+        got = eng.step(d(si["node_ids"]), d(si["head_local"]), d(si["tail_local"]), d(si["rel_ids"]), d(si["neg_ids"]),
+                       Cs, Ns, neg_head).cpu().numpy()
+        for i, k in enumerate(("pos_loss", "neg_loss", "loss", "regularization")):
+            np.testing.assert_allclose(got[i], fb["log"][k], rtol=5e-5, atol=1e-9, err_msg="step %d %s" % (step, k))
+    th.cuda.synchronize()
+    for got, want, name in ((e, o[0], "entity table"), (e_s, o[1], "entity state"), (r, o[2], "relation table"),
+                            (r_s, o[3], "relation state")):
+        w = want.numpy()
+        np.testing.assert_allclose(got.cpu().numpy(), w, rtol=1e-4, atol=5e-6 * float(np.abs(w).max()), err_msg=name)
+
+
 def test_fused_and_unfused_paths_agree():
     """Same step through the fused kernel and through the separate GEMM / loss kernels (kge_set_fused 0)."""
     from dglke_b200 import _lib
@@ -150,3 +180,44 @@ def test_fused_and_unfused_paths_agree():
     np.testing.assert_allclose(res[0][0], res[1][0], rtol=2e-5)
     np.testing.assert_allclose(res[0][1], res[1][1], rtol=1e-4, atol=1e-6)
     np.testing.assert_allclose(res[0][2], res[1][2], rtol=1e-4, atol=1e-6)
+
+
+def test_fused_kernel_stress_200_runs():
+    """200 back-to-back runs of the fused kernels on fresh random rows (hot chunk shape, both corruption modes): every
+    run's scores and both coefficient passes against float64.  A race in the TMA / mbarrier / TMEM hand-offs would show
+    up as sporadic garbage; this is the default engine's collected stress test (tests/stress_umma.py is the manual one
+    for the stand-alone GEMMs)."""
+    from dglke_b200 import _lib
+    hp = ko.Hyper(model="TransE_l2", hidden_dim=400, gamma=19.9, lr=0.1, reg_coef=1e-9, adversarial=True)
+    n_ent, n_rel, B, Cs, Ns = 3000, 11, 800, 200, 200
+    g = th.Generator().manual_seed(123)
+    bad = []
+    eng = None
+    dump = None
+    for it in range(200):
+        ent = (th.rand(n_ent, 400, generator=g) - 0.5) * 0.11
+        rel = (th.rand(n_rel, 400, generator=g) - 0.5) * 0.11
+        es, rs = th.zeros(n_ent), th.zeros(n_rel)
+        neg_head = bool(it & 1)
+        si, C = _random_step(hp, n_ent, n_rel, B, Cs, Ns, neg_head, seed=1000 + it)
+        S64, V64 = _fp64_reference(hp, (ent, es, rel, rs), si, C, Cs, Ns)
+        eng, _ = _engine(hp, ent, es, rel, rs)
+        if dump is None:
+            dump = th.empty(2 * B * Ns, dtype=th.float32, device=eng.device)
+        dump.fill_(float("nan"))
+        eng.h.set_dump(dump)
+        try:
+            d = lambda t: t.to(eng.device)
+            eng.forward_backward(d(si["node_ids"]), d(si["head_local"]), d(si["tail_local"]), d(si["rel_ids"]),
+                                 d(si["neg_ids"]), Cs, Ns, neg_head)
+            S = eng.read(_lib.BUF_NEG_SCORE, (B, Ns)).double().cpu()
+            VP = dump[:B * Ns].reshape(B, Ns).double().cpu()
+            VN = dump[B * Ns:].reshape(C, Ns, Cs).transpose(1, 2).reshape(B, Ns).double().cpu()
+        finally:
+            eng.h.set_dump(None)
+        eS = float(((S - S64).abs() / (1e-5 * S64.abs() + 2e-5)).max())
+        eP = float(((VP - V64).abs() / (2e-5 * V64.abs() + 2e-6 * float(V64.abs().max()))).max())
+        eN = float(((VN - V64).abs() / (2e-5 * V64.abs() + 2e-6 * float(V64.abs().max()))).max())
+        if not (eS <= 1.0 and eP <= 1.0 and eN <= 1.0):        # also catches NaN
+            bad.append((it, eS, eP, eN))
+    assert not bad, "runs outside tolerance (iteration, score, coef P, coef N in units of the tolerance): %s" % bad[:10]

@@ -137,6 +137,7 @@ HOT = [  # (model, hidden, gamma, double_ent, n_ent, n_rel, B, Cs, Ns, adv)
     ("ComplEx", 400, 143.0, False, 5000, 100, 600, 200, 200, True),
     ("RotatE", 200, 12.0, True, 5000, 53, 512, 256, 256, True),            # configs[2] shape: D_e=400, D_r=200
     ("RESCAL", 64, 12.0, False, 2000, 20, 128, 64, 64, False),
+    ("RESCAL", 500, 12.0, False, 2000, 6, 128, 64, 64, False),             # the reference recipe's d=500 (1 MB per relation)
     ("TransE_l2", 100, 10.0, False, 977, 13, 300, 100, 60, False),         # ragged: Cs != Ns, D % 64 != 0
     ("DistMult", 36, 5.0, False, 500, 7, 70, 70, 33, True),                # single chunk, odd Ns
 ]

@@ -16,6 +16,7 @@ SHAPES = [  # (model, hidden, gamma, n_ent, n_rel, B, Cs, Ns)
     ("ComplEx", 400, 143.0, 5000, 100, 400, 200, 200),
     ("TransE_l2", 96, 10.0, 977, 13, 320, 160, 72),          # ragged: Cs != Ns, small D
     ("DistMult", 512, 143.0, 20000, 50, 512, 256, 512),      # Ns > 256: two N tiles in GEMM1
+    ("DistMult", 512, 143.0, 50000, 100, 2048, 1024, 1024),  # BASELINE configs[4] chunk shape: d=512, neg=1024
 ]
 
 
