@@ -386,7 +386,8 @@ def measure(args, workload, rank, world, local_rank, dev, cpu_base, K_steps, ful
     kern_ms = sum(prof.values())
     dominant = max(prof.items(), key=lambda kv: kv[1]) if prof else ("", 0.0)
 
-    del graphs
+    used_graph = graphs is not None
+    graphs = None
     if world > 1:
         dist.barrier()
         torch.cuda.synchronize()
@@ -421,7 +422,7 @@ def measure(args, workload, rank, world, local_rank, dev, cpu_base, K_steps, ful
         "config": {"workload": desc, "batch_per_gpu": B, "global_batch": B * world, "chunk_size": Cs,
                    "neg_sample_size": neg, "entities": n_ent, "relations": n_rel, "parallelism": parallelism,
                    "l2": "cold: 256 MiB written between timed steps" if not args.no_flush else "warm (no flush)",
-                   "launch": "one CUDA graph per step" if graphs is not None else "eager launches",
+                   "launch": "one CUDA graph per step" if used_graph else "eager launches",
                    "sampling": "excluded (pre-generated seeded batches), as on the reference arm",
                    "arithmetic": "fp32 rows; contractions on tcgen05 as 3xTF32 (hi/lo split) with fp32 accumulation" if model in ("TransE_l2", "DistMult", "ComplEx", "RESCAL") else "fp32 CUDA-core tiles",
                    "bytes_per_edge": bpe},

@@ -759,7 +759,7 @@ __device__ __forceinline__ void grid_barrier(unsigned int* ctr) {
   if (threadIdx.x == 0) {
     __threadfence();
     atomicAdd(ctr, 1u);
-    while (ld_acquire_u32(ctr) < gridDim.x) __nanosleep(40);
+    while (ld_acquire_u32(ctr) < gridDim.x) __nanosleep(200);
     __threadfence();
   }
   __syncthreads();
@@ -776,6 +776,47 @@ __device__ __forceinline__ void upd_node(const StepParams& p, const TableView& e
   const bool sharded = ent.n_shards > 1;
   const bool reg_on = (p.reg_coef > 0.f && p.reg_norm > 0);
   float* st = state_ptr(ent, id);
+  if (nv <= 4 * kWarp) {
+    // D <= 512: all of the row's loads (NG and the traced copy) are issued before any arithmetic, and the sums stay in
+    // registers for the second half -- one trip through memory and 8 independent 16-byte loads in flight per lane
+    float4 x[4], gq[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int v = lane + kWarp * q;
+      x[q] = (v < nv) ? ld4(nc + 4 * v) : z;
+      gq[q] = (v < nv) ? ld4(ng + 4 * v) : z;
+    }
+    float gs = 0.f, reg = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      gq[q] = f4_add(gq[q], reg_grad4(x[q], p.reg_norm, p.reg_coef));     // padding lanes: 0 + reg'(0) = 0
+      gs += f4_dot(gq[q], gq[q]);
+      if (reg_on && !p.use_nc) reg += abs_pow4_sum(x[q], p.reg_norm);
+    }
+    gs = warp_sum(gs) / (float)p.D;
+    if (!p.use_nc) {            // no k_gather_nodes ran: this node's share of the regulariser is produced here
+      reg = warp_sum(reg);
+      if (lane == 0) w.regp[p.B + p.Nn + u] = reg;
+    }
+    float* st = state_ptr(ent, id);
+    float s_new = 0.f;
+    if (lane == 0) {
+      if (sharded) s_new = atomicAdd_system(st, gs) + gs;   // remote-safe: other GPUs may add to the same state
+      else { s_new = *st + gs; *st = s_new; }
+    }
+    s_new = __shfl_sync(0xffffffffu, s_new, 0);
+    const float nlr_std = -p.lr / (sqrtf(s_new) + 1e-10f);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int v = lane + kWarp * q;
+      if (v < nv) {
+        if (sharded) red_add4_sys(row + 4 * v, f4_scale(gq[q], nlr_std));
+        else st4(row + 4 * v, f4_fma(gq[q], nlr_std, x[q]));
+        st4(ng + 4 * v, z);
+      }
+    }
+    return;
+  }
   // pass 1: g = NG + reg'(x), mean(g^2)
   float gs = 0.f, reg = 0.f;
   for (int v = lane; v < nv; v += kWarp) {
@@ -832,20 +873,37 @@ __device__ __forceinline__ void upd_rel_dense(const TableView& rel, float* rg, f
 }
 
 __device__ __forceinline__ void apply_row(const TableView& t, long long id, const float* g, int dim, float lr, int lane) {
+  float* row = row_ptr(t, id);
+  const int nv = dim >> 2;
+  if (nv <= 4 * kWarp && (dim & 3) == 0) {
+    // all loads of the gradient row in flight before the state scalar is needed
+    float4 x[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int v = lane + kWarp * q;
+      x[q] = (v < nv) ? ld4(g + 4 * v) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const float nlr_std = -lr / (sqrtf(*state_ptr(t, id)) + 1e-10f);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int v = lane + kWarp * q;
+      if (v < nv) table_red_add4(t, row + 4 * v, f4_scale(x[q], nlr_std));
+    }
+    return;
+  }
   const float stdv = sqrtf(*state_ptr(t, id)) + 1e-10f;
   const float nlr_std = -lr / stdv;               // one division per row: (-lr * g) / std up to one rounding
-  float* row = row_ptr(t, id);
-  for (int v = lane; v < (dim >> 2); v += kWarp) {
+  for (int v = lane; v < nv; v += kWarp) {
     float4 x = ld4(g + 4 * v);
     table_red_add4(t, row + 4 * v, f4_scale(x, nlr_std));
   }
-  for (int k = ((dim >> 2) << 2) + lane; k < dim; k += kWarp) atomicAdd(row + k, (-lr * g[k]) / stdv);
+  for (int k = (nv << 2) + lane; k < dim; k += kWarp) atomicAdd(row + k, (-lr * g[k]) / stdv);
 }
 
 __device__ void reduce_log_part(const StepParams& p, const StepWs& w, long long nreg, const float* wbar, float* log4,
                                 int bid, int nb);
 
-__global__ void __launch_bounds__(kRowBlock) k_update(UpdArgs a) {
+__global__ void __launch_bounds__(kRowBlock, 4) k_update(UpdArgs a) {
   const StepParams& p = a.p;
   const StepWs& w = a.w;
   const int lane = threadIdx.x & 31;
