@@ -438,6 +438,9 @@ def measure(args, workload, rank, world, local_rank, dev, cpu_base, K_steps, ful
         "cpu_baseline": cpu_base,
         "clocks": clocks,
     }
+    if world > 1:
+        torch.cuda.synchronize()
+        eng.close()                     # unmap the shards: the next workload of this process allocates its own
     return line
 
 

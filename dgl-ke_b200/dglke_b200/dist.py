@@ -4,15 +4,18 @@ Replaces the reference's multi-GPU data flow (--mix_cpu_gpu: entity table in hos
 H2D gather / D2H scatter per step, train.py:92-95, tensor_models.py:292-294,330-361) with:
 
   * entity table + Adagrad state: contiguous row-range shards, one per GPU's HBM
-    (owner(id) = id // ceil(N_e / G)); every rank maps all peers' shards through CUDA IPC, so the
-    step kernels gather remote rows with peer loads and scatter updates with system-scope red.add over
-    NVLink / NVSwitch from inside the kernel -- no entity collective;
+    (owner(id) = id // ceil(N_e / G)); every rank maps all peers' shards (CUDA virtual-memory allocations passed
+    between the ranks as file descriptors: 2 MiB pages on both sides -- a cudaIpc mapping of a 69 GB shard is
+    TLB-miss bound, 6x slower), so the step kernels gather remote rows with peer loads and scatter updates with
+    system-scope red.add over NVLink / NVSwitch from inside the kernel -- no entity collective;
   * edges: data parallel, each rank trains on its own edge stream (reference: RandomPartition,
     dataloader/sampler.py:256-290), Hogwild across GPUs as the reference is across processes;
   * relation table: replicated; per-relation gradient sums and mean(g^2) sums are all-reduced with
     NCCL every step and every replica applies the identical Adagrad update (the only collective).
 """
 import ctypes as C
+import os
+import socket
 
 import torch
 import torch.distributed as dist
@@ -27,6 +30,34 @@ class _ExternalBuffer:
     def __init__(self, ptr, shape):
         self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False),
                                          "version": 3, "strides": None}
+
+
+def exchange_fds(fds, rank, world, group=None):
+    """Every rank hands its file descriptors to every peer over Unix sockets (SCM_RIGHTS).  Returns
+    {peer_rank: [fd, ...]} for the peers; the caller closes what it receives after mapping."""
+    token = [os.urandom(8).hex() if rank == 0 else None]
+    dist.broadcast_object_list(token, src=0, group=group)
+    name = lambda r: "\0kge_b200_%s_%d" % (token[0], r)                # abstract namespace: nothing to unlink
+    srv = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+    srv.bind(name(rank))
+    srv.listen(world)
+    dist.barrier(group=group)                                          # every rank is listening
+    for peer in range(world):
+        if peer == rank:
+            continue
+        with socket.socket(socket.AF_UNIX, socket.SOCK_STREAM) as c:
+            c.connect(name(peer))
+            socket.send_fds(c, [rank.to_bytes(4, "little")], list(fds))
+    got = {}
+    for _ in range(world - 1):
+        conn, _addr = srv.accept()
+        with conn:
+            msg, rfds, _flags, _a = socket.recv_fds(conn, 4, len(fds))
+            assert len(rfds) == len(fds), "short descriptor message"
+            got[int.from_bytes(msg, "little")] = rfds
+    srv.close()
+    dist.barrier(group=group)
+    return got
 
 
 def shard_rows(num_rows, world, rank):
@@ -54,41 +85,36 @@ class ShardedTrainer:
         per, lo, hi = shard_rows(n_ent, self.world, self.rank)
         assert hi > lo, "more GPUs than entity rows"
         self.n_ent, self.n_rel, self.rows_per_shard, self.row_lo, self.row_hi = n_ent, n_rel, per, lo, hi
-        # local shard: library-owned cudaMalloc (plain allocations are IPC-exportable)
+        # local shard: shareable VMM allocation (kge_shard_alloc); every shard has the size of a full one so that the
+        # importers know it
         n_local = hi - lo
+        emb_bytes, st_bytes = per * De * 4, max(per, 1) * 4
         p_emb, p_st = C.c_void_p(), C.c_void_p()
-        _lib.check(lib.kge_device_alloc(self.h.raw, n_local * De * 4, C.byref(p_emb)))
-        _lib.check(lib.kge_device_alloc(self.h.raw, max(n_local, 1) * 4, C.byref(p_st)))
-        self._owned = (p_emb, p_st)
+        fd_emb, fd_st = C.c_int(-1), C.c_int(-1)
+        _lib.check(lib.kge_shard_alloc(self.h.raw, emb_bytes, C.byref(p_emb), C.byref(fd_emb)))
+        _lib.check(lib.kge_shard_alloc(self.h.raw, st_bytes, C.byref(p_st), C.byref(fd_st)))
+        self._owned = [(p_emb.value, emb_bytes), (p_st.value, st_bytes)]
         self.ent_local = torch.as_tensor(_ExternalBuffer(p_emb.value, (n_local, De)), device=device)
         self.ent_state_local = torch.as_tensor(_ExternalBuffer(p_st.value, (n_local,)), device=device)
         g = torch.Generator(device=device).manual_seed(seed * 1000003 + self.rank)
         self.ent_local.uniform_(-hp.emb_init, hp.emb_init, generator=g)
         self.ent_state_local.zero_()
-        # exchange IPC handles
-        mine = torch.zeros(2, 72, dtype=torch.uint8)
-        for k, ptr in enumerate((p_emb, p_st)):
-            hbuf = C.create_string_buffer(64)
-            off = C.c_int64()
-            _lib.check(lib.kge_ipc_export(self.h.raw, ptr, hbuf, C.byref(off)))
-            mine[k, :64] = torch.frombuffer(bytearray(hbuf.raw), dtype=torch.uint8)
-            mine[k, 64:] = torch.frombuffer(bytearray(int(off.value).to_bytes(8, "little", signed=True)), dtype=torch.uint8)
-        allh = [None] * self.world
-        dist.all_gather_object(allh, mine.numpy().tobytes(), group=group)
+        peers = exchange_fds([fd_emb.value, fd_st.value], self.rank, self.world, group)
+        os.close(fd_emb.value)
+        os.close(fd_st.value)
         emb_ptrs, st_ptrs = [], []
         for r in range(self.world):
             if r == self.rank:
                 emb_ptrs.append(p_emb.value)
                 st_ptrs.append(p_st.value)
                 continue
-            raw = allh[r]
             ptrs = []
-            for k in range(2):
-                rec = raw[k * 72:(k + 1) * 72]
-                off = int.from_bytes(rec[64:72], "little", signed=True)
+            for fd, nbytes in zip(peers[r], (emb_bytes, st_bytes)):
                 out = C.c_void_p()
-                _lib.check(lib.kge_ipc_open(self.h.raw, rec[:64], off, C.byref(out)))
+                _lib.check(lib.kge_shard_import(self.h.raw, fd, nbytes, C.byref(out)))
+                os.close(fd)
                 ptrs.append(out.value)
+                self._owned.append((out.value, nbytes))
             emb_ptrs.append(ptrs[0])
             st_ptrs.append(ptrs[1])
         self.ent = DeviceTable(emb_ptrs, st_ptrs, n_ent, De, devices=list(range(self.world)))
@@ -139,6 +165,16 @@ class ShardedTrainer:
 
     def sync(self):
         torch.cuda.current_stream(self.device).synchronize()
+
+    def close(self):
+        """Unmap the local shard and the peers' (all ranks together: the memory goes when its last mapping does)."""
+        if getattr(self, "_owned", None):
+            self.barrier()
+            self.ent_local = self.ent_state_local = None
+            for ptr, nbytes in self._owned:
+                _lib.check(self.h.lib.kge_shard_free(self.h.raw, ptr, nbytes))
+            self._owned = []
+            self.barrier()
 
     def barrier(self):
         """force_sync_interval analogue (train_pytorch.py:157-159): a cross-GPU barrier."""

@@ -95,6 +95,17 @@ class RESCALScore(_ScoreBase):
         super().__init__(_hyper("RESCAL", entity_dim))
         self.relation_dim, self.entity_dim = relation_dim, entity_dim
 
+    def infer(self, head_emb, rel_emb, tail_emb):
+        """h^T M_r t for every combination (score_fun.py:397-402).  The tail-mode negative path of the reference
+        computes (M_r h).t' = h^T M_r^T t' (score_fun.py:437-447), so the generic route through it would transpose
+        M_r; the head-mode path is (M_r t).h', which IS the edge score: positives = all (rel, tail) pairs,
+        'negatives' = the heads."""
+        nh, nr, nt = head_emb.shape[0], rel_emb.shape[0], tail_emb.shape[0]
+        r = rel_emb.unsqueeze(1).expand(nr, nt, rel_emb.shape[1]).reshape(nr * nt, -1)
+        t = tail_emb.unsqueeze(0).expand(nr, nt, tail_emb.shape[1]).reshape(nr * nt, -1)
+        s = E.score_neg(self.hp, head_emb, r, t, 1, nr * nt, nh, True)
+        return s.reshape(nr, nt, nh).permute(2, 0, 1).contiguous()
+
 
 class RotatEScore(_ScoreBase):
     """gamma - sum_k |h_k e^{i theta_k} - t_k|, theta = r / (emb_init / pi)  (score_fun.py:451-554)"""

@@ -265,6 +265,17 @@ KGE_API int kge_device_alloc(kge_handle_t h, int64_t bytes, void** out);
 KGE_API int kge_device_free(kge_handle_t h, void* p);
 KGE_API int kge_ipc_export(kge_handle_t h, const void* dev_ptr, uint8_t handle_out[64], int64_t* offset_out);
 KGE_API int kge_ipc_open(kge_handle_t h, const uint8_t handle[64], int64_t offset, void** out);
+/* Shard memory for LARGE tables (what dglke_b200.dist uses): CUDA virtual-memory-management allocations, shared between
+ * the ranks as POSIX file descriptors (pass them over a Unix socket, SCM_RIGHTS) and mapped with 2 MiB pages on the owner
+ * and on every peer.  kge_ipc_open maps a peer's cudaMalloc range with small pages, and random row reads over a shard of
+ * tens of GB then miss the reader's TLB on every row (measured 340 us vs 60 us per 14 800 rows, tools/peer_gather_probe.py).
+ *   kge_shard_alloc   allocate `bytes` (rounded up to the mapping granularity) on the handle's device, map it read/write,
+ *                     return the pointer and a file descriptor the caller passes to peers and then close()s
+ *   kge_shard_import  map the allocation behind a received descriptor read/write on the handle's device (same `bytes`)
+ *   kge_shard_free    unmap (owner or importer side); the memory is released when the last mapping and descriptor go */
+KGE_API int kge_shard_alloc(kge_handle_t h, int64_t bytes, void** out, int* fd_out);
+KGE_API int kge_shard_import(kge_handle_t h, int fd, int64_t bytes, void** out);
+KGE_API int kge_shard_free(kge_handle_t h, void* ptr, int64_t bytes);
 
 #ifdef __cplusplus
 }

@@ -91,6 +91,26 @@ def test_infer_all_pairs():
     np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=1e-5, atol=1e-6)
 
 
+@pytest.mark.parametrize("model,de", [("TransE_l1", False), ("TransE_l2", False), ("DistMult", False), ("ComplEx", False),
+                                      ("RESCAL", False), ("RotatE", True)])
+def test_infer_equals_edge_func(model, de):
+    """infer(h, r, t)[i, j, k] is the edge score of (h_i, r_j, t_k) for every model -- in particular RESCAL, whose
+    tail-mode negative path transposes M_r (score_fun.py:397-402 vs :437-447)."""
+    from dglke_b200.general_models import KEModel
+    m = KEModel(_args(), model, 60, 5, 32 if model != "RotatE" else 16, 12.0, double_entity_emb=de)
+    h, r, t = m.entity_emb.emb[:4].contiguous(), m.relation_emb.emb[:3].contiguous(), m.entity_emb.emb[20:28].contiguous()
+    got = m.score_func.infer(h, r, t)
+    assert tuple(got.shape) == (4, 3, 8)
+    ii, jj, kk = th.meshgrid(th.arange(4), th.arange(3), th.arange(8), indexing="ij")
+
+    class Edges:
+        src = {"emb": h[ii.reshape(-1).to(h.device)].contiguous()}
+        data = {"emb": r[jj.reshape(-1).to(h.device)].contiguous()}
+        dst = {"emb": t[kk.reshape(-1).to(h.device)].contiguous()}
+    want = m.score_func.edge_func(Edges)["score"].reshape(4, 3, 8)
+    np.testing.assert_allclose(got.cpu().numpy(), want.cpu().numpy(), rtol=1e-5, atol=1e-5)
+
+
 def test_forward_test_ranks_match_oracle():
     from dglke_b200.general_models import KEModel
     from dglke_b200.graph import eval_batches
