@@ -59,6 +59,8 @@ def parse():
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS),
                     help="default: fb15k_transe_l2 (BASELINE configs[1]) on one GPU, freebase_transe_l2 (the 86 M-entity "
                          "HBM-resident table north_star's scaling target names) on several; the other one is measured beside it")
+    ap.add_argument("--no-pipeline", action="store_true",
+                    help="N>1: do not announce the next batch (no row prefetch by the fused kernels; every step gathers its own rows)")
     ap.add_argument("--no-beside", action="store_true", help="skip the second (beside) workload of a default run")
     ap.add_argument("--batch", type=int, default=0, help="edges per step per GPU (0 = workload default)")
     ap.add_argument("--n-ent", type=int, default=0, help="override the entity count (capacity experiments)")
@@ -289,15 +291,28 @@ def measure(args, workload, rank, world, local_rank, dev, cpu_base, K_steps, ful
     Cs = sampler.chunk_size
     h2d = sum(t.numel() * 8 for t in host[0][0])
 
+    pipelined = world > 1 and not args.no_pipeline
+
     def step_dev(k):
         b, nh = devb[k % NB]
         if world == 1:
             return eng.step(b[0], b[1], b[2], b[3], b[4], Cs, neg, nh, head_ids=b[5], tail_ids=b[6])
-        return eng.step(b[0], b[1], b[2], b[3], b[4], Cs, neg, nh)
+        nxt = devb[(k + 1) % NB][0]
+        return eng.step(b[0], b[1], b[2], b[3], b[4], Cs, neg, nh, next_batch=(nxt[0], nxt[4]) if pipelined else None)
 
     def step_host(k):
         b, nh = host[k % NB]
-        return eng.step_host(b[0], b[1], b[2], b[3], b[4], Cs, neg, nh)
+        if world == 1:
+            return eng.step_host(b[0], b[1], b[2], b[3], b[4], Cs, neg, nh)
+        return eng.step_host(b[0], b[1], b[2], b[3], b[4], Cs, neg, nh, next_host=host[(k + 1) % NB][0] if pipelined else None)
+
+    def prime():
+        """(pipelined) every measured sequence starts at batch 0: forget whatever an earlier sequence staged and run
+        the step before it, whose fused kernels fetch batch 0's rows"""
+        if pipelined:
+            eng.eng.announce_next(None)
+            step_dev(NB - 1)
+            torch.cuda.synchronize()
 
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
@@ -315,6 +330,7 @@ def measure(args, workload, rank, world, local_rank, dev, cpu_base, K_steps, ful
     for k in range(W):
         step_dev(k)
     torch.cuda.synchronize()
+    prime()
 
     # ---- CUDA graphs of the device-resident step (one per batch): no launch gaps inside a step ----
     graphs = None
@@ -338,6 +354,7 @@ def measure(args, workload, rank, world, local_rank, dev, cpu_base, K_steps, ful
 
     def timed(run_step, after=None):
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        prime()
         barrier()
         for k in range(K):
             flush()
@@ -361,6 +378,7 @@ def measure(args, workload, rank, world, local_rank, dev, cpu_base, K_steps, ful
     clocks = clk.stop() if clk else None
 
     # launches per step, counted from one eager step
+    prime()
     c0 = eng.h.launch_count()
     step_dev(0)
     torch.cuda.synchronize()
@@ -371,6 +389,7 @@ def measure(args, workload, rank, world, local_rank, dev, cpu_base, K_steps, ful
     ms_e2e = timed(step_host, after=eng.sync)
 
     # ---- per-kernel device time of one step (CUDA events around every launch, L2 flushed) --------
+    prime()
     eng.h.profile_enable(True)
     prof = {}
     nprof = 5
@@ -424,6 +443,8 @@ def measure(args, workload, rank, world, local_rank, dev, cpu_base, K_steps, ful
                    "l2": "cold: 256 MiB written between timed steps" if not args.no_flush else "warm (no flush)",
                    "launch": "one CUDA graph per step" if used_graph else "eager launches",
                    "sampling": "excluded (pre-generated seeded batches), as on the reference arm",
+                   "pipeline": ("next batch announced: its rows are fetched over NVLink by this step's fused kernels (entity reads "
+                                "lag the updates by one step, as under the reference's --async_update)") if pipelined else "none",
                    "arithmetic": "fp32 rows; contractions on tcgen05 as 3xTF32 (hi/lo split) with fp32 accumulation" if model in ("TransE_l2", "DistMult", "ComplEx", "RESCAL") else "fp32 CUDA-core tiles",
                    "bytes_per_edge": bpe},
         "e2e": {"value": e2e, "unit": "edges/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 16,

@@ -64,6 +64,19 @@ struct kge_context {
   float* ext_rg = nullptr;           // deferred relation mode: caller-owned dense buffers [n_rel * Dr], [n_rel] that k_chain sums
   float* ext_rgs = nullptr;          //   the relation gradients into (all-reduced by the caller, kge_set_relation_buffers)
   float* dump_v = nullptr;           // test hook (kge_debug_set_dump): coefficient matrices of the fused kernel
+  // kge_set_next_batch: rows of the next step staged by this step's fused kernels
+  struct Prefetch {
+    bool armed = false;              // a next batch is registered for the coming kge_step_fused_begin
+    kge_batch_t next{};
+    long long next_nneg = 0;
+    bool ready = false;              // the previous begin staged rows for the batch described by r_*
+    const void *r_nodes = nullptr, *r_negs = nullptr, *r_nU_dev = nullptr;
+    long long r_nU = 0, r_nneg = 0;
+    int r_buf = 0;                   // which nc[] holds them
+    float* nc[2] = {nullptr, nullptr};
+    float* bn = nullptr;
+    size_t nc_floats = 0, bn_floats = 0;
+  } pf;
   int fused_mode = -1;               // -1 default (fused kernel whenever the shape allows), 0 off
   size_t stage_bytes = 0;
   float* dev_log4 = nullptr;
@@ -300,7 +313,7 @@ int umma_grad(const LaunchCtx&, const StepParams&, const StepWs&, bool side_b, c
 // fused contraction (kge_fused.cu): mode 0 = P (scores, loss, GA), mode 1 = N (G_neg, mean squares)
 bool fused_supported(const StepParams&);
 int fused_launch(const LaunchCtx&, const StepParams&, const StepWs&, int mode, const float* wt, float* dumpS, float* dumpV,
-                 const TableView* ent, const long long* neg_ids, char* err, size_t errlen);
+                 const TableView* ent, const long long* neg_ids, const FusedPrefetch* pf, char* err, size_t errlen);
 }  // namespace kge
 
 extern "C" {
@@ -562,15 +575,66 @@ static int forward_backward_impl(kge_handle_t h, const kge_step_cfg_t* cfg, cons
   LaunchCtx c = lctx(h, stream);
   BatchView b = bview(batch);
   ensure_ng_zero(h, p, w, c, false);
-  if (p.use_nc) launch_gather_nodes(c, p, ve, b, w);      // pos_g.ndata['emb'] = entity_emb(pos_g.ndata['id'])  (general_models.py:548)
+  // rows staged by the previous step's prefetch warps (kge_set_next_batch) replace this step's gathers -- only for
+  // exactly the batch that was announced
+  auto& pf = h->pf;
+  float* const arena_nc = w.NC;
+  if (pf.ready) {
+    const bool match = fused_step && p.fused && p.use_nc && pf.r_nodes == batch->node_ids && pf.r_negs == batch->neg_ids &&
+                       pf.r_nU == batch->n_nodes && pf.r_nU_dev == (batch->n_nodes < 0 ? batch->n_nodes_dev : nullptr) &&
+                       pf.r_nneg == p.Nn;
+    pf.ready = false;
+    if (match) { w.NC = pf.nc[pf.r_buf]; w.BnRaw = pf.bn; p.nc_staged = 1; }
+  }
+  const FusedPrefetch* pfp = nullptr;
+  FusedPrefetch pfa{};
+  if (pf.armed) {
+    pf.armed = false;
+    const long long ncap = 2 * p.B;
+    const long long nU = pf.next.n_nodes < 0 ? ncap : pf.next.n_nodes;
+    if (fused_step && p.fused && p.use_nc && nU <= ncap && pf.next_nneg > 0 &&
+        fused_prefetch_slots(p, 0) >= 2 && fused_prefetch_slots(p, 1) >= 2) {
+      const size_t ncf = (size_t)ncap * p.D, bnf = (size_t)pf.next_nneg * p.D;
+      if (ncf > pf.nc_floats || bnf > pf.bn_floats) {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing((cudaStream_t)stream, &cs);
+        if (cs != cudaStreamCaptureStatusNone)
+          return fail(KGE_ERR_INVALID_ARG, "kge_set_next_batch: the staging buffers must exist before stream capture (run one eager step first)");
+        KGE_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
+        for (int i = 0; i < 2; ++i) { if (pf.nc[i]) cudaFree(pf.nc[i]); pf.nc[i] = nullptr; }
+        if (pf.bn) cudaFree(pf.bn);
+        pf.bn = nullptr; pf.nc_floats = pf.bn_floats = 0;
+        if (cudaMalloc(&pf.nc[0], ncf * 4) != cudaSuccess || cudaMalloc(&pf.nc[1], ncf * 4) != cudaSuccess ||
+            cudaMalloc(&pf.bn, bnf * 4) != cudaSuccess) {
+          cudaGetLastError();
+          return fail(KGE_ERR_NOMEM, "prefetch staging buffers (%zu MB)", (2 * ncf + bnf) * 4 >> 20);
+        }
+        pf.nc_floats = ncf; pf.bn_floats = bnf;
+        w.BnRaw = nullptr; w.NC = arena_nc; p.nc_staged = 0;      // whatever was staged is gone with the old buffers
+      }
+      const int tgt = p.nc_staged ? (pf.r_buf ^ 1) : 0;
+      pfa.node_ids = (const long long*)pf.next.node_ids;
+      pfa.nU_dev = pf.next.n_nodes < 0 ? (const long long*)pf.next.n_nodes_dev : nullptr;
+      pfa.nU = nU;
+      pfa.neg_ids = (const long long*)pf.next.neg_ids;
+      pfa.nNeg = pf.next_nneg;
+      pfa.nc = pf.nc[tgt]; pfa.bn = pf.bn;
+      pfp = &pfa;
+      pf.ready = true;
+      pf.r_nodes = pf.next.node_ids; pf.r_negs = pf.next.neg_ids; pf.r_nU = pf.next.n_nodes;
+      pf.r_nU_dev = pf.next.n_nodes < 0 ? pf.next.n_nodes_dev : nullptr;
+      pf.r_nneg = pf.next_nneg; pf.r_buf = tgt;
+    }
+  }
+  if (p.use_nc && !p.nc_staged) launch_gather_nodes(c, p, ve, b, w);      // pos_g.ndata['emb'] = entity_emb(pos_g.ndata['id'])  (general_models.py:548)
   if (p.model == KGE_RESCAL) launch_rescal_prep(c, p, ve, vr, b, w);
   else launch_prep(c, p, ve, vr, b, w);
   float* logdst = log4 ? log4 : h->dev_log4;
   if (p.fused) {
     launch_wbar(c, p, b.edge_weight, w);
-    if ((rc = fused_launch(c, p, w, 0, b.edge_weight, fused_step ? nullptr : w.S, h->dump_v, &ve, b.neg_ids, g_err, sizeof(g_err)))) return rc;
+    if ((rc = fused_launch(c, p, w, 0, b.edge_weight, fused_step ? nullptr : w.S, h->dump_v, &ve, b.neg_ids, pfp, g_err, sizeof(g_err)))) return rc;
     if ((rc = fused_launch(c, p, w, 1, b.edge_weight, nullptr,
-                           h->dump_v ? h->dump_v + (size_t)p.B * p.Ns : nullptr, &ve, b.neg_ids, g_err, sizeof(g_err)))) return rc;
+                           h->dump_v ? h->dump_v + (size_t)p.B * p.Ns : nullptr, &ve, b.neg_ids, pfp, g_err, sizeof(g_err)))) return rc;
   } else {
     if ((rc = run_score(h, c, p, w))) return rc;
     launch_wbar(c, p, b.edge_weight, w);
@@ -642,6 +706,19 @@ KGE_API int kge_step_fused_end(kge_handle_t h, const kge_step_cfg_t* cfg, const 
                        const kge_batch_t* batch, float* log4, void* stream) {
   if (!h) return fail(KGE_ERR_INVALID_ARG, "handle is null");
   return update_impl(h, cfg, ent, rel, batch, log4 ? log4 : h->dev_log4, stream);
+}
+
+// Announce the batch of the NEXT kge_step_fused_begin: its table rows are copied by the spare warps of this step's fused
+// kernels (sharded tables: the NVLink latency of step k+1 hides behind the tensor-core work of step k).
+KGE_API int kge_set_next_batch(kge_handle_t h, const kge_batch_t* next, int64_t n_neg) {
+  if (!h) return fail(KGE_ERR_INVALID_ARG, "handle is null");
+  if (!next) { h->pf.armed = false; h->pf.ready = false; return KGE_OK; }      // also drops rows already staged
+  if (!next->node_ids || !next->neg_ids || n_neg <= 0 || (next->n_nodes < 0 && !next->n_nodes_dev) || next->n_nodes == 0)
+    return fail(KGE_ERR_INVALID_ARG, "kge_set_next_batch: node_ids / neg_ids / counts missing");
+  h->pf.next = *next;
+  h->pf.next_nneg = n_neg;
+  h->pf.armed = true;
+  return KGE_OK;
 }
 
 // Fused schedule (one GPU, supported shape): k_prep -> k_fused<P> -> k_fused<N> -> k_chain -> k_update = 5 launches.

@@ -53,7 +53,11 @@ struct StepParams {
   int rel_dense;     // 1: k_chain sums relation gradients per relation into ws.rg / ws.rgs (fused single-GPU step)
   int use_nc;        // 1: head/tail rows are read from the gathered copy NC (3-call API, sharded tables); 0: from the table
   int fused;         // 1: contraction by the fused tcgen05 kernel (kge_fused.cu): operands exist only as TF32 hi/lo slabs
+  int nc_staged;     // 1: NC was filled by the previous step's prefetch warps (kge_set_next_batch): no k_gather_nodes ran
 };
+
+// who produces the unique nodes' share of the regulariser: k_gather_nodes when it runs, else the node update
+__host__ __device__ __forceinline__ bool node_reg_in_update(const StepParams& p) { return !p.use_nc || p.nc_staged; }
 
 // Device workspace of one step (all pointers into the handle's arena).
 struct StepWs {
@@ -83,6 +87,7 @@ struct StepWs {
   float* stat_k;   // [B]      w_i / (2B den_i)                    (fused kernel: mode P -> mode N)
   float* rg;       // [n_rel, Dr] dense per-relation gradient sums (rel_dense), zero between steps
   float* rgs;      // [n_rel]     dense per-relation sums of mean(g^2)          , zero between steps
+  const float* BnRaw;         // [Nn, D] negative rows staged by the previous step's prefetch warps, or null
   unsigned int* sync_ctr;     // [4] grid-barrier counters of k_update (zero between launches)
   float* red_partial;         // [64 * 3] partial sums of k_reduce_log
   unsigned int* red_ticket;   // [1] completion ticket of k_reduce_log (zero between launches)
@@ -335,6 +340,17 @@ void launch_sampler(const LaunchCtx&, const SamplerParams&, long long step);
 
 void launch_gather(const LaunchCtx&, const TableView& t, const long long* idx, long long n, float* out);
 void launch_gather_nodes(const LaunchCtx&, const StepParams&, const TableView& ent, const BatchView&, const StepWs&);
+// Rows of the NEXT step that the fused kernel's spare warps copy while it computes (kge_set_next_batch)
+struct FusedPrefetch {
+  const long long* node_ids;   // next batch's unique nodes
+  const long long* nU_dev;     // their count on the device, or null
+  long long nU;                // their count (capacity when nU_dev is set)
+  const long long* neg_ids;
+  long long nNeg;
+  float* nc;                   // [nU, D] destination of the node rows
+  float* bn;                   // [nNeg, D] destination of the negative rows
+};
+int fused_prefetch_slots(const StepParams& p, int mode);   // row slots per prefetch warp the shape leaves room for (< 2: none)
 void launch_prep(const LaunchCtx&, const StepParams&, const TableView& ent, const TableView& rel,
                  const BatchView&, const StepWs&);
 // dense-row variant used by kge_score_pos / kge_score_neg (rows already gathered)

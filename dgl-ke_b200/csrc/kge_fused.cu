@@ -38,6 +38,7 @@ constexpr int kTileM = 128;
 constexpr int kThreadsF = 384;                    // warps 0-7 epilogue (two warpgroups), 8 TMA producer, 9 MMA issuer, 10-11 idle
 constexpr int kProducerWarp = 8, kMmaWarp = 9;
 constexpr int kMaxS1 = 4, kMaxS2 = 8;
+constexpr int kMaxPf = 8;                          // row slots per prefetch warp
 constexpr uint32_t kRingBytes = 192 * 1024;
 constexpr int kStagePitch = 20;                      // floats per row of an epilogue staging tile (16 + 4 pad, 16-byte aligned rows)
 constexpr uint32_t kEpiStageBytes = 8 * 32 * kStagePitch * 4;   // one 32 x 16 tile per epilogue warp
@@ -74,6 +75,18 @@ struct FusedArgs {
   TableView xtab;          //   (one fp32 load instead of hi + lo; nothing updates the table before k_update)
   float* gsn;            // [C*Rx] mean(G_neg^2)
   float* out;            // P: GA [C*Rx, D]; N: G_neg [C*Rx, D]
+  // next step's rows, copied by the two spare warps while this step's tiles are computed (sharded tables: the remote-row
+  // latency of step k+1 hides behind the tensor-core work of step k).  Virtual row v of [nodes | negatives]; this launch
+  // takes the v with v % 2 == pf_parity (the P and the N kernel split the list).
+  int pf_slots;                    // row slots per warp (0 = no prefetch), carved from the ring behind the GEMM stages
+  int pf_parity;
+  uint32_t pf_off, pf_row_bytes;
+  const long long* pf_node_ids;    // next batch's unique nodes
+  const long long* pf_nU_dev;      // their count on the device, or null
+  long long pf_nU, pf_nNeg;
+  const long long* pf_neg_ids;
+  float* pf_nc;                    // [nU, D] destination of the node rows (the next step's NC)
+  float* pf_bn;                    // [nNeg, D] destination of the negative rows
   unsigned long long* dbg;   // optional per-CTA timestamps of the first tile (KGE_B200_FUSED_TIMING=1)
   int exp_halfload;          // experiment (KGE_B200_FUSED_HALFLOAD): skip the TMA loads of the lo tiles (WRONG results;
                              // shows how much of the GEMM time is operand traffic)
@@ -100,6 +113,7 @@ k_fused(const __grid_constant__ CUtensorMap mXh, const __grid_constant__ CUtenso
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full1[kMaxS1], empty1[kMaxS1], full2[kMaxS2], empty2[kMaxS2];
   __shared__ __align__(8) uint64_t s_full, v_ready, acc_full, acc_empty;
+  __shared__ __align__(8) uint64_t pf_full[2][kMaxPf];
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(16) float colA[256], colB[256], colC[256];
   __shared__ float xch[4][2][kTileM];
@@ -123,6 +137,7 @@ k_fused(const __grid_constant__ CUtensorMap mXh, const __grid_constant__ CUtenso
     for (int s = 0; s < kMaxS1; ++s) { mbar_init(&full1[s], 1); mbar_init(&empty1[s], 1); }
     for (int s = 0; s < kMaxS2; ++s) { mbar_init(&full2[s], 1); mbar_init(&empty2[s], 1); }
     mbar_init(&s_full, 1); mbar_init(&v_ready, 8); mbar_init(&acc_full, 1); mbar_init(&acc_empty, 8);
+    for (int s = 0; s < kMaxPf; ++s) { mbar_init(&pf_full[0][s], 1); mbar_init(&pf_full[1][s], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kProducerWarp && lane == 0) {
@@ -270,6 +285,36 @@ k_fused(const __grid_constant__ CUtensorMap mXh, const __grid_constant__ CUtenso
         }
       }
     }
+  } else if (g.pf_slots > 0 && lane == 0) {
+    // ================================ prefetch warps 10, 11 ================================
+    // One lane per warp streams table rows (peer memory when the table is sharded) through a few shared-memory slots into
+    // the next step's buffers: bulk load -> mbarrier -> bulk store.  Slot of item k-1 is re-loaded with item k-1+S once the
+    // store of item k-1 has finished reading it, so S-1 loads are always in flight.
+    const int w = warp - 10, S = g.pf_slots;
+    const long long nU = g.pf_nU_dev ? *g.pf_nU_dev : g.pf_nU;
+    const long long total = nU + g.pf_nNeg;
+    const long long nhalf = total > g.pf_parity ? (total - g.pf_parity + 1) / 2 : 0;   // v = parity + 2 j < total
+    const long long stride = 2ll * gridDim.x, j0 = 2ll * blockIdx.x + w;
+    const long long n = j0 < nhalf ? (nhalf - j0 + stride - 1) / stride : 0;
+    uint8_t* slots = ring + g.pf_off + (size_t)w * S * g.pf_row_bytes;
+    auto load = [&](long long k) {
+      const long long v = g.pf_parity + 2 * (j0 + k * stride);
+      const long long id = v < nU ? g.pf_node_ids[v] : g.pf_neg_ids[v - nU];
+      const int s = (int)(k % S);
+      mbar_expect_tx(&pf_full[w][s], g.pf_row_bytes);
+      bulk_g2s(slots + (size_t)s * g.pf_row_bytes, row_ptr(g.xtab, id), g.pf_row_bytes, &pf_full[w][s]);
+    };
+    for (long long k = 0; k < n && k < S; ++k) load(k);
+    for (long long k = 0; k < n; ++k) {
+      const int s = (int)(k % S);
+      mbar_wait(&pf_full[w][s], (uint32_t)((k / S) & 1));
+      const long long v = g.pf_parity + 2 * (j0 + k * stride);
+      float* dst = v < nU ? g.pf_nc + v * (long long)g.D : g.pf_bn + (v - nU) * (long long)g.D;
+      bulk_s2g(dst, slots + (size_t)s * g.pf_row_bytes, g.pf_row_bytes);
+      bulk_commit();
+      if (k >= 1 && k - 1 + S < n) { bulk_wait_read<1>(); load(k - 1 + S); }
+    }
+    bulk_wait_all();
   }
   } else {
     // ================================ epilogue warps 0..7 ================================
@@ -641,26 +686,61 @@ bool fused_supported(const StepParams& p) {
 }
 
 // mode 0 (P): S = A.Bn^T -> loss, coefficients -> GA;  mode 1 (N): S^T -> coefficients -> G_neg (+ mean square)
+namespace {
+// GEMM stage geometry of one mode + what the ring leaves for prefetch row slots
+struct Geometry { int Rx, Ry, N1, Wc, nS1, nS2, pf_slots; uint32_t stage1Bytes, stage2Bytes, pf_off; bool ok; };
+Geometry geometry(const StepParams& p, int mode, bool want_prefetch) {
+  Geometry q{};
+  const bool P = mode == 0;
+  q.Rx = P ? p.Cs : p.Ns; q.Ry = P ? p.Ns : p.Cs;
+  q.N1 = pad16(q.Ry);
+  int wc = (512 - 2 * q.N1) & ~31;
+  if (wc > 256) wc = 256;
+  const int dpad = (p.D + 31) & ~31;
+  if (wc > dpad) wc = dpad;
+  q.Wc = wc;
+  q.stage1Bytes = 2u * 16384u + 2u * (uint32_t)q.N1 * 128u;
+  q.stage2Bytes = 2u * (uint32_t)(wc >> 5) * 4096u;
+  q.nS1 = (int)(kRingBytes / q.stage1Bytes); if (q.nS1 > kMaxS1) q.nS1 = kMaxS1;
+  q.nS2 = (int)(kRingBytes / q.stage2Bytes); if (q.nS2 > kMaxS2) q.nS2 = kMaxS2;
+  q.ok = q.nS1 >= 2 && q.nS2 >= 2 && wc >= 32;
+  if (q.ok && want_prefetch) {
+    // GEMM1 keeps its stages; GEMM2 gives up stages (never below 4) until both prefetch warps have kMaxPf row slots
+    const uint32_t row = (uint32_t)p.D * 4u;
+    int nS2 = q.nS2;
+    uint32_t used = (uint32_t)q.nS1 * q.stage1Bytes;
+    uint32_t want = 2u * kMaxPf * row;
+    if (want > kRingBytes - used) want = kRingBytes - used;           // never more than GEMM1 leaves
+    while (nS2 > 4 && kRingBytes - (uint32_t)nS2 * q.stage2Bytes < want) --nS2;
+    if ((uint32_t)nS2 * q.stage2Bytes > used) used = (uint32_t)nS2 * q.stage2Bytes;
+    int slots = (int)((kRingBytes - used) / (2u * row));
+    if (slots > kMaxPf) slots = kMaxPf;
+    if (slots >= 2) { q.pf_slots = slots; q.nS2 = nS2; q.pf_off = used; }
+  }
+  return q;
+}
+}  // namespace
+
+int fused_prefetch_slots(const StepParams& p, int mode) { return geometry(p, mode, true).pf_slots; }
+
 int fused_launch(const LaunchCtx& c, const StepParams& p, const StepWs& w, int mode, const float* wt, float* dumpS,
-                 float* dumpV, const TableView* ent, const long long* neg_ids, char* err, size_t errlen) {
+                 float* dumpV, const TableView* ent, const long long* neg_ids, const FusedPrefetch* pf, char* err, size_t errlen) {
   FusedArgs g{};
   g.model = p.model; g.adversarial = p.adversarial;
   g.gamma = p.gamma; g.Tl2e = p.adv_temperature * kLog2e; g.inv2B = 0.5f / (float)p.B; g.uni = 1.f / (float)p.Ns;
   g.reg_coef = p.reg_coef; g.reg_norm = p.reg_norm;
   g.C = p.C; g.D = p.D; g.nblkD = slab_blocks(p.D);
   const bool P = mode == 0;
-  g.Rx = P ? p.Cs : p.Ns; g.Ry = P ? p.Ns : p.Cs;
-  g.N1 = pad16(g.Ry);
-  int wc = (512 - 2 * g.N1) & ~31;
-  if (wc > 256) wc = 256;
-  const int dpad = (p.D + 31) & ~31;
-  if (wc > dpad) wc = dpad;
-  g.Wc = wc;
-  g.stage1Bytes = 2u * 16384u + 2u * (uint32_t)g.N1 * 128u;
-  g.stage2Bytes = 2u * (uint32_t)(wc >> 5) * 4096u;
-  g.nS1 = (int)(kRingBytes / g.stage1Bytes); if (g.nS1 > kMaxS1) g.nS1 = kMaxS1;
-  g.nS2 = (int)(kRingBytes / g.stage2Bytes); if (g.nS2 > kMaxS2) g.nS2 = kMaxS2;
-  if (g.nS1 < 2 || g.nS2 < 2 || wc < 32) { snprintf(err, errlen, "fused kernel: shape does not fit (N1=%d)", g.N1); return KGE_ERR_UNSUPPORTED; }
+  const Geometry q = geometry(p, mode, pf != nullptr && ent != nullptr);
+  if (!q.ok) { snprintf(err, errlen, "fused kernel: shape does not fit (N1=%d)", q.N1); return KGE_ERR_UNSUPPORTED; }
+  g.Rx = q.Rx; g.Ry = q.Ry; g.N1 = q.N1; g.Wc = q.Wc; g.nS1 = q.nS1; g.nS2 = q.nS2;
+  g.stage1Bytes = q.stage1Bytes; g.stage2Bytes = q.stage2Bytes;
+  if (pf && ent && q.pf_slots >= 2) {
+    g.pf_slots = q.pf_slots; g.pf_off = q.pf_off; g.pf_row_bytes = (uint32_t)p.D * 4u; g.pf_parity = mode;
+    g.pf_node_ids = pf->node_ids; g.pf_nU_dev = pf->nU_dev; g.pf_nU = pf->nU; g.pf_nNeg = pf->nNeg;
+    g.pf_neg_ids = pf->neg_ids; g.pf_nc = pf->nc; g.pf_bn = pf->bn;
+    g.xtab = *ent;
+  }
   const float *Xh = P ? w.Ahi : w.Bhi, *Xl = P ? w.Alo : w.Blo, *Yh = P ? w.Bhi : w.Ahi, *Yl = P ? w.Blo : w.Alo;
   g.x2 = P ? w.a2 : w.b2; g.y2 = P ? w.b2 : w.a2;
   g.pos = w.pos; g.wt = wt; g.wbar = w.wbar;

@@ -203,8 +203,8 @@ __global__ void __launch_bounds__(kRowBlock) k_prep(StepParams p, TableView ent,
   }
   job -= p.B;
   if (job < p.Nn) {
-    const float* src = row_ptr(ent, b.neg_ids[job]);
     const long long ro = job * (long long)p.D;
+    const float* src = w.BnRaw ? w.BnRaw + ro : row_ptr(ent, b.neg_ids[job]);   // staged by the previous step, or the table
     // fused contraction: the negatives exist only as TF32 hi/lo slabs (Bn receives their gradient later)
     const RowOut bo{p.fused ? nullptr : w.Bn + ro, w.Bhi, w.Blo, job / p.Ns, slab_blocks(p.D), p.Ns, (int)(job % p.Ns)};
     float b2 = 0.f, reg = 0.f;
@@ -791,10 +791,10 @@ __device__ __forceinline__ void upd_node(const StepParams& p, const TableView& e
     for (int q = 0; q < 4; ++q) {
       gq[q] = f4_add(gq[q], reg_grad4(x[q], p.reg_norm, p.reg_coef));     // padding lanes: 0 + reg'(0) = 0
       gs += f4_dot(gq[q], gq[q]);
-      if (reg_on && !p.use_nc) reg += abs_pow4_sum(x[q], p.reg_norm);
+      if (reg_on && node_reg_in_update(p)) reg += abs_pow4_sum(x[q], p.reg_norm);
     }
     gs = warp_sum(gs) / (float)p.D;
-    if (!p.use_nc) {            // no k_gather_nodes ran: this node's share of the regulariser is produced here
+    if (node_reg_in_update(p)) {            // no k_gather_nodes ran: this node's share of the regulariser is produced here
       reg = warp_sum(reg);
       if (lane == 0) w.regp[p.B + p.Nn + u] = reg;
     }
@@ -823,10 +823,10 @@ __device__ __forceinline__ void upd_node(const StepParams& p, const TableView& e
     const float4 x = ld4(nc + 4 * v);
     float4 g = f4_add(ld4(ng + 4 * v), reg_grad4(x, p.reg_norm, p.reg_coef));
     gs += f4_dot(g, g);
-    if (reg_on && !p.use_nc) reg += abs_pow4_sum(x, p.reg_norm);
+    if (reg_on && node_reg_in_update(p)) reg += abs_pow4_sum(x, p.reg_norm);
   }
   gs = warp_sum(gs) / (float)p.D;
-  if (!p.use_nc) {            // no k_gather_nodes ran: this node's share of the regulariser is produced here
+  if (node_reg_in_update(p)) {            // no k_gather_nodes ran: this node's share of the regulariser is produced here
     reg = warp_sum(reg);
     if (lane == 0) w.regp[p.B + p.Nn + u] = reg;
   }

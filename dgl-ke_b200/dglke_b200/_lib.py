@@ -20,7 +20,8 @@ EXPORTS = ["kge_abi_version", "kge_last_error", "kge_create", "kge_destroy", "kg
            "kge_step_fused", "kge_step_fused_begin", "kge_step_fused_end", "kge_step_fused_host", "kge_sync", "kge_debug_read", "kge_launch_count",
            "kge_set_engine", "kge_set_fused", "kge_debug_set_dump", "kge_profile_enable", "kge_profile_read", "kge_set_relation_mode", "kge_set_relation_buffers",
            "kge_rel_grad_dense", "kge_rel_apply_dense", "kge_device_alloc", "kge_device_free", "kge_ipc_export",
-           "kge_ipc_open", "kge_shard_alloc", "kge_shard_import", "kge_shard_free", "kge_sampler_create", "kge_sampler_destroy", "kge_sampler_sample"]
+           "kge_ipc_open", "kge_shard_alloc", "kge_shard_import", "kge_shard_free",
+           "kge_set_next_batch", "kge_sampler_create", "kge_sampler_destroy", "kge_sampler_sample"]
 
 
 class KgeError(RuntimeError):
@@ -101,6 +102,7 @@ def load_library():
     lib.kge_shard_alloc.argtypes = [vp, i64, P(vp), P(C.c_int)]
     lib.kge_shard_import.argtypes = [vp, C.c_int, i64, P(vp)]
     lib.kge_shard_free.argtypes = [vp, vp, i64]
+    lib.kge_set_next_batch.argtypes = [vp, P(Batch), i64]
     lib.kge_sampler_create.argtypes = [vp, vp, vp, vp, i64, i64, i64, i32, C.c_uint64, P(vp)]
     lib.kge_sampler_destroy.argtypes = [vp]
     lib.kge_sampler_sample.argtypes = [vp, i64, P(Batch), P(i32), vp]

@@ -137,14 +137,18 @@ class ShardedTrainer:
 
     # -- one training step: forward/backward, entity Adagrad over NVLink, relation all-reduce + apply
     def step(self, node_ids, head_local=None, tail_local=None, rel_ids=None, neg_ids=None, chunk_size=None,
-             neg_sample_size=None, neg_head=None, edge_weight=None, log4=None, sync_between=False):
+             neg_sample_size=None, neg_head=None, edge_weight=None, log4=None, sync_between=False, next_batch=None):
         """sync_between (tests): a cross-rank barrier between the gradient half and the update half, so that every
-        rank's gradients come from the same table snapshot."""
+        rank's gradients come from the same table snapshot.
+        next_batch (--async_update): the batch of the NEXT call (DeviceBatch or (node_ids, neg_ids)); its rows are
+        fetched over NVLink by this step's fused kernels while they compute, so the next step starts without a gather --
+        and reads rows that may lag this step's updates by one step, the staleness the reference's async update has."""
         lib, h = self.h.lib, self.h
         # gather (peer loads) .. k_chain: per-relation gradient sums land in rbuf
         # (node_ids may be a sampler.DeviceBatch: the indices then never visit the host)
         self.eng.step_begin(node_ids, head_local, tail_local, rel_ids, neg_ids, chunk_size=chunk_size,
-                            neg_sample_size=neg_sample_size, neg_head=neg_head, edge_weight=edge_weight)
+                            neg_sample_size=neg_sample_size, neg_head=neg_head, edge_weight=edge_weight,
+                            next_batch=next_batch)
         # the relation all-reduce (NCCL stream) overlaps the entity Adagrad kernel, which does not touch rbuf
         if sync_between:
             self.barrier()
@@ -156,10 +160,22 @@ class ShardedTrainer:
         return out
 
     def step_host(self, node_ids, head_local, tail_local, rel_ids, neg_ids, chunk_size, neg_sample_size, neg_head,
-                  edge_weight=None):
+                  edge_weight=None, next_host=None):
+        """Host index tensors.  next_host = the NEXT call's (node_ids, head_local, tail_local, rel_ids, neg_ids): they
+        are uploaded now (one batch of indices crosses PCIe per step either way) and announced to the library, whose
+        fused kernels then fetch that batch's rows while this step computes."""
         d = lambda t: t.to(self.device, non_blocking=True)
-        out = self.step(d(node_ids), d(head_local), d(tail_local), d(rel_ids), d(neg_ids), chunk_size,
-                        neg_sample_size, neg_head, None if edge_weight is None else d(edge_weight))
+        up = getattr(self, "_uploaded", None)
+        if up is not None and up[0] is node_ids:
+            cur = up[1]
+        else:
+            cur = [d(node_ids), d(head_local), d(tail_local), d(rel_ids), d(neg_ids)]
+        self._uploaded, nb = None, None
+        if next_host is not None:
+            nxt = [d(t) for t in next_host[:5]]
+            self._uploaded, nb = (next_host[0], nxt), (nxt[0], nxt[4])
+        out = self.step(cur[0], cur[1], cur[2], cur[3], cur[4], chunk_size, neg_sample_size, neg_head,
+                        None if edge_weight is None else d(edge_weight), next_batch=nb)
         self._log_host.copy_(out, non_blocking=True)
         return self._log_host
 

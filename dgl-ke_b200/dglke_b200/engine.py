@@ -117,10 +117,30 @@ class StepEngine:
                                            out.data_ptr(), self.h.stream()))
         return out
 
+    def announce_next(self, next_batch):
+        """kge_set_next_batch: `next_batch` is the batch of the NEXT step_begin -- a sampler.DeviceBatch or a
+        (node_ids, neg_ids) pair of int64 CUDA tensors that stay alive and unchanged until that step.  Its table rows are
+        copied while this step's contraction runs (sharded tables; one-step-stale reads as under --async_update)."""
+        if next_batch is None:
+            _lib.check(self.lib.kge_set_next_batch(self.h.raw, None, 0))
+            return
+        if hasattr(next_batch, "c"):                                          # DeviceBatch
+            nb, n_neg, keep = next_batch.c, next_batch.Nn, next_batch
+        else:
+            nodes, negs = next_batch
+            assert nodes.is_cuda and negs.is_cuda and nodes.dtype == torch.int64 and negs.dtype == torch.int64
+            nb = _lib.Batch(nodes.data_ptr(), nodes.numel(), None, None, None, negs.data_ptr(), None, None, None, None)
+            n_neg, keep = negs.numel(), (nodes, negs)
+        _lib.check(self.lib.kge_set_next_batch(self.h.raw, C.byref(nb), int(n_neg)))
+        self._next_keep = keep
+
     def step_begin(self, node_ids, head_local=None, tail_local=None, rel_ids=None, neg_ids=None, chunk_size=None,
-                   neg_sample_size=None, neg_head=None, edge_weight=None):
+                   neg_sample_size=None, neg_head=None, edge_weight=None, next_batch=None):
         """first half of step(): everything up to the gradients (kge_step_fused_begin).  `node_ids` may be a
-        sampler.DeviceBatch (then only chunk_size / neg_sample_size are read from the other arguments)."""
+        sampler.DeviceBatch (then only chunk_size / neg_sample_size are read from the other arguments).
+        next_batch: see announce_next()."""
+        if next_batch is not None:
+            self.announce_next(next_batch)
         if hasattr(node_ids, "c") and hasattr(node_ids, "neg_head"):        # DeviceBatch
             batch = node_ids
             cfg = self.cfg(batch.B, chunk_size, neg_sample_size, batch.neg_head)

@@ -216,9 +216,17 @@ def _multi_gpu_worker(rank, world, args, n_ent, n_rel, edges, port):
                             seed=1000 + rank, device=dev.index)
     start = t0 = time.time()
     logs = []
+    # --async_update (tensor_models.py:136-175: the update runs behind the trainer, which may read rows one update old):
+    # the sampler runs one batch ahead and the fused kernels of step k fetch the rows of step k+1 over NVLink while they
+    # compute (kge_set_next_batch); without the flag every step gathers its own, fully up-to-date rows
+    pipelined = bool(getattr(args, "async_update", False))
+    ahead = sampler.sample(0) if pipelined else None
     for step in range(args.max_step):
-        b = sampler.sample(step)
-        log4 = trainer.step(b, chunk_size=sampler.chunk_size, neg_sample_size=args.neg_sample_size)
+        if pipelined:
+            b, ahead = ahead, sampler.sample(step + 1)      # the sampler's output buffers alternate: both batches stay valid
+        else:
+            b = sampler.sample(step)
+        log4 = trainer.step(b, chunk_size=sampler.chunk_size, neg_sample_size=args.neg_sample_size, next_batch=ahead)
         if (step + 1) % args.log_interval == 0:
             v = log4.cpu().tolist()
             print("[proc {}][Train]({}/{}) average loss: {} (pos {}, neg {}, reg {})".format(rank, step + 1, args.max_step, v[2],

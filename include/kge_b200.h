@@ -185,6 +185,17 @@ KGE_API int kge_step_fused_begin(kge_handle_t h, const kge_step_cfg_t* cfg, cons
 KGE_API int kge_step_fused_end(kge_handle_t h, const kge_step_cfg_t* cfg, const kge_table_t* ent,
                        const kge_table_t* rel, const kge_batch_t* batch, float* log4, void* stream);
 
+/* Software pipelining for sharded tables (the reference's --async_update staleness, tensor_models.py:136-175: the rows a
+ * step reads may lag the updates of the step before it).  kge_set_next_batch announces the batch of the NEXT
+ * kge_step_fused_begin; the spare warps of this step's fused kernels then copy that batch's unique-node rows and negative
+ * rows (peer loads over NVLink) into staging buffers while the tensor cores work, and the next begin -- called with
+ * exactly that batch: same device arrays, contents unchanged -- skips its own gathers.  One announcement serves one step;
+ * a begin with any other batch simply ignores the staged rows.  Only node_ids / n_nodes(_dev) / neg_ids of `next` are
+ * read; n_neg = num_chunks * neg_sample_size of the next step.  next = NULL cancels the announcement and drops
+ * rows already staged.  The staging buffers are allocated
+ * on first use (not during stream capture). */
+KGE_API int kge_set_next_batch(kge_handle_t h, const kge_batch_t* next, int64_t n_neg);
+
 /* Same as kge_step_fused but the batch index arrays (and edge weights) are HOST memory, as they
  * come out of the sampler.  Pageable arrays are staged through the handle's pinned buffer (they may be
  * reused as soon as the call returns); page-locked arrays (cudaHostAlloc / torch pin_memory) are DMA'd

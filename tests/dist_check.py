@@ -13,6 +13,10 @@ rows reached with peer loads / system-scope red.add from inside the kernels, rel
             initial state_sum the order in which the ranks' state adds land changes an update by < 1e-3 of its size,
             while a lost or doubled atomic changes it by O(1).
 
+  pipelined the disjoint setting with kge_set_next_batch (--async_update): the fused kernels of step s copy the rows of
+            step s+1, which therefore reads the entity table as it was BEFORE the update of step s (one step stale; the
+            relation table and all updates are current).  The oracle is driven with exactly that lag.
+
 DIST_SAME_GPU=1 puts every rank on cuda:0 with the gloo backend (NCCL refuses two ranks on one device): the IPC mapping,
 the sharded TableView and the system-scope atomics are then exercised on a single-GPU box."""
 import os
@@ -55,13 +59,15 @@ def main():
         tr.barrier()
     full0 = tr.gather_entity_table().cpu()
     rel0 = tr.rel_emb.cpu().clone()
-    steps = 3 if mode == "disjoint" else 1
+    steps = {"disjoint": 3, "pipelined": 4}.get(mode, 1)
     batches = {}
     for r in range(world):
         for s in range(steps):
             rng = np.random.default_rng(1000 * r + s)
-            if mode == "disjoint":
+            if mode in ("disjoint", "pipelined"):
                 ids, rels = np.arange(r, n_ent, world), np.arange(r, n_rel, world)
+                if mode == "pipelined":
+                    ids = ids[:400]                 # consecutive steps of a rank share most of their rows: the lag matters
             else:                                   # every rank hammers the same 300 entities / 4 relations
                 ids, rels = np.arange(0, 300), np.arange(0, 4)
             h, t, ng = rng.choice(ids, B), rng.choice(ids, B), rng.choice(ids, B)
@@ -69,10 +75,16 @@ def main():
             nodes, inv = np.unique(np.concatenate([h, t]), return_inverse=True)
             T = lambda a: th.from_numpy(np.ascontiguousarray(a.astype(np.int64)))
             batches[(r, s)] = [T(nodes), T(inv[:B]), T(inv[B:]), T(rr), T(ng)]
+    mine = [[x.to(dev) for x in batches[(rank, s)]] for s in range(steps)]
+    launches = []
     for s in range(steps):
-        b = [x.to(dev) for x in batches[(rank, s)]]
-        tr.step(*b, N, N, bool(s % 2), sync_between=(mode == "overlap"))
+        nxt = (mine[s + 1][0], mine[s + 1][4]) if (mode == "pipelined" and s + 1 < steps) else None
+        n0 = tr.h.lib.kge_launch_count(tr.h.raw)
+        tr.step(*mine[s], N, N, bool(s % 2), sync_between=(mode == "overlap"), next_batch=nxt)
+        launches.append(tr.h.lib.kge_launch_count(tr.h.raw) - n0)
         tr.barrier()
+    if mode == "pipelined":      # steps fed by the previous step's prefetch run without their own node gather
+        assert all(l == launches[0] - 1 for l in launches[1:]), "staged rows were not used: launches per step %r" % (launches,)
     got_ent = tr.gather_entity_table().cpu()
     got_rel = tr.rel_emb.cpu()
     # all replicas of the relation table must be identical
@@ -88,6 +100,28 @@ def main():
                     ko.train_step(ohp, ent, es, rel, rs, *batches[(r, s)], B // N, N, N, bool(s % 2))
             np.testing.assert_allclose(got_ent.numpy(), ent.numpy(), rtol=1e-4, atol=2e-6)
             np.testing.assert_allclose(got_rel.numpy(), rel.numpy(), rtol=1e-4, atol=2e-6)
+        elif mode == "pipelined":
+            # ids are disjoint across ranks, so the ranks can be replayed one after the other; within a rank step s reads
+            # the entity rows of the table BEFORE update s-1 (what step s-1's kernels copied), relations are current
+            for r in range(world):
+                snaps = [ent.clone()]
+                for s in range(steps):
+                    nodes, _, _, rr, ng = batches[(r, s)]
+                    fb = ko.forward_backward(ohp, snaps[max(s - 1, 0)], rel, *batches[(r, s)], B // N, N, N, bool(s % 2))
+                    with th.no_grad():
+                        ko.adagrad_entry(ent, es, nodes, fb["nodes_grad"], ohp.lr)
+                        ko.adagrad_entry(ent, es, ng, fb["negs_grad"], ohp.lr)
+                        ko.adagrad_entry(rel, rs, rr, fb["rels_grad"], ohp.lr)
+                    snaps.append(ent.clone())
+            np.testing.assert_allclose(got_ent.numpy(), ent.numpy(), rtol=1e-4, atol=2e-6)
+            np.testing.assert_allclose(got_rel.numpy(), rel.numpy(), rtol=1e-4, atol=2e-6)
+            # and the lag is real: the synchronous replay differs
+            ent2, rel2 = full0.clone(), rel0.clone()
+            es2, rs2 = th.full((n_ent,), state0), th.full((n_rel,), state0)
+            for s in range(steps):
+                for r in range(world):
+                    ko.train_step(ohp, ent2, es2, rel2, rs2, *batches[(r, s)], B // N, N, N, bool(s % 2))
+            assert float((ent2 - ent).abs().max()) > 1e-4, "test is blind: stale and synchronous replays coincide"
         else:
             # synchronous oracle: all gradients from the snapshot, then every Adagrad entry
             fbs = [ko.forward_backward(ohp, full0, rel0, *batches[(r, 0)], B // N, N, N, False) for r in range(world)]
@@ -107,7 +141,7 @@ def main():
                   % (upd, err, upd_rel, err_rel), flush=True)
             assert err <= 2e-3 * upd and err_rel <= 2e-3 * upd_rel, "cross-GPU atomics lost or doubled updates"
         moved = float((got_ent - full0).abs().max())
-        assert moved > (1e-4 if mode == "disjoint" else 1e-5), "tables did not move"
+        assert moved > (1e-5 if mode == "overlap" else 1e-4), "tables did not move"
         print("DIST_CHECK_OK model=%s mode=%s world=%d max|delta|=%.3e" % (model, mode, world, moved), flush=True)
     dist.barrier()
     dist.destroy_process_group()

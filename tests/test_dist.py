@@ -20,7 +20,7 @@ def _torchrun(nproc, script, *args, timeout=600, env=None):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode", ["disjoint", "overlap"])
+@pytest.mark.parametrize("mode", ["disjoint", "overlap", "pipelined"])
 @pytest.mark.parametrize("model", ["TransE_l2", "ComplEx"])
 def test_sharded_trainer_matches_oracle(model, mode):
     """2 ranks: on 2 GPUs over NCCL/NVLink when the box has them, else both ranks on cuda:0 (gloo for the relation
