@@ -166,7 +166,7 @@ int make_params(const kge_step_cfg_t* cfg, long long n_nodes, StepParams* p, boo
   p->Nn = (long long)p->C * p->Ns;
   p->U = n_nodes >= 0 ? n_nodes : 2 * p->B;      // capacity when only the device knows the count
   p->U_dev = nullptr;
-  p->rel_deferred = 0; p->rel_dense = 0; p->use_nc = 1; p->fused = 0;
+  p->rel_deferred = 0; p->rel_dense = 0; p->use_nc = 1; p->fused = 0; p->nc_staged = 0;
 
   (void)need_tables;
   return KGE_OK;

@@ -707,15 +707,16 @@ Geometry geometry(const StepParams& p, int mode, bool want_prefetch) {
   if (q.ok && want_prefetch) {
     // GEMM1 keeps its stages; GEMM2 gives up stages (never below 4) until both prefetch warps have kMaxPf row slots
     const uint32_t row = (uint32_t)p.D * 4u;
-    int nS2 = q.nS2;
-    uint32_t used = (uint32_t)q.nS1 * q.stage1Bytes;
+    int nS1 = q.nS1, nS2 = q.nS2;
     uint32_t want = 2u * kMaxPf * row;
+    while (nS1 > 2 && kRingBytes - (uint32_t)nS1 * q.stage1Bytes < want) --nS1;   // a deep GEMM1 ring gives up stages first
+    uint32_t used = (uint32_t)nS1 * q.stage1Bytes;
     if (want > kRingBytes - used) want = kRingBytes - used;           // never more than GEMM1 leaves
     while (nS2 > 4 && kRingBytes - (uint32_t)nS2 * q.stage2Bytes < want) --nS2;
     if ((uint32_t)nS2 * q.stage2Bytes > used) used = (uint32_t)nS2 * q.stage2Bytes;
     int slots = (int)((kRingBytes - used) / (2u * row));
     if (slots > kMaxPf) slots = kMaxPf;
-    if (slots >= 2) { q.pf_slots = slots; q.nS2 = nS2; q.pf_off = used; }
+    if (slots >= 2) { q.pf_slots = slots; q.nS1 = nS1; q.nS2 = nS2; q.pf_off = used; }
   }
   return q;
 }

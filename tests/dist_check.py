@@ -59,7 +59,7 @@ def main():
         tr.barrier()
     full0 = tr.gather_entity_table().cpu()
     rel0 = tr.rel_emb.cpu().clone()
-    steps = {"disjoint": 3, "pipelined": 4}.get(mode, 1)
+    steps = {"disjoint": 3, "pipelined": 5}.get(mode, 1)
     batches = {}
     for r in range(world):
         for s in range(steps):
@@ -77,14 +77,18 @@ def main():
             batches[(r, s)] = [T(nodes), T(inv[:B]), T(inv[B:]), T(rr), T(ng)]
     mine = [[x.to(dev) for x in batches[(rank, s)]] for s in range(steps)]
     launches = []
+    # pipelined: steps 1 .. steps-2 are announced by their predecessor; the first and the last step gather their own rows
+    # (the last one is the launch-count reference: one kernel more than a step fed from staged rows)
+    announced = [mode == "pipelined" and 0 < s < steps - 1 for s in range(steps)]      # step s reads staged rows
     for s in range(steps):
-        nxt = (mine[s + 1][0], mine[s + 1][4]) if (mode == "pipelined" and s + 1 < steps) else None
+        nxt = (mine[s + 1][0], mine[s + 1][4]) if (s + 1 < steps and announced[s + 1]) else None
         n0 = tr.h.lib.kge_launch_count(tr.h.raw)
         tr.step(*mine[s], N, N, bool(s % 2), sync_between=(mode == "overlap"), next_batch=nxt)
         launches.append(tr.h.lib.kge_launch_count(tr.h.raw) - n0)
         tr.barrier()
     if mode == "pipelined":      # steps fed by the previous step's prefetch run without their own node gather
-        assert all(l == launches[0] - 1 for l in launches[1:]), "staged rows were not used: launches per step %r" % (launches,)
+        assert all(launches[s] == launches[-1] - 1 for s in range(steps) if announced[s]), \
+            "staged rows were not used: launches per step %r" % (launches,)
     got_ent = tr.gather_entity_table().cpu()
     got_rel = tr.rel_emb.cpu()
     # all replicas of the relation table must be identical
@@ -107,7 +111,7 @@ def main():
                 snaps = [ent.clone()]
                 for s in range(steps):
                     nodes, _, _, rr, ng = batches[(r, s)]
-                    fb = ko.forward_backward(ohp, snaps[max(s - 1, 0)], rel, *batches[(r, s)], B // N, N, N, bool(s % 2))
+                    fb = ko.forward_backward(ohp, snaps[s - 1] if announced[s] else snaps[s], rel, *batches[(r, s)], B // N, N, N, bool(s % 2))
                     with th.no_grad():
                         ko.adagrad_entry(ent, es, nodes, fb["nodes_grad"], ohp.lr)
                         ko.adagrad_entry(ent, es, ng, fb["negs_grad"], ohp.lr)

@@ -11,6 +11,8 @@ CMD="python bench.py --steps 4 --warmup 3 --no-graph --no-cpu-baseline --no-besi
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/${TAG}_ncu_l.log 2>&1
 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'k_fused|k_prep|k_chain|k_update' -s 15 -c 10 -f -o gpurun_out/${TAG}_full $CMD > gpurun_out/${TAG}_ncu_f.log 2>&1
 timeout 300 python bench.py --workload wikikg2_rotate --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_bench_rotate.json 2> gpurun_out/${TAG}_bench_rotate.err
+# race check of the fused step (shared-memory hazards between the TMA / MMA / epilogue / prefetch roles) on one small case
+timeout 900 compute-sanitizer --tool racecheck --racecheck-report all python -m pytest tests/test_gpu_fused.py -q -m gpu -x -k "five_launches and TransE_l2_d64" > gpurun_out/${TAG}_racecheck.log 2>&1; echo "racecheck rc=$?"; grep -E "RACECHECK SUMMARY|passed|failed|error" gpurun_out/${TAG}_racecheck.log | tail -4
 ls -la gpurun_out/${TAG}_full.ncu-rep
 python - <<P
 import json
