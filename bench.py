@@ -410,6 +410,7 @@ def measure(args, workload, rank, world, local_rank, dev, cpu_base, K_steps, ful
     if world > 1:
         dist.barrier()
         torch.cuda.synchronize()
+        eng.close()                     # every rank unmaps the shards: the next workload of this process allocates its own
     if rank != 0:
         return None
 
@@ -459,9 +460,6 @@ def measure(args, workload, rank, world, local_rank, dev, cpu_base, K_steps, ful
         "cpu_baseline": cpu_base,
         "clocks": clocks,
     }
-    if world > 1:
-        torch.cuda.synchronize()
-        eng.close()                     # unmap the shards: the next workload of this process allocates its own
     return line
 
 

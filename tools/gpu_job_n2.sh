@@ -3,8 +3,8 @@ TAG=${1:-n2}
 N=${2:-2}
 mkdir -p gpurun_out
 nvidia-smi topo -m > gpurun_out/${TAG}_topo.txt 2>&1
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"; tail -5 gpurun_out/${TAG}_bench.err
-timeout 600 python -m pytest tests/test_dist.py -q -m gpu -x > gpurun_out/${TAG}_dist.log 2>&1; tail -3 gpurun_out/${TAG}_dist.log
+timeout ${BENCH_TIMEOUT:-420} python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"; tail -5 gpurun_out/${TAG}_bench.err
+if [ -z "$SKIP_DIST" ]; then timeout 600 python -m pytest tests/test_dist.py -q -m gpu -x > gpurun_out/${TAG}_dist.log 2>&1; tail -3 gpurun_out/${TAG}_dist.log; fi
 python - <<P
 import json
 try:
