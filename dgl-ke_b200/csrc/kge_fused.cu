@@ -285,11 +285,13 @@ k_fused(const __grid_constant__ CUtensorMap mXh, const __grid_constant__ CUtenso
         }
       }
     }
-  } else if (g.pf_slots > 0 && lane == 0) {
+  } else if (g.pf_slots > 0) {
     // ================================ prefetch warps 10, 11 ================================
-    // One lane per warp streams table rows (peer memory when the table is sharded) through a few shared-memory slots into
-    // the next step's buffers: bulk load -> mbarrier -> bulk store.  Slot of item k-1 is re-loaded with item k-1+S once the
-    // store of item k-1 has finished reading it, so S-1 loads are always in flight.
+    // Each warp streams table rows (peer memory when the table is sharded) through a few shared-memory slots into the
+    // next step's buffers: bulk load -> mbarrier -> bulk store.  The slot of item k-1 is re-loaded with item k-1+S once
+    // the store of item k-1 has finished reading it, so S-1 loads are always in flight.  The loop is warp-uniform (one
+    // elected lane issues): the row ids arrive 32 at a time, one coalesced load per lane, and are handed out by shuffle
+    // -- a per-row dependent id load by a single lane costs more than the copy itself.
     const int w = warp - 10, S = g.pf_slots;
     const long long nU = g.pf_nU_dev ? *g.pf_nU_dev : g.pf_nU;
     const long long total = nU + g.pf_nNeg;
@@ -297,24 +299,43 @@ k_fused(const __grid_constant__ CUtensorMap mXh, const __grid_constant__ CUtenso
     const long long stride = 2ll * gridDim.x, j0 = 2ll * blockIdx.x + w;
     const long long n = j0 < nhalf ? (nhalf - j0 + stride - 1) / stride : 0;
     uint8_t* slots = ring + g.pf_off + (size_t)w * S * g.pf_row_bytes;
-    auto load = [&](long long k) {
-      const long long v = g.pf_parity + 2 * (j0 + k * stride);
-      const long long id = v < nU ? g.pf_node_ids[v] : g.pf_neg_ids[v - nU];
+    auto vrow = [&](long long k) { return g.pf_parity + 2 * (j0 + k * stride); };
+    auto fetch_ids = [&](long long kb) {            // ids of items kb .. kb+31, one per lane
+      const long long k = kb + lane;
+      if (k >= n) return 0ll;
+      const long long v = vrow(k);
+      return v < nU ? g.pf_node_ids[v] : g.pf_neg_ids[v - nU];
+    };
+    long long ids_lo = fetch_ids(0), ids_hi = fetch_ids(32);      // items [base, base+32) and [base+32, base+64)
+    long long base = 0;
+    auto load = [&](long long k) {                  // k in [base, base + 64)
+      const int o = (int)(k - base);
+      const long long id = __shfl_sync(0xffffffffu, o < 32 ? ids_lo : ids_hi, o & 31);
       const int s = (int)(k % S);
-      mbar_expect_tx(&pf_full[w][s], g.pf_row_bytes);
-      bulk_g2s(slots + (size_t)s * g.pf_row_bytes, row_ptr(g.xtab, id), g.pf_row_bytes, &pf_full[w][s]);
+      if (elect_one()) {
+        mbar_expect_tx(&pf_full[w][s], g.pf_row_bytes);
+        bulk_g2s(slots + (size_t)s * g.pf_row_bytes, row_ptr(g.xtab, id), g.pf_row_bytes, &pf_full[w][s]);
+      }
+      __syncwarp();
     };
     for (long long k = 0; k < n && k < S; ++k) load(k);
     for (long long k = 0; k < n; ++k) {
       const int s = (int)(k % S);
       mbar_wait(&pf_full[w][s], (uint32_t)((k / S) & 1));
-      const long long v = g.pf_parity + 2 * (j0 + k * stride);
+      const long long v = vrow(k);
       float* dst = v < nU ? g.pf_nc + v * (long long)g.D : g.pf_bn + (v - nU) * (long long)g.D;
-      bulk_s2g(dst, slots + (size_t)s * g.pf_row_bytes, g.pf_row_bytes);
-      bulk_commit();
-      if (k >= 1 && k - 1 + S < n) { bulk_wait_read<1>(); load(k - 1 + S); }
+      const bool reload = k >= 1 && k - 1 + S < n;
+      if (reload && k - 1 + S >= base + 64) { base += 32; ids_lo = ids_hi; ids_hi = fetch_ids(base + 32); }
+      if (elect_one()) {
+        bulk_s2g(dst, slots + (size_t)s * g.pf_row_bytes, g.pf_row_bytes);
+        bulk_commit();
+        if (reload) bulk_wait_read<1>();
+      }
+      __syncwarp();
+      if (reload) load(k - 1 + S);
     }
-    bulk_wait_all();
+    if (elect_one()) bulk_wait_all();
+    __syncwarp();
   }
   } else {
     // ================================ epilogue warps 0..7 ================================
