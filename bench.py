@@ -464,6 +464,11 @@ def measure(args, workload, rank, world, local_rank, dev, cpu_base, K_steps, ful
 
 
 if __name__ == "__main__":
+    # stdout carries exactly ONE line, the JSON: native libraries that print there (NCCL's version banner ...) are sent
+    # to stderr for the duration of the run
+    _real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(_real_stdout, "w", buffering=1)
     a = parse()
     if a.impl == "reference":
         run_reference(a)

@@ -325,7 +325,8 @@ k_fused(const __grid_constant__ CUtensorMap mXh, const __grid_constant__ CUtenso
       const long long v = vrow(k);
       float* dst = v < nU ? g.pf_nc + v * (long long)g.D : g.pf_bn + (v - nU) * (long long)g.D;
       const bool reload = k >= 1 && k - 1 + S < n;
-      if (reload && k - 1 + S >= base + 64) { base += 32; ids_lo = ids_hi; ids_hi = fetch_ids(base + 32); }
+      // rotate the id window one batch early: the fresh batch is needed 32 items from now
+      if (reload && k - 1 + S >= base + 32) { base += 32; ids_lo = ids_hi; ids_hi = fetch_ids(base + 32); }
       if (elect_one()) {
         bulk_s2g(dst, slots + (size_t)s * g.pf_row_bytes, g.pf_row_bytes);
         bulk_commit();

@@ -746,6 +746,7 @@ struct UpdArgs {
   float* log4;          // non-null: phase 3 also reduces {pos_loss, neg_loss, loss, reg}
   const float* wt;      // edge weights (for the log scalars) or null
   int phase_lo, phase_hi;
+  int bulk_red;         // row scatters as bulk reductions (UBLKRED) instead of per-lane red.add
 };
 
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
@@ -765,8 +766,39 @@ __device__ __forceinline__ void grid_barrier(unsigned int* ctr) {
   __syncthreads();
 }
 
+// Row scatter as ONE bulk reduction (cp.reduce.async.bulk ... add.f32, SASS UBLKRED): the warp writes the scaled
+// gradient row to a shared-memory staging buffer and an elected lane hands it to the copy engine, which adds it into the
+// table row -- in this GPU's L2 or, for a peer's row, over NVLink in large packets instead of one 16-byte red.add per
+// lane (100 per 1600-B row).  Two buffers per warp: the reduction of row i reads one while row i+1 is staged in the other.
+constexpr int kRedRowFloats = 512;
+struct RedStage {
+  float* buf[2];
+  unsigned n;           // rows issued by this warp
+};
+__device__ __forceinline__ float* red_stage_acquire(RedStage& r, int lane) {
+  // the bulk group issued two rows ago read this buffer: all but the newest group must have finished reading
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+  __syncwarp();
+  return r.buf[r.n & 1u];
+}
+__device__ __forceinline__ void red_stage_issue(RedStage& r, float* dst, int dim, int lane) {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the async proxy
+  __syncwarp();
+  if (lane == 0) {
+    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
+                 :: "l"(dst), "r"((unsigned)__cvta_generic_to_shared(r.buf[r.n & 1u])), "r"((unsigned)dim * 4u) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  }
+  ++r.n;
+}
+__device__ __forceinline__ void red_stage_drain(int lane) {
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  __syncwarp();
+}
+__device__ __forceinline__ void st_shared4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
 __device__ __forceinline__ void upd_node(const StepParams& p, const TableView& ent, const BatchView& b, const StepWs& w,
-                                         long long u, int lane) {
+                                         long long u, int lane, RedStage* rs) {
   const long long id = b.node_ids[u];
   float* row = row_ptr(ent, id);
   float* ng = w.NG + u * (long long)p.D;
@@ -806,15 +838,18 @@ __device__ __forceinline__ void upd_node(const StepParams& p, const TableView& e
     }
     s_new = __shfl_sync(0xffffffffu, s_new, 0);
     const float nlr_std = -p.lr / (sqrtf(s_new) + 1e-10f);
+    float* stage = (sharded && rs) ? red_stage_acquire(*rs, lane) : nullptr;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int v = lane + kWarp * q;
       if (v < nv) {
-        if (sharded) red_add4_sys(row + 4 * v, f4_scale(gq[q], nlr_std));
+        if (stage) st_shared4(stage + 4 * v, f4_scale(gq[q], nlr_std));
+        else if (sharded) red_add4_sys(row + 4 * v, f4_scale(gq[q], nlr_std));
         else st4(row + 4 * v, f4_fma(gq[q], nlr_std, x[q]));
         st4(ng + 4 * v, z);
       }
     }
+    if (stage) red_stage_issue(*rs, row, p.D, lane);
     return;
   }
   // pass 1: g = NG + reg'(x), mean(g^2)
@@ -872,7 +907,8 @@ __device__ __forceinline__ void upd_rel_dense(const TableView& rel, float* rg, f
   }
 }
 
-__device__ __forceinline__ void apply_row(const TableView& t, long long id, const float* g, int dim, float lr, int lane) {
+__device__ __forceinline__ void apply_row(const TableView& t, long long id, const float* g, int dim, float lr, int lane,
+                                          RedStage* rs = nullptr) {
   float* row = row_ptr(t, id);
   const int nv = dim >> 2;
   if (nv <= 4 * kWarp && (dim & 3) == 0) {
@@ -884,6 +920,16 @@ __device__ __forceinline__ void apply_row(const TableView& t, long long id, cons
       x[q] = (v < nv) ? ld4(g + 4 * v) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     const float nlr_std = -lr / (sqrtf(*state_ptr(t, id)) + 1e-10f);
+    if (rs) {
+      float* stage = red_stage_acquire(*rs, lane);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int v = lane + kWarp * q;
+        if (v < nv) st_shared4(stage + 4 * v, f4_scale(x[q], nlr_std));
+      }
+      red_stage_issue(*rs, row, dim, lane);
+      return;
+    }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int v = lane + kWarp * q;
@@ -904,9 +950,12 @@ __device__ void reduce_log_part(const StepParams& p, const StepWs& w, long long 
                                 int bid, int nb);
 
 __global__ void __launch_bounds__(kRowBlock, 4) k_update(UpdArgs a) {
+  __shared__ __align__(128) float red_stage[kWarpsPerBlock][2][kRedRowFloats];
   const StepParams& p = a.p;
   const StepWs& w = a.w;
   const int lane = threadIdx.x & 31;
+  RedStage rstage{{red_stage[threadIdx.x >> 5][0], red_stage[threadIdx.x >> 5][1]}, 0u};
+  RedStage* rs = a.bulk_red ? &rstage : nullptr;
   const long long warp0 = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * kWarpsPerBlock;
   const bool rel_edge = !p.rel_deferred && !p.rel_dense;      // relation entry handled per edge, here
@@ -915,7 +964,7 @@ __global__ void __launch_bounds__(kRowBlock, 4) k_update(UpdArgs a) {
       const long long nrel = (p.rel_dense && !p.rel_deferred) ? a.rel.num_rows : 0;
       const long long U = node_count(p);
       for (long long j = warp0; j < U + nrel; j += nwarps) {
-        if (j < U) upd_node(p, a.ent, a.b, w, j, lane);
+        if (j < U) upd_node(p, a.ent, a.b, w, j, lane, rs);
         else upd_rel_dense(a.rel, w.rg, w.rgs, j - U, p.lr, lane);
       }
     } else if (phase == 2) {
@@ -939,7 +988,7 @@ __global__ void __launch_bounds__(kRowBlock, 4) k_update(UpdArgs a) {
     } else {
       const long long nr = rel_edge ? p.B : 0;
       for (long long j = warp0; j < p.Nn + nr; j += nwarps) {
-        if (j < p.Nn) apply_row(a.ent, a.b.neg_ids[j], w.Bn + j * (long long)p.D, p.D, p.lr, lane);
+        if (j < p.Nn) apply_row(a.ent, a.b.neg_ids[j], w.Bn + j * (long long)p.D, p.D, p.lr, lane, rs);
         else apply_row(a.rel, a.b.rel_ids[j - p.Nn], w.GR + (j - p.Nn) * (long long)p.Dr, p.Dr, p.lr, lane);
       }
       if (a.log4) {
@@ -951,6 +1000,7 @@ __global__ void __launch_bounds__(kRowBlock, 4) k_update(UpdArgs a) {
     }
     if (phase < a.phase_hi) grid_barrier(w.sync_ctr + (phase - 1));
   }
+  if (rs) red_stage_drain(lane);        // every bulk reduction of this warp has landed
   if (a.phase_hi > a.phase_lo) {
     // leave the barrier counters at zero for the next launch: the last CTA to get here resets them
     __syncthreads();
@@ -967,7 +1017,8 @@ __global__ void __launch_bounds__(kRowBlock, 4) k_update(UpdArgs a) {
 
 int launch_update(const LaunchCtx& c, const StepParams& p, const TableView& ent, const TableView& rel,
                   const BatchView& b, const StepWs& w, float* log4, const float* wt) {
-  UpdArgs a{p, ent, rel, b, w, log4, wt, 1, 3};
+  static const bool no_bulk = getenv("KGE_B200_NO_BULKRED") != nullptr;
+  UpdArgs a{p, ent, rel, b, w, log4, wt, 1, 3, (!no_bulk && p.D <= kRedRowFloats && (p.D & 3) == 0) ? 1 : 0};
   // job counts per phase (warps): nodes (+ relations), negatives (+ edges), negatives + edges
   const long long nrel = (p.rel_dense && !p.rel_deferred) ? rel.num_rows : 0;
   const long long nr = (!p.rel_deferred && !p.rel_dense) ? p.B : 0;

@@ -18,7 +18,7 @@ python - <<P
 import json
 for n in ('bench','bench_ref','bench_rotate'):
     try:
-        d=json.load(open('gpurun_out/${TAG}_%s.json'%n))
+        txt=open('gpurun_out/${TAG}_%s.json'%n).read(); d=json.loads(txt[txt.index('{'):])
         print(n,'value %.2fM e2e %.2fM ms %s'%(d['value']/1e6,d['e2e']['value']/1e6,d.get('ms_per_step')), 'frac', d.get('roofline',{}).get('frac'), 'cpu', d.get('cpu_baseline'))
         if 'beside' in d: print('  beside %.2fM'%(d['beside']['value']/1e6), d['beside']['config']['workload'][:40])
     except Exception as e: print(n,'ERR',e)

@@ -8,7 +8,7 @@ if [ -z "$SKIP_DIST" ]; then timeout 600 python -m pytest tests/test_dist.py -q 
 python - <<P
 import json
 try:
-    d=json.load(open('gpurun_out/${TAG}_bench.json'))
+    txt=open('gpurun_out/${TAG}_bench.json').read(); d=json.loads(txt[txt.index('{'):])
     print('N=%d value %.1fM e2e %.1fM ms %.4f'%(d['n_gpus'],d['value']/1e6,d['e2e']['value']/1e6,d['ms_per_step']), d['config']['workload'][:50])
     print({k:round(v*1e3,1) for k,v in d['roofline']['kernel_ms'].items()})
     if 'beside' in d:
