@@ -59,6 +59,9 @@ def parse():
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS),
                     help="default: fb15k_transe_l2 (BASELINE configs[1]) on one GPU, freebase_transe_l2 (the 86 M-entity "
                          "HBM-resident table north_star's scaling target names) on several; the other one is measured beside it")
+    ap.add_argument("--edge-placement", default="head-owner", choices=["head-owner", "random"],
+                    help="N>1: which edges a rank trains on -- those whose head row it owns (half of the positive-node rows "
+                         "are then local), or any (every row remote with probability (N-1)/N)")
     ap.add_argument("--no-pipeline", action="store_true",
                     help="N>1: do not announce the next batch (no row prefetch by the fused kernels; every step gathers its own rows)")
     ap.add_argument("--no-beside", action="store_true", help="skip the second (beside) workload of a default run")
@@ -278,7 +281,12 @@ def measure(args, workload, rank, world, local_rank, dev, cpu_base, K_steps, ful
 
     # ---- batches: NB distinct pre-sampled batches per rank, device and pinned-host copies --------
     NB = 8
-    sampler = SyntheticSampler(n_ent, n_rel, B, neg, seed=0, rank=rank)
+    head_range = None
+    if world > 1 and args.edge_placement == "head-owner":
+        from dglke_b200.dist import shard_rows
+        _, lo, hi = shard_rows(n_ent, world, rank)
+        head_range = (lo, hi)
+    sampler = SyntheticSampler(n_ent, n_rel, B, neg, seed=0, rank=rank, head_range=head_range)
     host, devb = [], []
     for k in range(NB):
         pg, ng = sampler.batch(k)
@@ -444,6 +452,8 @@ def measure(args, workload, rank, world, local_rank, dev, cpu_base, K_steps, ful
                    "l2": "cold: 256 MiB written between timed steps" if not args.no_flush else "warm (no flush)",
                    "launch": "one CUDA graph per step" if used_graph else "eager launches",
                    "sampling": "excluded (pre-generated seeded batches), as on the reference arm",
+                   "edge_placement": ("each rank trains on the edges whose head row it owns (tails and negatives anywhere)"
+                                      if head_range else "random" if world > 1 else "n/a"),
                    "pipeline": ("next batch announced: its rows are fetched over NVLink by this step's fused kernels (entity reads "
                                 "lag the updates by one step, as under the reference's --async_update)") if pipelined else "none",
                    "arithmetic": "fp32 rows; contractions on tcgen05 as 3xTF32 (hi/lo split) with fp32 accumulation" if model in ("TransE_l2", "DistMult", "ComplEx", "RESCAL") else "fp32 CUDA-core tiles",

@@ -74,7 +74,7 @@ struct kge_context {
     long long r_nU = 0, r_nneg = 0;
     int r_buf = 0;                   // which nc[] holds them
     float* nc[2] = {nullptr, nullptr};
-    float* bn = nullptr;
+    float* bn[2] = {nullptr, nullptr};  // double-buffered like nc: k_fused<N> of step k reads bn[cur] while it stages bn[cur^1]
     size_t nc_floats = 0, bn_floats = 0;
   } pf;
   int fused_mode = -1;               // -1 default (fused kernel whenever the shape allows), 0 off
@@ -584,7 +584,7 @@ static int forward_backward_impl(kge_handle_t h, const kge_step_cfg_t* cfg, cons
                        pf.r_nU == batch->n_nodes && pf.r_nU_dev == (batch->n_nodes < 0 ? batch->n_nodes_dev : nullptr) &&
                        pf.r_nneg == p.Nn;
     pf.ready = false;
-    if (match) { w.NC = pf.nc[pf.r_buf]; w.BnRaw = pf.bn; p.nc_staged = 1; }
+    if (match) { w.NC = pf.nc[pf.r_buf]; w.BnRaw = pf.bn[pf.r_buf]; p.nc_staged = 1; }
   }
   const FusedPrefetch* pfp = nullptr;
   FusedPrefetch pfa{};
@@ -601,13 +601,16 @@ static int forward_backward_impl(kge_handle_t h, const kge_step_cfg_t* cfg, cons
         if (cs != cudaStreamCaptureStatusNone)
           return fail(KGE_ERR_INVALID_ARG, "kge_set_next_batch: the staging buffers must exist before stream capture (run one eager step first)");
         KGE_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
-        for (int i = 0; i < 2; ++i) { if (pf.nc[i]) cudaFree(pf.nc[i]); pf.nc[i] = nullptr; }
-        if (pf.bn) cudaFree(pf.bn);
-        pf.bn = nullptr; pf.nc_floats = pf.bn_floats = 0;
+        for (int i = 0; i < 2; ++i) {
+          if (pf.nc[i]) cudaFree(pf.nc[i]);
+          if (pf.bn[i]) cudaFree(pf.bn[i]);
+          pf.nc[i] = pf.bn[i] = nullptr;
+        }
+        pf.nc_floats = pf.bn_floats = 0;
         if (cudaMalloc(&pf.nc[0], ncf * 4) != cudaSuccess || cudaMalloc(&pf.nc[1], ncf * 4) != cudaSuccess ||
-            cudaMalloc(&pf.bn, bnf * 4) != cudaSuccess) {
+            cudaMalloc(&pf.bn[0], bnf * 4) != cudaSuccess || cudaMalloc(&pf.bn[1], bnf * 4) != cudaSuccess) {
           cudaGetLastError();
-          return fail(KGE_ERR_NOMEM, "prefetch staging buffers (%zu MB)", (2 * ncf + bnf) * 4 >> 20);
+          return fail(KGE_ERR_NOMEM, "prefetch staging buffers (%zu MB)", (2 * ncf + 2 * bnf) * 4 >> 20);
         }
         pf.nc_floats = ncf; pf.bn_floats = bnf;
         w.BnRaw = nullptr; w.NC = arena_nc; p.nc_staged = 0;      // whatever was staged is gone with the old buffers
@@ -618,7 +621,7 @@ static int forward_backward_impl(kge_handle_t h, const kge_step_cfg_t* cfg, cons
       pfa.nU = nU;
       pfa.neg_ids = (const long long*)pf.next.neg_ids;
       pfa.nNeg = pf.next_nneg;
-      pfa.nc = pf.nc[tgt]; pfa.bn = pf.bn;
+      pfa.nc = pf.nc[tgt]; pfa.bn = pf.bn[tgt];
       pfp = &pfa;
       pf.ready = true;
       pf.r_nodes = pf.next.node_ids; pf.r_negs = pf.next.neg_ids; pf.r_nU = pf.next.n_nodes;

@@ -73,6 +73,7 @@ struct FusedArgs {
   const float *Xhi, *Xlo;  // slabs of the lane-side rows (negatives): b = hi + lo in the epilogue
   const long long* xids;   // mode N, one GPU: entity ids of the lane-side rows -- b is then read from the table itself
   TableView xtab;          //   (one fp32 load instead of hi + lo; nothing updates the table before k_update)
+  const float* xraw;       // mode N, sharded + staged: the lane-side rows as fp32 [C*Rx, D] (the previous step's prefetch)
   float* gsn;            // [C*Rx] mean(G_neg^2)
   float* out;            // P: GA [C*Rx, D]; N: G_neg [C*Rx, D]
   // next step's rows, copied by the two spare warps while this step's tiles are computed (sharded tables: the remote-row
@@ -367,11 +368,13 @@ k_fused(const __grid_constant__ CUtensorMap mXh, const __grid_constant__ CUtenso
       // mode N, one GPU: table rows of the 4 lane-side rows this lane handles in the transposed epilogue mapping
       // (ids fetched now, while GEMM1 runs: the epilogue's row loads then depend on nothing)
       const float* brow[4] = {nullptr, nullptr, nullptr, nullptr};
-      if (MODE == F_N && g.xids) {
+      const bool bdirect = MODE == F_N && (g.xids || g.xraw);
+      if (bdirect) {
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
           const int mr = m0 + q * 32 + (lane >> 2) + 8 * it;
-          brow[it] = row_ptr(g.xtab, mr < g.Rx ? g.xids[(long long)c * g.Rx + mr] : 0);
+          const long long xr = (long long)c * g.Rx + (mr < g.Rx ? mr : 0);
+          brow[it] = g.xraw ? g.xraw + xr * (long long)g.D : row_ptr(g.xtab, g.xids[xr]);
         }
       }
       mbar_wait(&s_full, it & 1);
@@ -541,7 +544,7 @@ k_fused(const __grid_constant__ CUtensorMap mXh, const __grid_constant__ CUtenso
           const int pc = i >> 2, it = i & 3;
           const int k = d0n + cbn + pc * 16 + tc4, mr = mrow0 + tr + 8 * it;
           if (chn < nchunks && pc < npn && k < g.D && mr < g.Rx) {
-            if (g.xids) {
+            if (bdirect) {
               bnext[i] = ld4(brow[it] + k);
             } else {
               const long long so = slab_off(c, g.nblkD, g.Rx, mr, k);
@@ -636,7 +639,7 @@ k_fused(const __grid_constant__ CUtensorMap mXh, const __grid_constant__ CUtenso
             if (MODE == F_P) o = f4_scale(o, rsc[it]);            // 1 / softmax denominator of the row
             if (MODE == F_N) {
               float4 b;
-              if (g.xids) b = ld4(brow[it] + k);
+              if (bdirect) b = ld4(brow[it] + k);
               else { const long long so = slab_off(c, g.nblkD, g.Rx, mr, k); b = f4_add(ld4(g.Xhi + so), ld4(g.Xlo + so)); }
               if (l2) o = f4_fma(b, -rsc[it], o);                   // sum_i V_ij a_i - (sum_i V_ij) b_j
               o = f4_add(o, reg_grad4_fast(b, g.reg_norm, g.reg_coef));
@@ -774,6 +777,7 @@ int fused_launch(const LaunchCtx& c, const StepParams& p, const StepWs& w, int m
   // one GPU: the negatives' own rows come straight from the table (exact fp32, one load); sharded tables would make
   // that a remote read per row, so they use the local hi + lo slabs
   if (!P && ent && ent->n_shards == 1 && neg_ids) { g.xids = neg_ids; g.xtab = *ent; }
+  if (!P && w.BnRaw) g.xraw = w.BnRaw;
   g.gsn = w.gsn;
   g.out = P ? w.GA : w.Bn;
   const long long rowsX = (long long)p.C * g.Rx * g.nblkD, rowsY = (long long)p.C * g.Ry * g.nblkD;

@@ -72,6 +72,16 @@ def owner_of(ids, num_rows, world):
     return ids // per
 
 
+def partition_edges_by_head_owner(heads, n_ent, world, rank):
+    """Indices of the edges whose HEAD row lives in `rank`'s shard.  With this edge partition half of a batch's
+    positive-node rows are local (gather and Adagrad scatter stay on the GPU); the reference's analogue is its partitioned
+    training, where a trainer's edges are those whose entities are mostly local (METIS, partition.py / RandomPartition
+    keeps no locality at all).  Every edge still belongs to exactly one rank."""
+    import numpy as np
+    per = (n_ent + world - 1) // world
+    return np.nonzero(np.asarray(heads) // per == rank)[0]
+
+
 class ShardedTrainer:
     """StepEngine-compatible driver (step / step_host / sync / h) over a sharded entity table."""
 

@@ -92,7 +92,10 @@ class SyntheticSampler:
     """Bidirectional one-shot iterator over seeded uniform batches: step 1,3,5.. corrupt tails,
     2,4,6.. corrupt heads (NewBidirectionalOneShotIterator, sampler.py:853-859)."""
 
-    def __init__(self, n_entities, n_relations, batch_size, neg_sample_size, seed=0, rank=0):
+    def __init__(self, n_entities, n_relations, batch_size, neg_sample_size, seed=0, rank=0, head_range=None):
+        """head_range = (lo, hi): heads are drawn from [lo, hi) only -- the edges of a rank whose edge partition is
+        'head owned by this rank' (dist.partition_edges_by_head_owner)"""
+        self.head_range = head_range
         lay = chunk_layout(batch_size, neg_sample_size)
         if lay is None:
             raise ValueError("batch_size must be a multiple of neg_sample_size (utils.get_compatible_batch_size)")
@@ -104,6 +107,8 @@ class SyntheticSampler:
     def batch(self, k):
         rng = np.random.default_rng(self.seed + k)
         h, t = rng.integers(0, self.n_ent, self.B), rng.integers(0, self.n_ent, self.B)
+        if self.head_range is not None:
+            h = self.head_range[0] + h % max(1, self.head_range[1] - self.head_range[0])
         r = rng.integers(0, self.n_rel, self.B)
         ng = rng.integers(0, self.n_ent, self.num_chunks * self.Ns)
         pos_g = build_pos_graph(h, r, t)

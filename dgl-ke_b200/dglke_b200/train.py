@@ -210,8 +210,15 @@ def _multi_gpu_worker(rank, world, args, n_ent, n_rel, edges, port):
                adversarial=args.neg_adversarial_sampling, adv_temperature=args.adversarial_temperature,
                double_ent=args.double_ent, double_rel=args.double_rel)
     trainer = ShardedTrainer(hp, n_ent, n_rel, dev, seed=0)
-    # RandomPartition (dataloader/sampler.py:256-290): a fixed random split of the edges over the ranks
-    perm = np.random.default_rng(0).permutation(len(edges[0]))[rank::world]
+    # edge partition: the edges whose head row this rank owns (half of the positive-node traffic stays on the GPU);
+    # KGE_B200_EDGE_PART=random gives the reference's RandomPartition (dataloader/sampler.py:256-290)
+    if os.environ.get("KGE_B200_EDGE_PART", "head_owner") == "random":
+        perm = np.random.default_rng(0).permutation(len(edges[0]))[rank::world]
+    else:
+        from .dist import partition_edges_by_head_owner
+        perm = partition_edges_by_head_owner(edges[0], n_ent, world, rank)
+        if len(perm) < args.batch_size:
+            raise SystemExit("rank %d owns the heads of only %d edges (< batch_size): use KGE_B200_EDGE_PART=random" % (rank, len(perm)))
     sampler = DeviceSampler(edges[0][perm], edges[1][perm], edges[2][perm], n_ent, args.batch_size, args.neg_sample_size,
                             seed=1000 + rank, device=dev.index)
     start = t0 = time.time()
