@@ -289,8 +289,7 @@ k_fused(const __grid_constant__ CUtensorMap mXh, const __grid_constant__ CUtenso
   } else if (g.pf_slots > 0) {
     // ================================ prefetch warps 10, 11 ================================
     // Each warp streams table rows (peer memory when the table is sharded) through a few shared-memory slots into the
-    // next step's buffers: bulk load -> mbarrier -> bulk store.  The slot of item k-1 is re-loaded with item k-1+S once
-    // the store of item k-1 has finished reading it, so S-1 loads are always in flight.  The loop is warp-uniform (one
+    // next step's buffers: bulk load -> mbarrier -> bulk store, S slots per warp re-used round robin.  The loop is warp-uniform (one
     // elected lane issues): the row ids arrive 32 at a time, one coalesced load per lane, and are handed out by shuffle
     // -- a per-row dependent id load by a single lane costs more than the copy itself.
     const int w = warp - 10, S = g.pf_slots;
@@ -320,21 +319,26 @@ k_fused(const __grid_constant__ CUtensorMap mXh, const __grid_constant__ CUtenso
       __syncwarp();
     };
     for (long long k = 0; k < n && k < S; ++k) load(k);
+    // A slot is re-loaded L stores after its own store was issued: waiting for the newest store to release its slot would
+    // serialise every row on the copy engine's queue (shared with the GEMM operand loads); waiting for the store issued
+    // L rows ago almost never blocks, and S - L loads stay in flight.
+    const int L = S >= 6 ? 3 : (S >= 4 ? 2 : 1);
     for (long long k = 0; k < n; ++k) {
       const int s = (int)(k % S);
       mbar_wait(&pf_full[w][s], (uint32_t)((k / S) & 1));
       const long long v = vrow(k);
       float* dst = v < nU ? g.pf_nc + v * (long long)g.D : g.pf_bn + (v - nU) * (long long)g.D;
-      const bool reload = k >= 1 && k - 1 + S < n;
+      const long long kr = k - L + S;                // the item that takes over the slot of item k - L
+      const bool reload = k >= L && kr < n;
       // rotate the id window one batch early: the fresh batch is needed 32 items from now
-      if (reload && k - 1 + S >= base + 32) { base += 32; ids_lo = ids_hi; ids_hi = fetch_ids(base + 32); }
+      if (reload && kr >= base + 32) { base += 32; ids_lo = ids_hi; ids_hi = fetch_ids(base + 32); }
       if (elect_one()) {
         bulk_s2g(dst, slots + (size_t)s * g.pf_row_bytes, g.pf_row_bytes);
         bulk_commit();
-        if (reload) bulk_wait_read<1>();
+        if (reload) { if (L == 3) bulk_wait_read<3>(); else if (L == 2) bulk_wait_read<2>(); else bulk_wait_read<1>(); }
       }
       __syncwarp();
-      if (reload) load(k - 1 + S);
+      if (reload) load(kr);
     }
     if (elect_one()) bulk_wait_all();
     __syncwarp();
