@@ -81,6 +81,7 @@ struct FusedArgs {
   // takes the v with v % 2 == pf_parity (the P and the N kernel split the list).
   int pf_slots;                    // row slots per warp (0 = no prefetch), carved from the ring behind the GEMM stages
   int pf_parity;
+  int pf_lag;                      // stores between a slot's own store and its re-load (>= 1)
   uint32_t pf_off, pf_row_bytes;
   const long long* pf_node_ids;    // next batch's unique nodes
   const long long* pf_nU_dev;      // their count on the device, or null
@@ -319,10 +320,10 @@ k_fused(const __grid_constant__ CUtensorMap mXh, const __grid_constant__ CUtenso
       __syncwarp();
     };
     for (long long k = 0; k < n && k < S; ++k) load(k);
-    // A slot is re-loaded L stores after its own store was issued: waiting for the newest store to release its slot would
-    // serialise every row on the copy engine's queue (shared with the GEMM operand loads); waiting for the store issued
-    // L rows ago almost never blocks, and S - L loads stay in flight.
-    const int L = S >= 6 ? 3 : (S >= 4 ? 2 : 1);
+    // A slot is re-loaded L stores after its own store was issued (S - L loads in flight).  L = 1 keeps the most loads in
+    // flight, which is what matters when the rows are remote (8 GPUs: ~4 us per row); a larger L (KGE_B200_PF_LAG) never
+    // waits on the copy engine's queue for the newest store -- measured equal at 2 GPUs.
+    const int L = g.pf_lag < S - 1 ? g.pf_lag : (S > 2 ? S - 2 : 1);
     for (long long k = 0; k < n; ++k) {
       const int s = (int)(k % S);
       mbar_wait(&pf_full[w][s], (uint32_t)((k / S) & 1));
@@ -766,6 +767,8 @@ int fused_launch(const LaunchCtx& c, const StepParams& p, const StepWs& w, int m
   g.Rx = q.Rx; g.Ry = q.Ry; g.N1 = q.N1; g.Wc = q.Wc; g.nS1 = q.nS1; g.nS2 = q.nS2;
   g.stage1Bytes = q.stage1Bytes; g.stage2Bytes = q.stage2Bytes;
   if (pf && ent && q.pf_slots >= 2) {
+    static const int lag_env = getenv("KGE_B200_PF_LAG") ? atoi(getenv("KGE_B200_PF_LAG")) : 1;
+    g.pf_lag = lag_env < 1 ? 1 : (lag_env > 3 ? 3 : lag_env);
     g.pf_slots = q.pf_slots; g.pf_off = q.pf_off; g.pf_row_bytes = (uint32_t)p.D * 4u; g.pf_parity = mode;
     g.pf_node_ids = pf->node_ids; g.pf_nU_dev = pf->nU_dev; g.pf_nU = pf->nU; g.pf_nNeg = pf->nNeg;
     g.pf_neg_ids = pf->neg_ids; g.pf_nc = pf->nc; g.pf_bn = pf->bn;
