@@ -907,10 +907,8 @@ __device__ __forceinline__ void upd_rel_dense(const TableView& rel, float* rg, f
   }
 }
 
-// st_pre: the row's state_sum when the caller already loaded it (k_update fetches it one row ahead: for a peer's row the
-// load is an NVLink round trip), else null
 __device__ __forceinline__ void apply_row(const TableView& t, long long id, const float* g, int dim, float lr, int lane,
-                                          RedStage* rs = nullptr, const float* st_pre = nullptr) {
+                                          RedStage* rs = nullptr) {
   float* row = row_ptr(t, id);
   const int nv = dim >> 2;
   if (nv <= 4 * kWarp && (dim & 3) == 0) {
@@ -921,7 +919,7 @@ __device__ __forceinline__ void apply_row(const TableView& t, long long id, cons
       const int v = lane + kWarp * q;
       x[q] = (v < nv) ? ld4(g + 4 * v) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    const float nlr_std = -lr / (sqrtf(st_pre ? *st_pre : *state_ptr(t, id)) + 1e-10f);
+    const float nlr_std = -lr / (sqrtf(*state_ptr(t, id)) + 1e-10f);
     if (rs) {
       float* stage = red_stage_acquire(*rs, lane);
 #pragma unroll
@@ -951,79 +949,6 @@ __device__ __forceinline__ void apply_row(const TableView& t, long long id, cons
 __device__ void reduce_log_part(const StepParams& p, const StepWs& w, long long nreg, const float* wbar, float* log4,
                                 int bid, int nb);
 
-// Sharded tables, unique positive nodes: the node update of upd_node() split in two so that the round trip of the
-// system-scope state atomic (the owner may be a peer GPU) overlaps the next node's row loads.
-//   stage: g = NG + reg'(x), mean(g^2); g parked UNSCALED in a staging buffer; state atomic issued, result left pending
-//   finish (one node later): scale the parked row by -lr / sqrt(state) in place and hand it to the copy engine
-struct PendingNode {
-  float s_new;        // lane 0: state_sum after this node's add (the atomic's return value + gs)
-  float* row;         // table row (possibly in a peer's HBM)
-  float* buf;         // staging buffer holding g
-  int have;
-};
-__device__ __forceinline__ void node_finish(const StepParams& p, PendingNode& pn, int lane) {
-  const float s_new = __shfl_sync(0xffffffffu, pn.s_new, 0);
-  const float nlr_std = -p.lr / (sqrtf(s_new) + 1e-10f);
-  const int nv = p.D >> 2;
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int v = lane + kWarp * q;
-    if (v < nv) {
-      float4* e = reinterpret_cast<float4*>(pn.buf + 4 * v);      // the element this lane parked itself
-      *e = f4_scale(*e, nlr_std);
-    }
-  }
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  __syncwarp();
-  if (lane == 0) {
-    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
-                 :: "l"(pn.row), "r"((unsigned)__cvta_generic_to_shared(pn.buf)), "r"((unsigned)p.D * 4u) : "memory");
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-  }
-  pn.have = 0;
-}
-__device__ __forceinline__ void node_stage(const StepParams& p, const TableView& ent, const BatchView& b, const StepWs& w,
-                                           long long u, int lane, float* buf, PendingNode& out) {
-  const long long id = b.node_ids[u];
-  float* ng = w.NG + u * (long long)p.D;
-  const float* nc = node_row(p, ent, b, w, u);
-  const int nv = p.D >> 2;
-  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-  const bool reg_on = (p.reg_coef > 0.f && p.reg_norm > 0);
-  float4 x[4], gq[4];
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int v = lane + kWarp * q;
-    x[q] = (v < nv) ? ld4(nc + 4 * v) : z;
-    gq[q] = (v < nv) ? ld4(ng + 4 * v) : z;
-  }
-  float gs = 0.f, reg = 0.f;
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    gq[q] = f4_add(gq[q], reg_grad4(x[q], p.reg_norm, p.reg_coef));
-    gs += f4_dot(gq[q], gq[q]);
-    if (reg_on && node_reg_in_update(p)) reg += abs_pow4_sum(x[q], p.reg_norm);
-  }
-  gs = warp_sum(gs) / (float)p.D;
-  if (node_reg_in_update(p)) {
-    reg = warp_sum(reg);
-    if (lane == 0) w.regp[p.B + p.Nn + u] = reg;
-  }
-  // the bulk reduction that last read `buf` (two nodes ago) was issued a whole node ago: make sure it is done reading
-  if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-  __syncwarp();
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int v = lane + kWarp * q;
-    if (v < nv) { st_shared4(buf + 4 * v, gq[q]); st4(ng + 4 * v, z); }
-  }
-  out.s_new = 0.f;
-  if (lane == 0) out.s_new = atomicAdd_system(state_ptr(ent, id), gs) + gs;     // consumed one node later
-  out.row = row_ptr(ent, id);
-  out.buf = buf;
-  out.have = 1;
-}
-
 __global__ void __launch_bounds__(kRowBlock, 4) k_update(UpdArgs a) {
   __shared__ __align__(128) float red_stage[kWarpsPerBlock][2][kRedRowFloats];
   const StepParams& p = a.p;
@@ -1038,26 +963,9 @@ __global__ void __launch_bounds__(kRowBlock, 4) k_update(UpdArgs a) {
     if (phase == 1) {
       const long long nrel = (p.rel_dense && !p.rel_deferred) ? a.rel.num_rows : 0;
       const long long U = node_count(p);
-      if (rs && a.ent.n_shards > 1 && (p.D >> 2) <= 4 * kWarp) {
-        // sharded table: two nodes in flight per warp (see node_stage / node_finish)
-        PendingNode pend{0.f, nullptr, nullptr, 0};
-        unsigned par = 0;
-        for (long long j = warp0; j < U; j += nwarps) {
-          PendingNode cur;
-          node_stage(p, a.ent, a.b, w, j, lane, rs->buf[par & 1u], cur);
-          if (pend.have) node_finish(p, pend, lane);
-          pend = cur;
-          ++par;
-        }
-        if (pend.have) node_finish(p, pend, lane);
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // phase 3 re-uses the buffers
-        __syncwarp();
-        for (long long j = U + warp0; j < U + nrel; j += nwarps) upd_rel_dense(a.rel, w.rg, w.rgs, j - U, p.lr, lane);
-      } else {
-        for (long long j = warp0; j < U + nrel; j += nwarps) {
-          if (j < U) upd_node(p, a.ent, a.b, w, j, lane, rs);
-          else upd_rel_dense(a.rel, w.rg, w.rgs, j - U, p.lr, lane);
-        }
+      for (long long j = warp0; j < U + nrel; j += nwarps) {
+        if (j < U) upd_node(p, a.ent, a.b, w, j, lane, rs);
+        else upd_rel_dense(a.rel, w.rg, w.rgs, j - U, p.lr, lane);
       }
     } else if (phase == 2) {
       if (p.fused) {
@@ -1079,16 +987,9 @@ __global__ void __launch_bounds__(kRowBlock, 4) k_update(UpdArgs a) {
       }
     } else {
       const long long nr = rel_edge ? p.B : 0;
-      // the state scalar of the NEXT negative row is requested before this row is processed
-      float st_next = (warp0 < p.Nn) ? *state_ptr(a.ent, a.b.neg_ids[warp0]) : 0.f;
       for (long long j = warp0; j < p.Nn + nr; j += nwarps) {
-        if (j < p.Nn) {
-          const float st_cur = st_next;
-          if (j + nwarps < p.Nn) st_next = *state_ptr(a.ent, a.b.neg_ids[j + nwarps]);
-          apply_row(a.ent, a.b.neg_ids[j], w.Bn + j * (long long)p.D, p.D, p.lr, lane, rs, &st_cur);
-        } else {
-          apply_row(a.rel, a.b.rel_ids[j - p.Nn], w.GR + (j - p.Nn) * (long long)p.Dr, p.Dr, p.lr, lane);
-        }
+        if (j < p.Nn) apply_row(a.ent, a.b.neg_ids[j], w.Bn + j * (long long)p.D, p.D, p.lr, lane, rs);
+        else apply_row(a.rel, a.b.rel_ids[j - p.Nn], w.GR + (j - p.Nn) * (long long)p.Dr, p.Dr, p.lr, lane);
       }
       if (a.log4) {
         const int nb = gridDim.x < 64 ? gridDim.x : 64;

@@ -204,7 +204,6 @@ def _multi_gpu_worker(rank, world, args, n_ent, n_rel, edges, port):
                       LOCAL_RANK=str(rank))
     dev = th.device("cuda", args.gpu[rank])
     th.cuda.set_device(dev)
-    os.environ.setdefault("NCCL_MAX_CTAS", "16")      # the all-reduce shares the GPU with k_update, which leaves it 16 SMs
     dist.init_process_group("nccl", device_id=dev)
     hp = Hyper(model=args.model_name, hidden_dim=args.hidden_dim, gamma=args.gamma, lr=args.lr,
                reg_coef=args.regularization_coef, reg_norm=args.regularization_norm,
