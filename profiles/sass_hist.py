@@ -3,7 +3,8 @@
     python profiles/sass_hist.py > profiles/<tag>_sass.md
 
 UTC*MMA = tcgen05.mma (gdesc = operand from shared memory, tmem = operand from tensor memory), LDTM/STTM = tcgen05.ld/st,
-UTMALDG = TMA tile load (cp.async.bulk.tensor), UBLKCP = cp.async.bulk, SYNCS = mbarrier ops, REDG/ATOMG = global
+UTMALDG = TMA tile load (cp.async.bulk.tensor), UBLKCP = cp.async.bulk, UBLKRED = cp.reduce.async.bulk (row scatter of the
+update, into local or peer HBM), FFMA2/FMUL2/FADD2 = packed fp32x2 (RotatE), SYNCS = mbarrier ops, REDG/ATOMG = global
 reductions / atomics (".SYS" = system scope: NVLink peers), MUFU = special-function unit, HMMA would be the legacy path."""
 import collections
 import os
@@ -13,8 +14,8 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "dgl-ke_b200", "lib", "libkge_b200.so")
-KEYS = ["UTCHMMA", "UTCHMMA(tmem A)", "LDTM", "STTM", "UTMALDG", "UBLKCP", "SYNCS", "UTCBAR", "REDG", "REDG.SYS", "ATOMG", "LDG", "STG",
-        "LDS", "STS", "MUFU", "FFMA", "HMMA", "BAR"]
+KEYS = ["UTCHMMA", "UTCHMMA(tmem A)", "LDTM", "STTM", "UTMALDG", "UBLKCP", "UBLKRED", "SYNCS", "UTCBAR", "REDG", "REDG.SYS", "ATOMG", "LDG",
+        "STG", "LDS", "STS", "MUFU", "FFMA", "FFMA2", "FMUL2", "FADD2", "HMMA", "BAR"]
 
 
 def main():

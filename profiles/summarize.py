@@ -35,7 +35,7 @@ def launches(path):
 def short(name):
     """Canonical kernel label: namespaces (kge::, the anonymous namespace in either spelling) and the argument list
     dropped, template arguments kept (k_fused<0> and k_fused<1> are different kernels)."""
-    name = re.sub(r"\(anonymous namespace\)::|<unnamed>::|kge::|^void ", "", name)
+    name = re.sub(r"\(anonymous namespace\)::|<unnamed>::|unnamed>::|kge::|^void ", "", name)
     depth, out = 0, []
     for ch in name:                      # cut at the first '(' outside template brackets
         if ch == "<":
@@ -58,9 +58,14 @@ def main():
     with open("profiles/%s_launches.md" % tag, "w") as f:
         f.write("# %s: every launch with its device time (ncu --metrics gpu__time_duration.sum --clock-control none)\n\n" % tag)
         f.write("Cold-cache, serialised launches: compare SHARES, not absolutes.  %d steps in the list.\n\n" % steps)
-        f.write("| kernel | launches | per step | avg us | share |\n|---|---|---|---|---|\n")
+        own = {n: v for n, v in agg.items() if n.startswith("k_") and len(v) >= steps}
+        tot_own = sum(sum(v) for v in own.values())
+        f.write("Share = of the step's own kernels (k_*, launched every step); the other rows are the bench harness (table "
+                "initialisation, L2 flush, profiling spin) and one-time set-up.\n\n")
+        f.write("| kernel | launches | per step | avg us | share of the step |\n|---|---|---|---|---|\n")
         for n, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
-            f.write("| `%s` | %d | %.2f | %.2f | %.3f |\n" % (n, len(v), len(v) / steps, sum(v) / len(v), sum(v) / tot))
+            f.write("| `%s` | %d | %.2f | %.2f | %s |\n" % (n, len(v), len(v) / steps, sum(v) / len(v),
+                                                           "%.3f" % (sum(v) / tot_own) if n in own else "-"))
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     h = rows[0]
@@ -88,8 +93,13 @@ def main():
                 per_kernel.setdefault(short(r[ki]), []).append(rd * mul("dram__bytes_read.sum") + wr * mul("dram__bytes_write.sum"))
             except Exception:
                 pass
+    # the kernels of a STEP: the library's own (k_*) that run every step.  The bench harness's kernels (torch's table
+    # initialisation, the 256 MiB L2-flush fill, the profiling spin) and one-time set-up kernels (fewer launches than steps)
+    # are listed in the launch table but are not part of the step's traffic.
     detail, missing = {}, []
     for n, v in agg.items():
+        if not n.startswith("k_") or len(v) < steps:
+            continue
         if n in per_kernel:
             detail[n] = sum(per_kernel[n]) / len(per_kernel[n]) * (len(v) / steps)
         else:
