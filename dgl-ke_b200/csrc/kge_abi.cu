@@ -167,6 +167,15 @@ int make_params(const kge_step_cfg_t* cfg, long long n_nodes, StepParams* p, boo
   p->U = n_nodes >= 0 ? n_nodes : 2 * p->B;      // capacity when only the device knows the count
   p->U_dev = nullptr;
   p->rel_deferred = 0; p->rel_dense = 0; p->use_nc = 1; p->fused = 0; p->nc_staged = 0;
+  if (cfg->loss_genre < KGE_LOSS_LOGSIGMOID || cfg->loss_genre > KGE_LOSS_BCE)
+    return fail(KGE_ERR_INVALID_ARG, "loss_genre %d is not a kge_loss_t", cfg->loss_genre);
+  if (cfg->pairwise && cfg->loss_genre != KGE_LOSS_HINGE && cfg->loss_genre != KGE_LOSS_LOGISTIC)
+    return fail(KGE_ERR_INVALID_ARG, "pairwise needs the Hinge or the Logistic criterion (loss.py:61-62)");
+  if (cfg->pairwise && cfg->adversarial)
+    return fail(KGE_ERR_INVALID_ARG, "loss cannot be pairwise and adversarial sampled (base_loss.py:83-84)");
+  p->hinge = cfg->loss_genre == KGE_LOSS_HINGE ? 1 : 0;
+  p->margin = cfg->margin;
+  p->pairwise = cfg->pairwise ? 1 : 0;
 
   (void)need_tables;
   return KGE_OK;

@@ -53,6 +53,9 @@ struct StepParams {
   int rel_dense;     // 1: k_chain sums relation gradients per relation into ws.rg / ws.rgs (fused single-GPU step)
   int use_nc;        // 1: head/tail rows are read from the gathered copy NC (3-call API, sharded tables); 0: from the table
   int fused;         // 1: contraction by the fused tcgen05 kernel (kge_fused.cu): operands exist only as TF32 hi/lo slabs
+  int hinge;         // 1: Hinge criterion (loss.py:10-17); 0: Logsigmoid == Logistic == BCE
+  float margin;      // Hinge margin
+  int pairwise;      // 1: criterion(pos_i - neg_ij, +1), plain mean over all (i, j) (loss.py:76-80)
   int nc_staged;     // 1: NC was filled by the previous step's prefetch warps (kge_set_next_batch): no k_gather_nodes ran
 };
 

@@ -356,11 +356,35 @@ void launch_prep_dense(const LaunchCtx& c, const StepParams& p, const float* hea
 struct LossRow {
   float w_i, inv2B, T, mx, den, uni;
   int adversarial, l2;
+  int hinge, pairwise;
+  float margin, ps, invBN;     // pairwise: the row's positive score, 1 / (B * Ns)
 };
-__device__ __forceinline__ float loss_elem(const LossRow& r, float sc, float dist, float& nls, float& rs) {
-  const float pij = r.adversarial ? expf(sc * r.T - r.mx) / r.den : r.uni;
-  nls += pij * (softplusf(sc) * r.w_i);
-  const float g = pij * sigmoidf(sc) * r.w_i * r.inv2B;       // dL/dneg_ij
+// criterion(x, label) and d/dx for label = +1 / -1 (loss.py:10-38): Hinge max(0, m - label x) -- zero gradient only where
+// the term is strictly negative (`loss[loss < 0] = 0`); Logsigmoid / Logistic / BCE softplus(-label x)
+__device__ __forceinline__ float crit(const LossRow& r, float x, float label, float& dx) {
+  if (r.hinge) {
+    const float t = r.margin - label * x;
+    dx = (t < 0.f) ? 0.f : -label;
+    return fmaxf(t, 0.f);
+  }
+  dx = -label * sigmoidf(-label * x);
+  return softplusf(-label * x);
+}
+__device__ __forceinline__ float loss_elem(const LossRow& r, float sc, float dist, float& nls, float& rs, float& gp) {
+  float g;
+  if (r.pairwise) {
+    float dd;
+    const float l = crit(r, r.ps - sc, 1.f, dd);           // criterion(pos_i - neg_ij, 1) * w_i, mean over all pairs
+    nls += l * r.w_i * r.uni;
+    g = -dd * r.w_i * r.invBN;                               // dL/dneg_ij
+    gp += dd * r.w_i * r.invBN;                              // dL/dpos_i, summed over j by the caller
+  } else {
+    const float pij = r.adversarial ? expf(sc * r.T - r.mx) / r.den : r.uni;
+    float dd;
+    const float l = crit(r, sc, -1.f, dd);
+    nls += pij * (l * r.w_i);
+    g = pij * dd * r.w_i * r.inv2B;                          // dL/dneg_ij
+  }
   float coef = g;
   // dist = |a-b| from the score kernel; a clamped distance (sq <= 1e-30) has zero gradient in the reference (clamp_min_)
   if (r.l2) { coef = (dist > 1.5e-15f) ? g / dist : 0.f; rs += coef; }
@@ -382,7 +406,10 @@ __global__ void __launch_bounds__(kRowBlock) k_loss(StepParams p, const float* _
   r.w_i = wt ? wt[i] : 1.f;
   r.inv2B = 0.5f / (float)p.B;
   r.T = p.adv_temperature; r.mx = -INFINITY; r.den = 1.f; r.uni = 1.f / (float)p.Ns;
-  r.adversarial = p.adversarial; r.l2 = (p.model == KGE_TRANSE_L2);
+  r.adversarial = p.adversarial && !p.pairwise; r.l2 = (p.model == KGE_TRANSE_L2);
+  r.hinge = p.hinge; r.pairwise = p.pairwise; r.margin = p.margin;
+  r.ps = pos[i]; r.invBN = 1.f / ((float)p.B * (float)p.Ns);
+  float gp = 0.f;
   const long long chunk = i / p.Cs;
   const int il = (int)(i % p.Cs), nblk = slab_blocks(p.Ns);
   float nls = 0.f, rs = 0.f;
@@ -395,7 +422,7 @@ __global__ void __launch_bounds__(kRowBlock) k_loss(StepParams p, const float* _
       sc[q] = (j < p.Ns) ? s[j] : -INFINITY;
       ds[q] = (r.l2 && j < p.Ns) ? v[j] : 1.f;
     }
-    if (p.adversarial) {
+    if (r.adversarial) {
       float mx = -INFINITY;
 #pragma unroll
       for (int q = 0; q < 8; ++q) mx = fmaxf(mx, sc[q] * r.T);     // padding contributes -inf
@@ -409,7 +436,7 @@ __global__ void __launch_bounds__(kRowBlock) k_loss(StepParams p, const float* _
     for (int q = 0; q < 8; ++q) {
       const int j = lane + kWarp * q;
       if (j >= p.Ns) continue;
-      const float coef = loss_elem(r, sc[q], ds[q], nls, rs);
+      const float coef = loss_elem(r, sc[q], ds[q], nls, rs, gp);
       v[j] = coef;
       if (Vhi) {
         float hh, ll;
@@ -419,7 +446,7 @@ __global__ void __launch_bounds__(kRowBlock) k_loss(StepParams p, const float* _
       }
     }
   } else {
-    if (p.adversarial) {
+    if (r.adversarial) {
       float mx = -INFINITY;
       for (int j = lane; j < p.Ns; j += kWarp) mx = fmaxf(mx, s[j] * r.T);
       r.mx = warp_max(mx);
@@ -428,7 +455,7 @@ __global__ void __launch_bounds__(kRowBlock) k_loss(StepParams p, const float* _
       r.den = warp_sum(d);
     }
     for (int j = lane; j < p.Ns; j += kWarp) {
-      const float coef = loss_elem(r, s[j], r.l2 ? v[j] : 1.f, nls, rs);
+      const float coef = loss_elem(r, s[j], r.l2 ? v[j] : 1.f, nls, rs, gp);
       v[j] = coef;
       if (Vhi) {
         float hh, ll;
@@ -440,12 +467,19 @@ __global__ void __launch_bounds__(kRowBlock) k_loss(StepParams p, const float* _
   }
   nls = warp_sum(nls);
   rs = warp_sum(rs);
+  gp = warp_sum(gp);
   if (lane == 0) {
     float ps = pos[i];
     float wb = wt ? *wbar : 1.f;        // loss.py:75,82: [B] * [B,1] -> mean(pl) * mean(w)
-    pl[i] = softplusf(-ps);
+    if (p.pairwise) {                   // one term per (i, j) pair; no separate positive loss
+      pl[i] = 0.f;
+      gpos[i] = gp;
+    } else {
+      float dd;
+      pl[i] = crit(r, ps, 1.f, dd);
+      gpos[i] = dd * wb * r.inv2B;
+    }
     nl[i] = nls;
-    gpos[i] = -sigmoidf(-ps) * wb * r.inv2B;
     if (r.l2) rowsum[i] = rs;
   }
 }
@@ -528,7 +562,9 @@ __device__ void reduce_log_part(const StepParams& p, const StepWs& w, long long 
     if (threadIdx.x == 0) {
       float pos_loss = sa / (float)p.B * (wbar ? *wbar : 1.f);
       float neg_loss = sb / (float)p.B;
-      log4[0] = pos_loss; log4[1] = neg_loss; log4[2] = (neg_loss + pos_loss) / 2.f;
+      // pairwise (loss.py:76-80): the mean over all pairs IS the loss, and the log holds no pos_loss / neg_loss
+      log4[0] = p.pairwise ? 0.f : pos_loss; log4[1] = p.pairwise ? 0.f : neg_loss;
+      log4[2] = p.pairwise ? neg_loss : (neg_loss + pos_loss) / 2.f;
       log4[3] = p.reg_coef * sr;
       *ticket = 0u;      // ready for the next step
     }

@@ -26,6 +26,9 @@ class Hyper:
     adv_temperature: float = 1.0
     double_ent: bool = False
     double_rel: bool = False
+    loss_genre: str = "Logsigmoid"      # Hinge | Logistic | Logsigmoid | BCE  (loss.py:41-62)
+    margin: float = 1.0
+    pairwise: bool = False
 
     @property
     def emb_init(self):
@@ -77,7 +80,7 @@ class StepEngine:
         hp = self.hp
         return _lib.make_cfg(hp.model, hp.entity_dim, hp.relation_dim, hp.gamma, hp.emb_init, hp.lr, hp.reg_coef,
                              hp.reg_norm, hp.adversarial, hp.adv_temperature, neg_head, batch, chunk_size,
-                             neg_sample_size)
+                             neg_sample_size, hp.loss_genre, hp.margin, hp.pairwise)
 
     # ---- the three-call shape of train_pytorch.py:141-152 -------------------------------------
     def forward_backward(self, node_ids, head_local, tail_local, rel_ids, neg_ids, chunk_size, neg_sample_size,
@@ -189,7 +192,7 @@ class StepEngine:
 def _cfg_for(hp, batch, chunk_size, neg_sample_size, neg_head):
     return _lib.make_cfg(hp.model, hp.entity_dim, hp.relation_dim, hp.gamma, hp.emb_init, hp.lr, hp.reg_coef,
                          hp.reg_norm, hp.adversarial, hp.adv_temperature, neg_head, batch, chunk_size,
-                         neg_sample_size)
+                         neg_sample_size, hp.loss_genre, hp.margin, hp.pairwise)
 
 
 def gather(table, idx):

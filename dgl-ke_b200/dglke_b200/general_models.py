@@ -39,7 +39,9 @@ class KEModel(object):
                              reg_norm=getattr(args, "regularization_norm", 3),
                              adversarial=getattr(args, "neg_adversarial_sampling", False),
                              adv_temperature=getattr(args, "adversarial_temperature", 1.0),
-                             double_ent=double_entity_emb, double_rel=double_relation_emb)
+                             double_ent=double_entity_emb, double_rel=double_relation_emb,
+                             loss_genre=getattr(args, "loss_genre", "Logsigmoid"), margin=getattr(args, "margin", 1.0),
+                             pairwise=getattr(args, "pairwise", False))
         entity_dim, rel_dim = self.hyper.entity_dim, self.hyper.relation_dim
         self.entity_dim, self.rel_dim = entity_dim, rel_dim
         self.strict_rel_part = getattr(args, "strict_rel_part", False)
@@ -156,7 +158,7 @@ class KEModel(object):
             eng.step_begin(batch, chunk_size=neg_g.chunk_size, neg_sample_size=neg_g.neg_sample_size)
             self._fused_pending = True
             with_reg = self.hyper.reg_coef > 0.0 and self.hyper.reg_norm > 0
-            return FusedLoss(eng.log4, with_reg, lazy=True), LazyLog(eng.log4, has_reg=with_reg, lazy=True)
+            return FusedLoss(eng.log4, with_reg, lazy=True), LazyLog(eng.log4, has_reg=with_reg, lazy=True, only_loss=self.hyper.pairwise)
         dev = self.device
         mv = lambda t: t if t.device == dev else t.to(dev, non_blocking=True)
         head_local, tail_local = pos_g.all_edges(order="eid")
@@ -166,7 +168,7 @@ class KEModel(object):
         log4 = eng.forward_backward(mv(pos_g.ndata["id"]), mv(head_local), mv(tail_local), mv(pos_g.edata["id"]),
                                     mv(neg_ids), neg_g.chunk_size, neg_g.neg_sample_size, bool(neg_g.neg_head), w)
         with_reg = self.hyper.reg_coef > 0.0 and self.hyper.reg_norm > 0
-        return FusedLoss(log4, with_reg), LazyLog(log4, has_reg=with_reg)
+        return FusedLoss(log4, with_reg), LazyLog(log4, has_reg=with_reg, only_loss=self.hyper.pairwise)
 
     def update(self, gpu_id=-1):
         if getattr(self, "_fused_pending", False):

@@ -37,7 +37,7 @@ extern "C" {
 #define KGE_API
 #endif
 
-#define KGE_ABI_VERSION 2
+#define KGE_ABI_VERSION 3
 #define KGE_MAX_SHARDS 8
 
 typedef enum {
@@ -96,7 +96,15 @@ typedef struct {
   int64_t batch;            /* B positives; must equal num_chunks * chunk_size            */
   int32_t chunk_size;       /* positives per chunk                                        */
   int32_t neg_sample_size;  /* negatives per chunk                                        */
+  /* ABI 3: the loss criterion (models/pytorch/loss.py:10-62).  Logistic and BCE are the Logsigmoid criterion written
+   * differently (softplus(-l*s) == -logsigmoid(l*s); BCE with labels 1 / 0 likewise) and share its kernels; the
+   * reference's BCE evaluates log(sigmoid(s)) and overflows to inf beyond |s| ~ 88 where this library stays finite. */
+  int32_t loss_genre;       /* kge_loss_t                                                 */
+  float margin;             /* Hinge: max(0, margin - label * score)                      */
+  int32_t pairwise;         /* -pw: criterion(pos_i - neg_ij, 1), mean over all pairs (Hinge / Logistic only; the
+                             * self-adversarial weighting does not apply, loss.py:76-80)   */
 } kge_step_cfg_t;
+typedef enum { KGE_LOSS_LOGSIGMOID = 0, KGE_LOSS_HINGE = 1, KGE_LOSS_LOGISTIC = 2, KGE_LOSS_BCE = 3 } kge_loss_t;
 
 /* The sampled batch, exactly the tensors KEModel.forward pulls out of (pos_g, neg_g)
  * (models/general_models.py:376-427,548-549):

@@ -41,6 +41,20 @@ CASES.append(("tc_ComplEx_adv", "ComplEx", dict(adv=True, hidden=32, batch=16, c
 CASES.append(("tc_RESCAL_adv", "RESCAL", dict(adv=True, hidden=32, batch=16, chunk=8, neg=8, n_ent=60, n_rel=3)))
 
 
+# the other loss criteria and the pairwise form (loss.py:10-62,76-80)
+CASES.append(("loss_Hinge_TransE_l2_adv", "TransE_l2", dict(adv=True, loss_genre="Hinge", margin=1.0, gamma=4.0)))
+CASES.append(("loss_Hinge_DistMult_uni_impts", "DistMult", dict(adv=False, loss_genre="Hinge", margin=0.5, impts=True)))
+CASES.append(("loss_Logistic_ComplEx_adv", "ComplEx", dict(adv=True, loss_genre="Logistic")))
+CASES.append(("loss_BCE_TransE_l1_uni", "TransE_l1", dict(adv=False, loss_genre="BCE")))
+CASES.append(("loss_pw_Logistic_DistMult", "DistMult", dict(adv=False, loss_genre="Logistic", pairwise=True)))
+CASES.append(("loss_pw_Hinge_TransE_l2_impts", "TransE_l2", dict(adv=False, loss_genre="Hinge", margin=2.0, pairwise=True,
+                                                                   impts=True, gamma=4.0)))
+CASES.append(("tc_loss_pw_Hinge_RotatE", "RotatE", dict(adv=False, loss_genre="Hinge", margin=1.0, pairwise=True, hidden=16,
+                                                        batch=16, chunk=8, neg=8, n_ent=60)))
+CASES.append(("tc_loss_Hinge_ComplEx", "ComplEx", dict(adv=True, loss_genre="Hinge", margin=1.0, hidden=32, batch=16,
+                                                       chunk=8, neg=8, n_ent=60)))
+
+
 def one_case(name, model, o):
     n_ent, n_rel = o.get("n_ent", 40), o.get("n_rel", 5)
     hidden = o.get("hidden", 8)
@@ -50,7 +64,9 @@ def one_case(name, model, o):
     args = rh.make_args(lr=o.get("lr", 0.25), regularization_coef=o.get("reg_coef", 2e-4),
                         regularization_norm=o.get("reg_norm", 3),
                         neg_adversarial_sampling=o["adv"], adversarial_temperature=o.get("temp", 1.5),
-                        has_edge_importance=bool(o.get("impts", False)))
+                        has_edge_importance=bool(o.get("impts", False)),
+                        loss_genre=o.get("loss_genre", "Logsigmoid"), margin=o.get("margin", 1.0),
+                        pairwise=bool(o.get("pairwise", False)))
     m = rh.build_reference_model(model, n_ent, n_rel, hidden, gamma, args, double_ent=double_ent, seed=7)
     rng = np.random.default_rng(1234)
     fx = dict(ent_emb0=m.entity_emb.emb.clone().numpy(), rel_emb0=m.relation_emb.emb.clone().numpy())
@@ -59,7 +75,9 @@ def one_case(name, model, o):
                 adversarial=bool(o["adv"]), adv_temperature=args.adversarial_temperature,
                 double_ent=double_ent, double_rel=False, batch=batch, chunk_size=chunk,
                 neg_sample_size=neg, num_chunks=batch // chunk, steps=2,
-                has_edge_importance=bool(o.get("impts", False)))
+                has_edge_importance=bool(o.get("impts", False)),
+                loss_genre=o.get("loss_genre", "Logsigmoid"), margin=o.get("margin", 1.0),
+                pairwise=bool(o.get("pairwise", False)))
     C = batch // chunk
     for step in range(2):
         neg_head = (step % 2 == 1)          # sampler.py:853-859: tail first, then head

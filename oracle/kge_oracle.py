@@ -38,6 +38,9 @@ class Hyper:
     adv_temperature: float = 1.0
     double_ent: bool = False
     double_rel: bool = False
+    loss_genre: str = "Logsigmoid"      # models/pytorch/loss.py:41-62
+    margin: float = 1.0
+    pairwise: bool = False
 
     @property
     def emb_init(self):
@@ -156,15 +159,39 @@ def negative_score(hp, heads, rels, tails, num_chunks, chunk_size, neg_sample_si
 
 
 # --------------------------------------------------------------------------- a7
+def criterion(hp, score, label):
+    """The four loss criteria (models/pytorch/loss.py:10-38)."""
+    if hp.loss_genre == "Hinge":
+        loss = hp.margin - label * score
+        return th.where(loss < 0, th.zeros_like(loss), loss)          # `loss[loss < 0] = 0`
+    if hp.loss_genre == "Logistic":
+        return th.nn.functional.softplus(-label * score)
+    if hp.loss_genre == "BCE":
+        sg = th.sigmoid(score)
+        return -(label * th.log(sg) + (1 - label) * th.log(1 - sg))
+    if hp.loss_genre == "Logsigmoid":
+        return -th.nn.functional.logsigmoid(label * score)
+    raise ValueError("loss genre %s is not support" % hp.loss_genre)
+
+
 def loss_terms(hp, pos_score, neg_score, edge_weight=None):
-    """LossGenerator.get_total_loss, Logsigmoid criterion (models/pytorch/loss.py:69-98).
+    """LossGenerator.get_total_loss (models/pytorch/loss.py:41-98).
 
     pos_score [B], neg_score [B, Ns].  Returns (loss tensor, log dict).  With an edge
     weight the reference views it [B,1] and multiplies the [B] positive loss by it, which
-    broadcasts to [B,B] (loss.py:75,82) -- reproduced."""
+    broadcasts to [B,B] (loss.py:75,82) -- reproduced.  pairwise (loss.py:76-80): one term per
+    (positive, negative) pair, plain mean, no adversarial weighting, log holds 'loss' only."""
     w = 1 if edge_weight is None else edge_weight.view(-1, 1)
-    pos_l = -th.nn.functional.logsigmoid(pos_score) * w
-    neg_l = -th.nn.functional.logsigmoid(-neg_score) * w
+    if hp.pairwise:
+        if hp.loss_genre not in ("Logistic", "Hinge"):
+            raise ValueError("%s loss cannot be applied to pairwise loss function" % hp.loss_genre)
+        if hp.adversarial:
+            raise ValueError("loss cannot be pairwise and adversarial sampled")      # base_loss.py:83-84
+        loss = th.mean(criterion(hp, pos_score.unsqueeze(-1) - neg_score, 1) * w)
+        return loss, {"loss": float(loss.detach())}
+    neg_label = 0 if hp.loss_genre == "BCE" else -1
+    pos_l = criterion(hp, pos_score, 1) * w
+    neg_l = criterion(hp, neg_score, neg_label) * w
     if hp.adversarial:
         p = th.softmax(neg_score * hp.adv_temperature, dim=-1).detach()
         neg_l = th.sum(p * neg_l, dim=-1)

@@ -23,16 +23,17 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), "libkge_b200.so does not export %s" % n
     assert sorted(names) == sorted(_lib.EXPORTS)
-    assert lib.kge_abi_version() == 2
+    assert lib.kge_abi_version() == 3
 
 
 def test_struct_layouts_match_header():
     from dglke_b200 import _lib
     assert C.sizeof(_lib.Shard) == 40
     assert C.sizeof(_lib.Table) == 32
-    assert C.sizeof(_lib.StepCfg) == 64
+    assert C.sizeof(_lib.StepCfg) == 80
     assert C.sizeof(_lib.Batch) == 80
     assert _lib.StepCfg.batch.offset == 48 and _lib.StepCfg.neg_sample_size.offset == 60
+    assert _lib.StepCfg.loss_genre.offset == 64 and _lib.StepCfg.margin.offset == 68 and _lib.StepCfg.pairwise.offset == 72
 
 
 def test_fails_loudly_without_gpu():

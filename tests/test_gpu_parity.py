@@ -19,7 +19,8 @@ def _engine(hp, ent, ent_s, rel, rel_s):
     e, es, r, rs = (x.to(dev).contiguous() for x in (ent, ent_s, rel, rel_s))
     hyper = Hyper(model=hp.model, hidden_dim=hp.hidden_dim, gamma=hp.gamma, lr=hp.lr, reg_coef=hp.reg_coef,
                   reg_norm=hp.reg_norm, adversarial=hp.adversarial, adv_temperature=hp.adv_temperature,
-                  double_ent=hp.double_ent, double_rel=hp.double_rel)
+                  double_ent=hp.double_ent, double_rel=hp.double_rel, loss_genre=hp.loss_genre, margin=hp.margin,
+                  pairwise=hp.pairwise)
     eng = StepEngine(hyper, DeviceTable.from_tensors(e, es), DeviceTable.from_tensors(r, rs), 0)
     return eng, (e, es, r, rs)
 
@@ -217,6 +218,63 @@ def test_gather_bit_exact_and_unfused_ops():
     E.adagrad(tab2, ii.to(dev), g.to(dev), 0.3)
     np.testing.assert_allclose(tab2.emb_shards[0].cpu().numpy(), e2.numpy(), rtol=2e-5, atol=1e-7)
     np.testing.assert_allclose(tab2.state_shards[0].cpu().numpy(), s2.numpy(), rtol=2e-5, atol=1e-9)
+
+
+LOSSES = [("Hinge", False, True, 1.0), ("Hinge", False, False, 0.3), ("Hinge", True, False, 2.0), ("Logistic", False, True, 1.0),
+          ("Logistic", True, False, 1.0), ("BCE", False, True, 1.0), ("Logsigmoid", False, False, 1.0)]
+
+
+@pytest.mark.parametrize("genre,pairwise,adv,margin", LOSSES)
+@pytest.mark.parametrize("Ns", [200, 300])           # row in registers (<= 256) / streamed
+def test_loss_criteria_match_oracle(genre, pairwise, adv, margin, Ns):
+    """LossGenerator.get_total_loss and its score gradients for every criterion of loss.py:10-62 (+ -pw, -adv, edge
+    weights) against autograd on the oracle's restatement -- which tests/test_oracle_golden.py pins to the reference."""
+    from dglke_b200.loss import LossGenerator
+    import argparse
+    dev = th.device("cuda", 0)
+    B = 96
+    gen = th.Generator().manual_seed(sum(map(ord, genre)) + 7 * pairwise + 13 * adv + Ns)
+    pos, neg = th.randn(B, generator=gen) * 2, th.randn(B, Ns, generator=gen) * 2
+    w = th.rand(B, generator=gen) + 0.5
+    hp = ko.Hyper(adversarial=adv, adv_temperature=0.8, loss_genre=genre, margin=margin, pairwise=pairwise)
+    lg = LossGenerator(argparse.Namespace(margin=margin), genre, adv, 0.8, pairwise)
+    for weight in (None, w):
+        # the oracle in float64: the reference's BCE evaluates log(1 - sigmoid(s)), which loses ~1e-4 of relative
+        # precision in fp32 for s ~ 9 -- the library computes the same quantity as softplus(s)
+        pl, nl = pos.double().requires_grad_(True), neg.double().requires_grad_(True)
+        loss, log = ko.loss_terms(hp, pl, nl, None if weight is None else weight.double())
+        loss.backward()
+        wd = None if weight is None else weight.to(dev)
+        got_loss, got_log = lg.get_total_loss(pos.to(dev), neg.to(dev), wd)
+        dpos, dneg = lg.score_gradients(pos.to(dev), neg.to(dev), wd)
+        assert sorted(got_log.keys()) == sorted(log.keys())
+        for k in log:
+            np.testing.assert_allclose(got_log[k], log[k], rtol=2e-5, err_msg=k)
+        np.testing.assert_allclose(float(got_loss), float(loss), rtol=2e-5)
+        np.testing.assert_allclose(dpos.cpu().numpy(), pl.grad.numpy(), rtol=2e-5, atol=1e-9)
+        np.testing.assert_allclose(dneg.cpu().numpy(), nl.grad.numpy(), rtol=2e-5, atol=1e-10)
+
+
+@pytest.mark.parametrize("genre,pairwise,adv,margin", [("Hinge", False, True, 1.0), ("Logistic", True, False, 1.0),
+                                                       ("Hinge", True, False, 4.0), ("Logistic", False, True, 1.0)])
+def test_training_step_with_other_criteria_at_hot_shape(genre, pairwise, adv, margin):
+    """d=400, neg=200: Hinge / pairwise take the stand-alone GEMM + k_loss route (the fused kernel's epilogue is the
+    Logsigmoid family), Logistic without -pw stays on the fused kernel; both against the oracle.  (BCE is left to the
+    small-score tests: at gamma = 19.9 the reference's own log(1 - sigmoid(s)) is -inf in fp32.)"""
+    hp = ko.Hyper(model="TransE_l2", hidden_dim=400, gamma=19.9, lr=0.25, reg_coef=1e-7, adversarial=adv,
+                  loss_genre=genre, margin=margin, pairwise=pairwise)
+    ent, es, rel, rs = ko.init_tables(hp, 3000, 40, seed=3)
+    for neg_head in (False, True):
+        si, C = _random_step(hp, 3000, 40, 400, 200, 200, neg_head, seed=11)
+        tables = [x.clone() for x in (ent, es, rel, rs)]
+        o = [x.clone() for x in tables]
+        fb = ko.train_step(hp, o[0], o[1], o[2], o[3], si["node_ids"], si["head_local"], si["tail_local"], si["rel_ids"],
+                           si["neg_ids"], C, 200, 200, neg_head)
+        ref = dict(pos_score=fb["pos_score"].numpy(), neg_score=fb["neg_score"].numpy(),
+                   log={k: fb["log"].get(k, 0.0) for k in ("pos_loss", "neg_loss", "loss", "regularization")},
+                   nodes_grad=fb["nodes_grad"].numpy(), negs_grad=fb["negs_grad"].numpy(), rels_grad=fb["rels_grad"].numpy(),
+                   ent_emb=o[0].numpy(), ent_state=o[1].numpy(), rel_emb=o[2].numpy(), rel_state=o[3].numpy())
+        _run_and_check(hp, tables, si, C, 200, 200, ref, tol=5e-5)
 
 
 @pytest.mark.parametrize("pinned", [False, True])

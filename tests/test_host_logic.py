@@ -106,12 +106,29 @@ def test_lazy_log_and_fused_loss_read_device_scalars_lazily():
     assert loss.backward() is None and abs(float(loss) - 0.625) < 1e-7 and loss.item() == float(loss)
 
 
-def test_unsupported_options_raise_instead_of_falling_back():
-    from dglke_b200.loss import LossGenerator
-    with pytest.raises(NotImplementedError):
-        LossGenerator(None, "Hinge")
-    with pytest.raises(NotImplementedError):
+def test_loss_generator_argument_errors_match_the_reference():
+    """loss.py:58-62, base_loss.py:83-84: the same ValueErrors for the same argument combinations."""
+    from dglke_b200.loss import LossGenerator, LazyLog
+    for genre in ("Hinge", "Logistic", "Logsigmoid", "BCE"):
+        g = LossGenerator(None, genre)
+        assert g.neg_label == (0 if genre == "BCE" else -1) and g.pairwise is False
+    assert LossGenerator(None, "Hinge", pairwise=True).pairwise and LossGenerator(None, "Logistic", pairwise=True).pairwise
+    with pytest.raises(ValueError):
         LossGenerator(None, "Logsigmoid", pairwise=True)
+    with pytest.raises(ValueError):
+        LossGenerator(None, "BCE", pairwise=True)
+    with pytest.raises(ValueError):
+        LossGenerator(None, "Hinge", neg_adversarial_sampling=True, pairwise=True)
+    with pytest.raises(ValueError):
+        LossGenerator(None, "Huber")
+    # the pairwise form logs 'loss' (+ 'regularization') only (loss.py:78-80)
+    assert sorted(LazyLog(th.zeros(4), has_reg=True, only_loss=True).keys()) == ["loss", "regularization"]
+    assert sorted(LazyLog(th.zeros(4), has_reg=False, only_loss=True).keys()) == ["loss"]
+
+
+def test_unsupported_options_raise_instead_of_falling_back():
     from dglke_b200 import _lib
     with pytest.raises(_lib.KgeError):
         _lib.make_cfg("TransR", 8, 8, 12.0, 0.1, 0.1, 0.0, 3, False, 1.0, False, 8, 8, 8)
+    with pytest.raises(ValueError):
+        _lib.make_cfg("DistMult", 8, 8, 12.0, 0.1, 0.1, 0.0, 3, False, 1.0, False, 8, 8, 8, loss_genre="Huber")
