@@ -131,12 +131,15 @@ class TripleSampler(SyntheticSampler):
     TrainDataset.create_sampler, dataloader/sampler.py:376-419; exclude_positive=False)."""
 
     def __init__(self, heads, rels, tails, n_entities, n_relations, batch_size, neg_sample_size, seed=0, rank=0,
-                 world=1):
+                 world=1, impts=None):
+        """impts: per-edge importance weights (--has_edge_importance: the 4th column of the triple files), carried into
+        pos_g.edata['impts'] (sampler.py:360-364)"""
         super().__init__(n_entities, n_relations, batch_size, neg_sample_size, seed, rank)
         idx = np.arange(len(heads))
         if world > 1:   # RandomPartition (sampler.py:256-290): a fixed random split of the edges over the ranks
             idx = np.random.default_rng(seed).permutation(len(heads))[rank::world]
         self.h, self.r, self.t = np.asarray(heads)[idx], np.asarray(rels)[idx], np.asarray(tails)[idx]
+        self.w = None if impts is None else np.asarray(impts, dtype=np.float32)[idx]
         self.n_edges = len(self.h)
         if self.n_edges < batch_size:
             raise ValueError("fewer edges (%d) than batch_size (%d)" % (self.n_edges, batch_size))
@@ -151,7 +154,7 @@ class TripleSampler(SyntheticSampler):
         e = self._perm[j * self.B:(j + 1) * self.B]
         rng = np.random.default_rng(self.seed + 15485863 + k)
         ng = rng.integers(0, self.n_ent, self.num_chunks * self.Ns)
-        pos_g = build_pos_graph(self.h[e], self.r[e], self.t[e])
+        pos_g = build_pos_graph(self.h[e], self.r[e], self.t[e], None if self.w is None else self.w[e])
         neg_g = NegGraph(torch.from_numpy(ng.astype(np.int64)), self.num_chunks, self.chunk_size, self.Ns,
                          neg_head=bool(k % 2))
         return pos_g, neg_g

@@ -4,9 +4,10 @@
         --neg_sample_size 200 --hidden_dim 400 --gamma 19.9 --lr 0.25 --max_step 24000 -adv --gpu 0
 
 All reference flags parse.  What differs, and why:
-  * data: there is no network in this environment, so built-in dataset names select the dataset's SHAPE
-    (entities / relations / training edges) and triples are drawn synthetically unless --data_files
-    points at udd_hrt-style integer triple files (entity_file relation_file train_file [valid] [test]);
+  * data: the reference's on-disk formats are read by dglke_b200.dataset (built-in layouts when they are unpacked under
+    --data_path, udd_{hrt..} integer files, raw_udd_{hrt..} string files whose dictionaries get built).  There is no
+    network in this environment: a built-in dataset that is not on disk selects the dataset's SHAPE (entities /
+    relations / training edges) and the triples are drawn synthetically;
   * --gpu is required (no CPU path).  One GPU id: one process, KEModel over the fused 5-kernel step.  Several ids
     (`--gpu 0 1 2 3`, the reference's multi-GPU spelling, train.py:290-317): one process per GPU is spawned, the entity
     table is row-sharded over the GPUs' HBM (replacing --mix_cpu_gpu's host table) and trained through
@@ -34,26 +35,23 @@ BUILTIN_SHAPES = {
 }
 
 
-def _read_udd(args):
-    files = args.data_files
-    if files is None or len(files) < 3:
-        raise SystemExit("--format udd_* needs --data_files entity_file relation_file train_file [valid] [test]")
-    path = lambda f: f if os.path.isabs(f) else os.path.join(args.data_path, f)
-    count = lambda f: sum(1 for line in open(path(f)) if line.strip())
-    n_ent, n_rel = count(files[0]), count(files[1])
-    order = args.format.split("_")[-1]            # e.g. hrt
-    col = {c: i for i, c in enumerate(order)}
-
-    def triples(f):
-        a = np.loadtxt(path(f), dtype=np.int64, delimiter=args.delimiter, ndmin=2)
-        if a.size and (a.min() < 0 or a[:, col["h"]].max() >= n_ent or a[:, col["t"]].max() >= n_ent
-                       or a[:, col["r"]].max() >= n_rel):
-            raise ValueError("triple ids out of range in %s" % f)
-        return a[:, col["h"]], a[:, col["r"]], a[:, col["t"]]
-    train = triples(files[2])
-    valid = triples(files[3]) if len(files) > 3 else None
-    test = triples(files[4]) if len(files) > 4 else None
-    return n_ent, n_rel, train, valid, test
+def _load_dataset(args):
+    """train.py:62-116 of the reference: get_dataset(data_path, dataset, format, delimiter, data_files,
+    has_edge_importance).  Returns (n_entities, n_relations, train, valid, test, dataset or None); a built-in dataset that
+    is not on disk (there is no network here) becomes a synthetic graph of its published shape."""
+    from .dataset import get_dataset
+    if args.format == "built_in" and args.dataset in BUILTIN_SHAPES:
+        try:
+            ds = get_dataset(args.data_path, args.dataset, "built_in")
+        except (FileNotFoundError, NotImplementedError) as e:
+            n_ent, n_rel, n_edges = BUILTIN_SHAPES[args.dataset]
+            print("NOTE: %s\nNOTE: training on a synthetic graph of %s's shape (%d entities, %d relations)" % (
+                e, args.dataset, n_ent, n_rel))
+            return n_ent, n_rel, None, None, None, None
+    else:
+        ds = get_dataset(args.data_path, args.dataset, args.format, args.delimiter, args.data_files,
+                         getattr(args, "has_edge_importance", False))
+    return ds.n_entities, ds.n_relations, ds.train, ds.valid, ds.test, ds
 
 
 class _DevicePosGraph:
@@ -156,17 +154,12 @@ def main(argv=None):
     args.strict_rel_part = args.soft_rel_part = False
     args.batch_size = get_compatible_batch_size(args.batch_size, args.neg_sample_size)
     args.batch_size_eval = get_compatible_batch_size(args.batch_size_eval, args.neg_sample_size_eval)
-    if args.format.startswith("udd") or args.format.startswith("raw_udd"):
-        if args.format.startswith("raw_udd"):
-            raise SystemExit("raw_udd (string ids) is not supported yet: convert to integer udd files first")
-        n_ent, n_rel, tr, va, te = _read_udd(args)
-    else:
-        if args.dataset not in BUILTIN_SHAPES:
-            raise SystemExit("unknown built-in dataset %s" % args.dataset)
-        n_ent, n_rel, n_edges = BUILTIN_SHAPES[args.dataset]
-        print("NOTE: no network -- training on a synthetic graph of %s's shape (%d entities, %d relations)" % (
-            args.dataset, n_ent, n_rel))
-        tr = va = te = None
+    n_ent, n_rel, tr, va, te, dataset = _load_dataset(args)
+    n_edges = BUILTIN_SHAPES[args.dataset][2] if tr is None else len(tr[0])
+    if dataset is not None:
+        print("|Train|: {}  entities: {}  relations: {}".format(len(tr[0]), n_ent, n_rel))
+    if tr is not None and len(tr) == 4 and not args.has_edge_importance:
+        tr = tr[:3]
     if len(args.gpu) > 1:
         return train_multi_gpu(args, n_ent, n_rel, tr if tr is not None else synthetic_edges(n_ent, n_rel, n_edges))
     th.cuda.set_device(args.gpu[0])
@@ -176,7 +169,8 @@ def main(argv=None):
     if host and tr is None:
         sampler = SyntheticSampler(n_ent, n_rel, args.batch_size, args.neg_sample_size, seed=0)
     elif host:
-        sampler = TripleSampler(tr[0], tr[1], tr[2], n_ent, n_rel, args.batch_size, args.neg_sample_size, seed=0)
+        sampler = TripleSampler(tr[0], tr[1], tr[2], n_ent, n_rel, args.batch_size, args.neg_sample_size, seed=0,
+                                impts=tr[3] if len(tr) == 4 else None)
     else:
         edges = tr if tr is not None else synthetic_edges(n_ent, n_rel, n_edges)
         sampler = DeviceGraphSampler(edges[0], edges[1], edges[2], n_ent, args.batch_size, args.neg_sample_size, seed=0,
