@@ -160,12 +160,58 @@ class TripleSampler(SyntheticSampler):
         return pos_g, neg_g
 
 
-def eval_batches(heads, rels, tails, n_entities, batch_size, neg_head, candidates=None):
+class TripleFilter:
+    """Which corruptions of a positive are TRUE triples of the graph (the `filter_false_neg` of DGL's EdgeSampler that
+    the reference's EvalSampler turns on, dataloader/sampler.py:514-597): those candidates get bias -1 and
+    KEModel.forward_test leaves them out of the ranking (general_models.py:463-468) -- the positive's own copy among the
+    candidates included, which is what makes the result the usual filtered MRR.
+
+    Two sorted key arrays ((head, rel) -> tails, (tail, rel) -> heads) built once from all known triples; a batch is two
+    binary searches and one scatter."""
+
+    def __init__(self, heads, rels, tails, n_relations):
+        h, r, t = (np.asarray(a, dtype=np.int64) for a in (heads, rels, tails))
+        self.n_rel = int(n_relations)
+        kt = h * self.n_rel + r
+        o = np.argsort(kt, kind="stable")
+        self.key_tail, self.val_tail = kt[o], t[o]
+        kh = t * self.n_rel + r
+        o = np.argsort(kh, kind="stable")
+        self.key_head, self.val_head = kh[o], h[o]
+
+    def bias(self, heads, rels, tails, n_candidates, neg_head, candidates=None):
+        """float32 [B, n_candidates]: -1 where replacing the head (neg_head) / tail by that candidate gives a known triple,
+        else 0.  `candidates`: sorted entity ids of the columns (default: column j = entity j)."""
+        h, r, t = (np.asarray(a, dtype=np.int64) for a in (heads, rels, tails))
+        keys, K, V = ((t * self.n_rel + r, self.key_head, self.val_head) if neg_head else
+                      (h * self.n_rel + r, self.key_tail, self.val_tail))
+        lo, hi = np.searchsorted(K, keys, "left"), np.searchsorted(K, keys, "right")
+        cnt = hi - lo
+        rows = np.repeat(np.arange(len(keys)), cnt)
+        pos = np.arange(int(cnt.sum())) - np.repeat(np.cumsum(cnt) - cnt, cnt) + np.repeat(lo, cnt)
+        ents = V[pos]
+        out = np.zeros((len(keys), int(n_candidates)), dtype=np.float32)
+        if candidates is None:
+            out[rows, ents] = -1.0
+        else:
+            cand = np.asarray(candidates, dtype=np.int64)
+            j = np.searchsorted(cand, ents)
+            ok = (j < len(cand)) & (cand[np.minimum(j, len(cand) - 1)] == ents)
+            out[rows[ok], j[ok]] = -1.0
+        return out
+
+
+def eval_batches(heads, rels, tails, n_entities, batch_size, neg_head, candidates=None, known=None):
     """Yield (pos_g, neg_g) where every positive is ranked against `candidates` (default: all entities):
     one chunk per batch, chunk_size = batch, neg_sample_size = #candidates (the reference views a
-    full-entity negative graph as one chunk, sampler.py:486-490)."""
-    cand = np.arange(n_entities) if candidates is None else np.asarray(candidates)
+    full-entity negative graph as one chunk, sampler.py:486-490).  known: a TripleFilter -> neg_g.edata['bias']
+    marks the candidates that are true triples (filtered evaluation)."""
+    cand = np.arange(n_entities) if candidates is None else np.sort(np.asarray(candidates))
     cand_t = torch.from_numpy(cand.astype(np.int64))
     for s in range(0, len(heads), batch_size):
         h, r, t = heads[s:s + batch_size], rels[s:s + batch_size], tails[s:s + batch_size]
-        yield build_pos_graph(h, r, t), NegGraph(cand_t, 1, len(h), len(cand), neg_head)
+        neg_g = NegGraph(cand_t, 1, len(h), len(cand), neg_head)
+        if known is not None:
+            neg_g.edata["bias"] = torch.from_numpy(known.bias(h, r, t, len(cand), neg_head,
+                                                              None if candidates is None else cand))
+        yield build_pos_graph(h, r, t), neg_g

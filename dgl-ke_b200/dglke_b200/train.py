@@ -24,7 +24,7 @@ import torch as th
 
 from .utils import ArgParser, get_compatible_batch_size, save_model, prepare_save_path
 from .general_models import KEModel
-from .graph import SyntheticSampler, TripleSampler, eval_batches, NegGraph
+from .graph import SyntheticSampler, TripleSampler, TripleFilter, eval_batches, NegGraph
 from .sampler import DeviceSampler
 
 # (entities, relations, training edges): docs/source/benchmarks.rst dataset table
@@ -176,10 +176,17 @@ def main(argv=None):
         sampler = DeviceGraphSampler(edges[0], edges[1], edges[2], n_ent, args.batch_size, args.neg_sample_size, seed=0,
                                      device=args.gpu[0])
 
+    # filtered evaluation (the default; --no_eval_filter turns it off): candidates that form a triple of train / valid /
+    # test are left out of the ranking (EvalDataset builds its graph from all three splits, sampler.py:604-640)
+    known = None
+    if args.eval_filter and dataset is not None and (va is not None or te is not None):
+        allt = [x for x in (tr, va, te) if x is not None]
+        known = TripleFilter(*(np.concatenate([x[k] for x in allt]) for k in range(3)), n_rel)
+
     def split_batches(split):
         def gen():
             for neg_head in (True, False):
-                yield from eval_batches(split[0], split[1], split[2], n_ent, args.batch_size_eval, neg_head)
+                yield from eval_batches(split[0], split[1], split[2], n_ent, args.batch_size_eval, neg_head, known=known)
         return gen
     train(args, model, sampler, split_batches(va) if (args.valid and va is not None) else None)
     if not args.no_save_emb:

@@ -132,3 +132,30 @@ def test_unsupported_options_raise_instead_of_falling_back():
         _lib.make_cfg("TransR", 8, 8, 12.0, 0.1, 0.1, 0.0, 3, False, 1.0, False, 8, 8, 8)
     with pytest.raises(ValueError):
         _lib.make_cfg("DistMult", 8, 8, 12.0, 0.1, 0.1, 0.0, 3, False, 1.0, False, 8, 8, 8, loss_genre="Huber")
+
+
+def test_triple_filter_marks_exactly_the_true_corruptions():
+    """Filtered evaluation (sampler.py:514-597 filter_false_neg -> neg_g.edata['bias'] = -1): brute force."""
+    from dglke_b200.graph import TripleFilter, eval_batches
+    rng = np.random.default_rng(0)
+    n_ent, n_rel, n = 50, 4, 600
+    h, r, t = rng.integers(0, n_ent, n), rng.integers(0, n_rel, n), rng.integers(0, n_ent, n)
+    f = TripleFilter(h, r, t, n_rel)
+    known = set(zip(h.tolist(), r.tolist(), t.tolist()))
+    for neg_head in (False, True):
+        got = f.bias(h[:40], r[:40], t[:40], n_ent, neg_head)
+        want = np.zeros((40, n_ent), np.float32)
+        for i in range(40):
+            for e in range(n_ent):
+                if ((e, r[i], t[i]) if neg_head else (h[i], r[i], e)) in known:
+                    want[i, e] = -1
+        assert np.array_equal(got, want)
+        assert all(got[i, (h if neg_head else t)[i]] == -1 for i in range(40))      # the positive's own copy is filtered
+        cand = np.sort(rng.choice(n_ent, 20, replace=False))
+        assert np.array_equal(f.bias(h[:40], r[:40], t[:40], 20, neg_head, cand), want[:, cand])
+    # a triple nobody has seen filters nothing
+    assert f.bias([0], [0], [0], n_ent, False).sum() == -sum(1 for e in range(n_ent) if (0, 0, e) in known)
+    for pg, ng in eval_batches(h[:10], r[:10], t[:10], n_ent, 4, True, known=f):
+        b = ng.edata["bias"]
+        assert tuple(b.shape) == (pg.number_of_edges(), n_ent) and b.dtype == th.float32
+        assert ng.num_chunks == 1 and ng.neg_sample_size == n_ent
