@@ -5,6 +5,7 @@ kge_forward_backward / kge_update / kge_step_fused[_host]; KEModel (general_mode
 bench.py are built on it.  Tables are plain torch CUDA tensors (or peer-mapped shards, dist.py).
 """
 import ctypes as C
+import os
 from dataclasses import dataclass
 
 import torch
@@ -82,9 +83,21 @@ class StepEngine:
                              hp.reg_norm, hp.adversarial, hp.adv_temperature, neg_head, batch, chunk_size,
                              neg_sample_size, hp.loss_genre, hp.margin, hp.pairwise)
 
+    def check_ids(self, node_ids, head_local, tail_local, rel_ids, neg_ids):
+        """KGE_B200_CHECK_IDS=1 (debugging aid, costs a device sync): the kernels index the tables with the ids they are
+        given; the reference's tensor indexing raises IndexError on an id outside the table, so does this."""
+        if os.environ.get("KGE_B200_CHECK_IDS") != "1":
+            return
+        for name, t, hi in (("node_ids", node_ids, self.ent.num_rows), ("neg_ids", neg_ids, self.ent.num_rows),
+                            ("rel_ids", rel_ids, self.rel.num_rows), ("head_local", head_local, node_ids.numel()),
+                            ("tail_local", tail_local, node_ids.numel())):
+            if t is not None and t.numel() and (int(t.min()) < 0 or int(t.max()) >= hi):
+                raise IndexError("%s: index out of range [0, %d)" % (name, hi))
+
     # ---- the three-call shape of train_pytorch.py:141-152 -------------------------------------
     def forward_backward(self, node_ids, head_local, tail_local, rel_ids, neg_ids, chunk_size, neg_sample_size,
                          neg_head, edge_weight=None, log4=None):
+        self.check_ids(node_ids, head_local, tail_local, rel_ids, neg_ids)
         cfg = self.cfg(head_local.numel(), chunk_size, neg_sample_size, neg_head)
         b, keep = _lib.make_batch(node_ids, head_local, tail_local, rel_ids, neg_ids, edge_weight)
         out = self.log4 if log4 is None else log4
