@@ -109,7 +109,6 @@ typedef enum { KGE_LOSS_LOGSIGMOID = 0, KGE_LOSS_HINGE = 1, KGE_LOSS_LOGISTIC = 
 /* The sampled batch, exactly the tensors KEModel.forward pulls out of (pos_g, neg_g).  The kernels index the tables
  * with these ids as given: an id outside [0, num_rows) is undefined behaviour (the reference's tensor indexing raises
  * IndexError); the Python layer validates them when KGE_B200_CHECK_IDS=1.
- *
  * (models/general_models.py:376-427,548-549):
  *   node_ids   = pos_g.ndata['id']              int64[n_nodes]  unique entity ids of the batch
  *   head_local,

@@ -11,9 +11,14 @@ import torch as th
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+_calls = [0]
+
+
 def _torchrun(nproc, script, *args, timeout=600, env=None):
+    _calls[0] += 1      # a fresh rendezvous port per launch: the previous launch's store may still hold its port
+    port = 29500 + (os.getpid() * 7 + _calls[0] * 131) % 2000
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc),
-           "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 2000), script, *args]
+           "--master-addr", "127.0.0.1", "--master-port", str(port), script, *args]
     e = dict(os.environ)
     e.update(env or {})
     return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT, env=e)
@@ -53,3 +58,24 @@ def test_relation_allreduce_equivalence_gloo():
     Adagrad once per replica equals ExternalEmbedding.update over the concatenated per-edge rows."""
     out = _torchrun(2, os.path.join(ROOT, "tests", "gloo_rel_check.py"), timeout=300)
     assert out.stdout.count("GLOO_REL_OK") == 1, out.stdout[-2000:] + out.stderr[-3000:]
+
+
+def test_descriptor_exchange_gloo():
+    """world_size-3 gloo: dist.exchange_fds hands every rank's file descriptors to every peer (what carries the VMM shard
+    allocations between the GPU processes)."""
+    out = _torchrun(3, os.path.join(ROOT, "tests", "gloo_fd_check.py"), timeout=300)
+    assert out.stdout.count("GLOO_FD_OK") == 1, out.stdout[-2000:] + out.stderr[-3000:]
+
+
+def test_head_owner_edge_partition_covers_every_edge_once():
+    from dglke_b200.dist import partition_edges_by_head_owner, shard_rows
+    rng = np.random.default_rng(0)
+    n_ent, world = 1003, 4
+    heads = rng.integers(0, n_ent, 5000)
+    seen = np.zeros(5000, dtype=int)
+    for r in range(world):
+        idx = partition_edges_by_head_owner(heads, n_ent, world, r)
+        _, lo, hi = shard_rows(n_ent, world, r)
+        assert ((heads[idx] >= lo) & (heads[idx] < hi)).all()
+        seen[idx] += 1
+    assert (seen == 1).all()
