@@ -30,3 +30,18 @@ def test_ours_arm_needs_gpu():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--no-cpu-baseline", "--steps", "1"],
                          capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert out.returncode != 0 and "no CPU path" in (out.stderr + out.stdout)
+
+
+def test_reference_arm_under_torchrun_prints_one_line_from_rank0():
+    """N > 1: the driver launches the reference arm with torchrun as well; rank 0 alone measures and prints, and the
+    workload is the one the GPU arm defaults to at N > 1 (the Freebase-shaped table, entity count capped and stated)."""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(29300 + os.getpid() % 500), os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
+           "--steps", "1", "--warmup", "1", "--cpu-procs", "2"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, out.stdout[-1000:]
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["n_gpus"] == 2 and line["value"] > 0
+    assert "Freebase" in line["config"]["workload"] and line["config"]["entities_scaled_down"] is True
