@@ -64,6 +64,8 @@ struct kge_context {
   float* ext_rg = nullptr;           // deferred relation mode: caller-owned dense buffers [n_rel * Dr], [n_rel] that k_chain sums
   float* ext_rgs = nullptr;          //   the relation gradients into (all-reduced by the caller, kge_set_relation_buffers)
   float* dump_v = nullptr;           // test hook (kge_debug_set_dump): coefficient matrices of the fused kernel
+  long long* negdeg_ids = nullptr;   // --neg_deg_sample: the augmented negative id list [C * (Cs + Ns)] of the last step
+  size_t negdeg_cap = 0;
   // kge_set_next_batch: rows of the next step staged by this step's fused kernels
   struct Prefetch {
     bool armed = false;              // a next batch is registered for the coming kge_step_fused_begin
@@ -163,6 +165,9 @@ int make_params(const kge_step_cfg_t* cfg, long long n_nodes, StepParams* p, boo
   p->neg_head = cfg->neg_head ? 1 : 0;
   p->B = cfg->batch; p->Cs = cfg->chunk_size; p->Ns = cfg->neg_sample_size;
   p->C = (int)(cfg->batch / cfg->chunk_size);
+  // --neg_deg_sample: every chunk's negatives are its own Cs corrupted-side rows followed by the Ns sampled ones
+  p->neg_deg = cfg->neg_deg_sample ? 1 : 0;
+  if (p->neg_deg) p->Ns += p->Cs;
   p->Nn = (long long)p->C * p->Ns;
   p->U = n_nodes >= 0 ? n_nodes : 2 * p->B;      // capacity when only the device knows the count
   p->U_dev = nullptr;
@@ -370,6 +375,8 @@ KGE_API int kge_destroy(kge_handle_t h) {
   if (h->dev_log4) cudaFree(h->dev_log4);
   if (h->red_partial) cudaFree(h->red_partial);
   if (h->rel_dense) cudaFree(h->rel_dense);
+  if (h->negdeg_ids) cudaFree(h->negdeg_ids);
+  for (int i = 0; i < 2; ++i) { if (h->pf.nc[i]) cudaFree(h->pf.nc[i]); if (h->pf.bn[i]) cudaFree(h->pf.bn[i]); }
   if (h->prof.created)
     for (int i = 0; i < Profiler::kMax; ++i) { cudaEventDestroy(h->prof.ev0[i]); cudaEventDestroy(h->prof.ev1[i]); }
   delete h;
@@ -583,6 +590,21 @@ static int forward_backward_impl(kge_handle_t h, const kge_step_cfg_t* cfg, cons
   else if (p.rel_dense && (rc = ensure_rel_dense(h, vr, &w, (cudaStream_t)stream))) return rc;
   LaunchCtx c = lctx(h, stream);
   BatchView b = bview(batch);
+  if (p.neg_deg) {
+    if (ve.n_shards != 1) return fail(KGE_ERR_UNSUPPORTED, "--neg_deg_sample needs a single-shard entity table");
+    if ((size_t)p.Nn > h->negdeg_cap) {
+      KGE_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
+      if (h->negdeg_ids) cudaFree(h->negdeg_ids);
+      h->negdeg_ids = nullptr; h->negdeg_cap = 0;
+      if (cudaMalloc(&h->negdeg_ids, (size_t)p.Nn * sizeof(long long)) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(KGE_ERR_NOMEM, "neg_deg_sample id list (%lld ids)", (long long)p.Nn);
+      }
+      h->negdeg_cap = (size_t)p.Nn;
+    }
+    launch_negdeg_ids(c, p, b, b.neg_ids, h->negdeg_ids);
+    b.neg_ids = h->negdeg_ids;          // from here on the step sees Cs + Ns ordinary negatives per chunk
+  }
   ensure_ng_zero(h, p, w, c, false);
   // rows staged by the previous step's prefetch warps (kge_set_next_batch) replace this step's gathers -- only for
   // exactly the batch that was announced
@@ -641,6 +663,7 @@ static int forward_backward_impl(kge_handle_t h, const kge_step_cfg_t* cfg, cons
   if (p.use_nc && !p.nc_staged) launch_gather_nodes(c, p, ve, b, w);      // pos_g.ndata['emb'] = entity_emb(pos_g.ndata['id'])  (general_models.py:548)
   if (p.model == KGE_RESCAL) launch_rescal_prep(c, p, ve, vr, b, w);
   else launch_prep(c, p, ve, vr, b, w);
+  if (p.neg_deg) launch_negdeg_zero_reg(c, p, w);
   float* logdst = log4 ? log4 : h->dev_log4;
   if (p.fused) {
     launch_wbar(c, p, b.edge_weight, w);
@@ -649,8 +672,10 @@ static int forward_backward_impl(kge_handle_t h, const kge_step_cfg_t* cfg, cons
                            h->dump_v ? h->dump_v + (size_t)p.B * p.Ns : nullptr, &ve, b.neg_ids, pfp, g_err, sizeof(g_err)))) return rc;
   } else {
     if ((rc = run_score(h, c, p, w))) return rc;
+    if (p.neg_deg) launch_negdeg_mask_scores(c, p, w);
     launch_wbar(c, p, b.edge_weight, w);
     launch_loss_rows(c, p, w.pos, w.S, b.edge_weight, w);
+    if (p.neg_deg) launch_negdeg_mask_coef(c, p, w);
     launch_colsum(c, p, w);
     if (use_umma(h, p)) {
       if ((rc = umma_grad(c, p, w, false, g_err, sizeof(g_err)))) return rc;
@@ -659,6 +684,7 @@ static int forward_backward_impl(kge_handle_t h, const kge_step_cfg_t* cfg, cons
       launch_grad_a(c, p, w);
       launch_grad_b(c, p, w);
     }
+    if (p.neg_deg) launch_negdeg_scatter(c, p, ve, b, w);
   }
   if (p.model == KGE_RESCAL) launch_rescal_chain(c, p, ve, vr, b, w);
   else launch_chain(c, p, ve, vr, b, w);
@@ -693,6 +719,7 @@ static int update_impl(kge_handle_t h, const kge_step_cfg_t* cfg, const kge_tabl
   StepParams q = h->last_p;       // the schedule flags (fused / use_nc / rel_dense / rel_deferred) of the forward pass
   q.lr = cfg->lr;
   BatchView b = bview(batch);
+  if (q.neg_deg) b.neg_ids = h->negdeg_ids;     // the list the forward pass built (Cs + Ns ids per chunk)
   if (launch_update(lctx(h, stream), q, ve, vr, b, h->last_w, log4, b.edge_weight) != KGE_OK)
     return fail(KGE_ERR_CUDA, "cooperative launch of k_update failed: %s (set KGE_B200_NO_COOP=1 for the three-launch form)",
                 cudaGetErrorString(cudaPeekAtLastError()));

@@ -56,6 +56,8 @@ struct StepParams {
   int hinge;         // 1: Hinge criterion (loss.py:10-17); 0: Logsigmoid == Logistic == BCE
   float margin;      // Hinge margin
   int pairwise;      // 1: criterion(pos_i - neg_ij, +1), plain mean over all (i, j) (loss.py:76-80)
+  int neg_deg;       // 1: --neg_deg_sample: Ns = chunk_size + sampled negatives, the first Cs rows of a chunk's negatives are
+                     //    the chunk's own corrupted-side rows (kge_negdeg.cu)
   int nc_staged;     // 1: NC was filled by the previous step's prefetch warps (kge_set_next_batch): no k_gather_nodes ran
 };
 
@@ -353,7 +355,13 @@ struct FusedPrefetch {
   float* nc;                   // [nU, D] destination of the node rows
   float* bn;                   // [nNeg, D] destination of the negative rows
 };
-int fused_prefetch_slots(const StepParams& p, int mode);   // row slots per prefetch warp the shape leaves room for (< 2: none)
+int fused_prefetch_slots(const StepParams& p, int mode);
+// --neg_deg_sample fix-up kernels (kge_negdeg.cu)
+void launch_negdeg_ids(const LaunchCtx&, const StepParams&, const BatchView&, const long long* sampled, long long* out);
+void launch_negdeg_zero_reg(const LaunchCtx&, const StepParams&, const StepWs&);
+void launch_negdeg_mask_scores(const LaunchCtx&, const StepParams&, const StepWs&);
+void launch_negdeg_mask_coef(const LaunchCtx&, const StepParams&, const StepWs&);
+void launch_negdeg_scatter(const LaunchCtx&, const StepParams&, const TableView& ent, const BatchView&, const StepWs&);   // row slots per prefetch warp the shape leaves room for (< 2: none)
 void launch_prep(const LaunchCtx&, const StepParams&, const TableView& ent, const TableView& rel,
                  const BatchView&, const StepWs&);
 // dense-row variant used by kge_score_pos / kge_score_neg (rows already gathered)

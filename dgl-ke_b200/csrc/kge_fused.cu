@@ -711,7 +711,7 @@ int pad16(int x) { return (x + 15) & ~15; }
 bool fused_supported(const StepParams& p) {
   const bool model_ok = p.model == KGE_TRANSE_L2 || p.model == KGE_DISTMULT || p.model == KGE_COMPLEX || p.model == KGE_RESCAL;
   if (!model_ok) return false;
-  if (p.hinge || p.pairwise) return false;     // the fused epilogue is the (non-pairwise) Logsigmoid criterion
+  if (p.hinge || p.pairwise || p.neg_deg) return false;   // the fused epilogue is the plain (non-pairwise, unmasked) Logsigmoid criterion
   if ((p.D % 8) || (p.Cs % 8) || (p.Ns % 8) || p.D < 32 || p.Cs < 8 || p.Ns < 8) return false;
   return pad16(p.Cs) <= 240 && pad16(p.Ns) <= 240;
 }

@@ -44,7 +44,7 @@ class StepCfg(C.Structure):
                 ("reg_norm", C.c_int32), ("adversarial", C.c_int32), ("adv_temperature", C.c_float),
                 ("neg_head", C.c_int32), ("batch", C.c_int64), ("chunk_size", C.c_int32),
                 ("neg_sample_size", C.c_int32), ("loss_genre", C.c_int32), ("margin", C.c_float),
-                ("pairwise", C.c_int32)]
+                ("pairwise", C.c_int32), ("neg_deg_sample", C.c_int32)]
 
 
 LOSS_IDS = {"Logsigmoid": 0, "Hinge": 1, "Logistic": 2, "BCE": 3}       # kge_loss_t
@@ -216,14 +216,14 @@ def make_table(shards_emb, shards_state, num_rows, dim, devices=None):
 
 def make_cfg(model, entity_dim, relation_dim, gamma, emb_init, lr, reg_coef, reg_norm, adversarial,
              adv_temperature, neg_head, batch, chunk_size, neg_sample_size, loss_genre="Logsigmoid", margin=1.0,
-             pairwise=False):
+             pairwise=False, neg_deg_sample=False):
     if model not in MODEL_IDS:
         raise KgeError("model %r is not on the accelerated hot path (supported: %s)" % (model, sorted(MODEL_IDS)))
     if loss_genre not in LOSS_IDS:
         raise ValueError("loss genre %s is not support" % loss_genre)            # loss.py:58-59
     return StepCfg(MODEL_IDS[model], entity_dim, relation_dim, gamma, emb_init, lr, reg_coef, reg_norm,
                    1 if adversarial else 0, adv_temperature, 1 if neg_head else 0, batch, chunk_size,
-                   neg_sample_size, LOSS_IDS[loss_genre], float(margin), 1 if pairwise else 0)
+                   neg_sample_size, LOSS_IDS[loss_genre], float(margin), 1 if pairwise else 0, 1 if neg_deg_sample else 0)
 
 
 def make_batch(node_ids, head_local, tail_local, rel_ids, neg_ids, edge_weight=None, head_ids=None, tail_ids=None):

@@ -30,6 +30,7 @@ class Hyper:
     loss_genre: str = "Logsigmoid"      # Hinge | Logistic | Logsigmoid | BCE  (loss.py:41-62)
     margin: float = 1.0
     pairwise: bool = False
+    neg_deg_sample: bool = False        # general_models.py:396-403,417-424: training steps only
 
     @property
     def emb_init(self):
@@ -81,7 +82,7 @@ class StepEngine:
         hp = self.hp
         return _lib.make_cfg(hp.model, hp.entity_dim, hp.relation_dim, hp.gamma, hp.emb_init, hp.lr, hp.reg_coef,
                              hp.reg_norm, hp.adversarial, hp.adv_temperature, neg_head, batch, chunk_size,
-                             neg_sample_size, hp.loss_genre, hp.margin, hp.pairwise)
+                             neg_sample_size, hp.loss_genre, hp.margin, hp.pairwise, hp.neg_deg_sample)
 
     def check_ids(self, node_ids, head_local, tail_local, rel_ids, neg_ids):
         """KGE_B200_CHECK_IDS=1 (debugging aid, costs a device sync): the kernels index the tables with the ids they are

@@ -41,7 +41,8 @@ class KEModel(object):
                              adv_temperature=getattr(args, "adversarial_temperature", 1.0),
                              double_ent=double_entity_emb, double_rel=double_relation_emb,
                              loss_genre=getattr(args, "loss_genre", "Logsigmoid"), margin=getattr(args, "margin", 1.0),
-                             pairwise=getattr(args, "pairwise", False))
+                             pairwise=getattr(args, "pairwise", False),
+                             neg_deg_sample=getattr(args, "neg_deg_sample", False))
         entity_dim, rel_dim = self.hyper.entity_dim, self.hyper.relation_dim
         self.entity_dim, self.rel_dim = entity_dim, rel_dim
         self.strict_rel_part = getattr(args, "strict_rel_part", False)
@@ -112,7 +113,8 @@ class KEModel(object):
 
     def predict_neg_score(self, pos_g, neg_g, to_device=None, gpu_id=-1, trace=False, neg_deg_sample=False):
         if neg_deg_sample:
-            raise NotImplementedError("--neg_deg_sample is not accelerated yet (SURVEY 8f-2)")
+            raise NotImplementedError("neg_deg_sample on the stand-alone (forward-only) negative score, i.e. "
+                                      "--neg_deg_sample_eval, is not implemented; training steps support it")
         num_chunks, chunk_size, neg_sample_size = neg_g.num_chunks, neg_g.chunk_size, neg_g.neg_sample_size
         head_ids, tail_ids = pos_g.all_edges(order="eid")
         rel = pos_g.edata["emb"]
@@ -150,8 +152,8 @@ class KEModel(object):
         A batch that comes from the device sampler (pos_g.device_batch, dglke_b200.sampler) takes the fused
         schedule: forward = kge_step_fused_begin, update = kge_step_fused_end, 5 kernels per step; the log scalars are
         produced by the update kernel and read lazily."""
-        if getattr(self.args, "neg_deg_sample", False):
-            raise NotImplementedError("--neg_deg_sample is not accelerated yet (SURVEY 8f-2)")
+        # --neg_deg_sample (general_models.py:396-403,417-424) travels in the step configuration (Hyper.neg_deg_sample):
+        # the library scores the chunk's own corrupted-side rows as extra negatives (kge_negdeg.cu)
         batch = getattr(pos_g, "device_batch", None)
         if batch is not None and not self.has_edge_importance:
             eng = self.engine()

@@ -37,7 +37,7 @@ extern "C" {
 #define KGE_API
 #endif
 
-#define KGE_ABI_VERSION 3
+#define KGE_ABI_VERSION 4
 #define KGE_MAX_SHARDS 8
 
 typedef enum {
@@ -103,6 +103,12 @@ typedef struct {
   float margin;             /* Hinge: max(0, margin - label * score)                      */
   int32_t pairwise;         /* -pw: criterion(pos_i - neg_ij, 1), mean over all pairs (Hinge / Logistic only; the
                              * self-adversarial weighting does not apply, loss.py:76-80)   */
+  /* ABI 4: --neg_deg_sample (models/general_models.py:396-403,417-424,429-432): the chunk's own corrupted-side rows are
+   * scored as chunk_size extra negatives in front of the sampled ones (score of a positive against its own row forced
+   * to 0, gradients of the extra columns go to the positive nodes).  neg_sample_size stays the SAMPLED count and
+   * batch.neg_ids holds num_chunks * neg_sample_size ids; the negative-score matrix (kge_debug_read) is
+   * [batch, chunk_size + neg_sample_size].  Training entry points only, single-shard tables. */
+  int32_t neg_deg_sample;
 } kge_step_cfg_t;
 typedef enum { KGE_LOSS_LOGSIGMOID = 0, KGE_LOSS_HINGE = 1, KGE_LOSS_LOGISTIC = 2, KGE_LOSS_BCE = 3 } kge_loss_t;
 

@@ -55,6 +55,15 @@ CASES.append(("tc_loss_Hinge_ComplEx", "ComplEx", dict(adv=True, loss_genre="Hin
                                                        chunk=8, neg=8, n_ent=60)))
 
 
+# --neg_deg_sample (general_models.py:396-403,417-424,429-432): the chunk's own corrupted-side rows as extra negatives
+for _m in ("TransE_l1", "TransE_l2", "DistMult", "ComplEx", "RESCAL", "RotatE"):
+    CASES.append(("negdeg_%s" % _m, _m, dict(adv=(_m != "DistMult"), neg_deg=True, n_ent=30)))
+CASES.append(("negdeg_TransE_l2_ragged_impts", "TransE_l2", dict(adv=True, neg_deg=True, chunk=6, neg=4, batch=12, impts=True)))
+CASES.append(("tc_negdeg_ComplEx", "ComplEx", dict(adv=True, neg_deg=True, hidden=32, batch=16, chunk=8, neg=8, n_ent=60)))
+CASES.append(("tc_negdeg_TransE_l2_hinge", "TransE_l2", dict(adv=False, neg_deg=True, hidden=32, batch=16, chunk=8, neg=16, n_ent=60,
+                                                            loss_genre="Hinge", margin=2.0, gamma=4.0)))
+
+
 def one_case(name, model, o):
     n_ent, n_rel = o.get("n_ent", 40), o.get("n_rel", 5)
     hidden = o.get("hidden", 8)
@@ -66,7 +75,7 @@ def one_case(name, model, o):
                         neg_adversarial_sampling=o["adv"], adversarial_temperature=o.get("temp", 1.5),
                         has_edge_importance=bool(o.get("impts", False)),
                         loss_genre=o.get("loss_genre", "Logsigmoid"), margin=o.get("margin", 1.0),
-                        pairwise=bool(o.get("pairwise", False)))
+                        pairwise=bool(o.get("pairwise", False)), neg_deg_sample=bool(o.get("neg_deg", False)))
     m = rh.build_reference_model(model, n_ent, n_rel, hidden, gamma, args, double_ent=double_ent, seed=7)
     rng = np.random.default_rng(1234)
     fx = dict(ent_emb0=m.entity_emb.emb.clone().numpy(), rel_emb0=m.relation_emb.emb.clone().numpy())
@@ -77,7 +86,7 @@ def one_case(name, model, o):
                 neg_sample_size=neg, num_chunks=batch // chunk, steps=2,
                 has_edge_importance=bool(o.get("impts", False)),
                 loss_genre=o.get("loss_genre", "Logsigmoid"), margin=o.get("margin", 1.0),
-                pairwise=bool(o.get("pairwise", False)))
+                pairwise=bool(o.get("pairwise", False)), neg_deg_sample=bool(o.get("neg_deg", False)))
     C = batch // chunk
     for step in range(2):
         neg_head = (step % 2 == 1)          # sampler.py:853-859: tail first, then head
@@ -99,7 +108,7 @@ def one_case(name, model, o):
         if w is not None:
             fx[p + "edge_weight"] = w
         fx[p + "pos_score"] = pos.numpy()
-        fx[p + "neg_score"] = negs.numpy().reshape(batch, neg)
+        fx[p + "neg_score"] = negs.numpy().reshape(batch, -1)           # [B, Ns] or, with neg_deg_sample, [B, Cs + Ns]
         assert np.array_equal(pos.numpy(), out["pos_score"].numpy())
         fx[p + "loss"] = np.array(out["loss"], dtype=np.float64)
         for k in ("pos_loss", "neg_loss", "loss", "regularization"):

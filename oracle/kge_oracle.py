@@ -41,6 +41,7 @@ class Hyper:
     loss_genre: str = "Logsigmoid"      # models/pytorch/loss.py:41-62
     margin: float = 1.0
     pairwise: bool = False
+    neg_deg_sample: bool = False        # models/general_models.py:396-403,417-424,429-432
 
     @property
     def emb_init(self):
@@ -226,10 +227,23 @@ def forward_backward(hp, ent_emb, rel_emb, node_ids, head_local, tail_local, rel
     h, t = nodes[head_local], nodes[tail_local]
     pos = positive_score(hp, h, rels, t)
     negs = gather(ent_emb, neg_ids).clone().requires_grad_(True)         # trace entry 2 (entity)
+    corrupt = negs
+    if hp.neg_deg_sample:
+        # general_models.py:396-403 / 417-424: the chunk's own heads (head mode) / tails (tail mode) -- rows of the NODE
+        # leaf, not a new traced tensor -- are put in front of the sampled negatives of every chunk, and the score of a
+        # positive against its own row is multiplied by 0 (mask[:, 0::(Ns' + 1)] = 0 on the [C, Cs * Ns'] view)
+        own = (h if neg_head else t).reshape(num_chunks, chunk_size, -1)
+        corrupt = th.cat([own, negs.reshape(num_chunks, neg_sample_size, -1)], 1)
+        neg_sample_size = chunk_size + neg_sample_size
+        corrupt = corrupt.reshape(num_chunks * neg_sample_size, -1)
     if neg_head:
-        neg = negative_score(hp, negs, rels, t, num_chunks, chunk_size, neg_sample_size, True)
+        neg = negative_score(hp, corrupt, rels, t, num_chunks, chunk_size, neg_sample_size, True)
     else:
-        neg = negative_score(hp, h, rels, negs, num_chunks, chunk_size, neg_sample_size, False)
+        neg = negative_score(hp, h, rels, corrupt, num_chunks, chunk_size, neg_sample_size, False)
+    if hp.neg_deg_sample:
+        mask = th.ones(num_chunks, chunk_size * neg_sample_size, dtype=neg.dtype)
+        mask[:, 0::(neg_sample_size + 1)] = 0
+        neg = neg * mask.reshape(num_chunks, chunk_size, neg_sample_size)          # general_models.py:429-432
     neg = neg.reshape(-1, neg_sample_size)
     loss, log = loss_terms(hp, pos, neg, edge_weight)
     if hp.reg_coef > 0.0 and hp.reg_norm > 0:

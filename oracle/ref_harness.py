@@ -190,5 +190,6 @@ def reference_neg_score(model, node_ids, head_local, tail_local, rel_ids, neg_id
         pos_g.ndata["emb"] = model.entity_emb(pos_g.ndata["id"], -1, False)
         pos_g.edata["emb"] = model.relation_emb(pos_g.edata["id"], -1, False)
         pos = model.predict_score(pos_g)
-        neg = model.predict_neg_score(pos_g, neg_g, trace=False, neg_deg_sample=False)
+        neg = model.predict_neg_score(pos_g, neg_g, trace=False,
+                                      neg_deg_sample=bool(getattr(model.args, "neg_deg_sample", False)))
     return pos.clone(), neg.clone()

@@ -25,7 +25,8 @@ def hyper_from_meta(meta):
                     reg_coef=meta["reg_coef"], reg_norm=meta["reg_norm"], adversarial=meta["adversarial"],
                     adv_temperature=meta["adv_temperature"], double_ent=meta["double_ent"],
                     double_rel=meta["double_rel"], loss_genre=meta.get("loss_genre", "Logsigmoid"),
-                    margin=meta.get("margin", 1.0), pairwise=meta.get("pairwise", False))
+                    margin=meta.get("margin", 1.0), pairwise=meta.get("pairwise", False),
+                    neg_deg_sample=meta.get("neg_deg_sample", False))
 
 
 def step_inputs(z, step):

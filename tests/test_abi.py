@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), "libkge_b200.so does not export %s" % n
     assert sorted(names) == sorted(_lib.EXPORTS)
-    assert lib.kge_abi_version() == 3
+    assert lib.kge_abi_version() == 4
 
 
 def test_struct_layouts_match_header():

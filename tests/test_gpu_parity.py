@@ -20,7 +20,7 @@ def _engine(hp, ent, ent_s, rel, rel_s):
     hyper = Hyper(model=hp.model, hidden_dim=hp.hidden_dim, gamma=hp.gamma, lr=hp.lr, reg_coef=hp.reg_coef,
                   reg_norm=hp.reg_norm, adversarial=hp.adversarial, adv_temperature=hp.adv_temperature,
                   double_ent=hp.double_ent, double_rel=hp.double_rel, loss_genre=hp.loss_genre, margin=hp.margin,
-                  pairwise=hp.pairwise)
+                  pairwise=hp.pairwise, neg_deg_sample=getattr(hp, "neg_deg_sample", False))
     eng = StepEngine(hyper, DeviceTable.from_tensors(e, es), DeviceTable.from_tensors(r, rs), 0)
     return eng, (e, es, r, rs)
 
@@ -56,9 +56,14 @@ def _run_and_check(hp, tables, si, C, Cs, Ns, ref, tol=2e-5, allow_fp64_arbitrat
     log4 = eng.forward_backward(d(si["node_ids"]), d(si["head_local"]), d(si["tail_local"]), d(si["rel_ids"]),
                                 d(si["neg_ids"]), Cs, Ns, si["neg_head"], w)
     B, U, Nn = si["head_local"].numel(), si["node_ids"].numel(), si["neg_ids"].numel()
-    got = dict(pos=eng.read(_lib.BUF_POS_SCORE, (B,)).cpu().numpy(), neg=eng.read(_lib.BUF_NEG_SCORE, (B, Ns)).cpu().numpy(),
+    nd = bool(getattr(hp, "neg_deg_sample", False))
+    Nse = Cs + Ns if nd else Ns                   # --neg_deg_sample: the chunk's own Cs rows in front of the sampled negatives
+    gg = eng.read(_lib.BUF_NEG_GRAD, (C * Nse, hp.entity_dim)).cpu().numpy()
+    if nd:                                        # the traced negatives are the sampled ones
+        gg = gg.reshape(C, Nse, -1)[:, Cs:, :].reshape(Nn, -1)
+    got = dict(pos=eng.read(_lib.BUF_POS_SCORE, (B,)).cpu().numpy(), neg=eng.read(_lib.BUF_NEG_SCORE, (B, Nse)).cpu().numpy(),
                gn=eng.read(_lib.BUF_NODE_GRAD, (U, hp.entity_dim)).cpu().numpy(),
-               gg=eng.read(_lib.BUF_NEG_GRAD, (Nn, hp.entity_dim)).cpu().numpy(),
+               gg=gg,
                gr=eng.read(_lib.BUF_REL_GRAD, (B, hp.relation_dim)).cpu().numpy(), log=log4.cpu().numpy())
     eng.update()
     th.cuda.synchronize()
@@ -96,7 +101,8 @@ def _run_and_check(hp, tables, si, C, Cs, Ns, ref, tol=2e-5, allow_fp64_arbitrat
         check(ref64)
 
 
-@pytest.mark.parametrize("name", golden_cases())
+# the --neg_deg_sample fixtures run in their own process (tests/test_z_negdeg.py)
+@pytest.mark.parametrize("name", [n for n in golden_cases() if "negdeg" not in n])
 def test_cuda_step_matches_reference_golden(name):
     meta, z = load_case(name)
     hp = hyper_from_meta(meta)
