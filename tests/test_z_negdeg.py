@@ -28,3 +28,71 @@ def test_neg_deg_sample_step_configuration():
     assert cfg.neg_deg_sample == 1 and cfg.neg_sample_size == 4 and C.sizeof(_lib.StepCfg) == 80
     assert _lib.StepCfg.neg_deg_sample.offset == 76
     assert Hyper(neg_deg_sample=True).neg_deg_sample and not Hyper().neg_deg_sample
+
+
+@pytest.mark.parametrize("model,de", [("TransE_l2", False), ("DistMult", False), ("RotatE", True), ("RESCAL", False)])
+@pytest.mark.parametrize("neg_head", [False, True])
+def test_fixup_algebra_of_kge_negdeg_equals_the_reference_semantics(model, de, neg_head):
+    """CPU emulation of what kge_negdeg.cu does around the UNCHANGED step, against the oracle's restatement of the
+    reference (which tests/test_oracle_golden.py pins to the reference's fixtures):
+
+      ordinary step over the augmented id list ids' (own rows | sampled rows, all treated as one traced negative tensor
+      with its regulariser terms) + masked diagonal  -->  fix-ups: drop the prepended rows' regulariser log share, move
+      (their gradient - reg'(row)) onto the positive node they are a copy of, zero their gradient rows (the negative Adagrad
+      entry then adds 0 to their state and rows)."""
+    import numpy as np
+    import torch as th
+    import kge_oracle as ko
+    hp = ko.Hyper(model=model, hidden_dim=8, gamma=6.0, lr=0.2, reg_coef=1e-3, reg_norm=3, adversarial=True,
+                  adv_temperature=0.7, double_ent=de, neg_deg_sample=True)
+    plain = ko.Hyper(**{**hp.__dict__, "neg_deg_sample": False})
+    n_ent, n_rel, B, Cs, Ns = 25, 3, 12, 4, 6
+    C, Nse = B // Cs, Cs + Ns
+    ent0, es0, rel0, rs0 = ko.init_tables(hp, n_ent, n_rel, seed=2)
+    es0 += 0.05
+    rng = np.random.default_rng(7)
+    h, t = rng.integers(0, n_ent, B), rng.integers(0, n_ent, B)
+    nodes, inv = np.unique(np.concatenate([h, t]), return_inverse=True)
+    T = lambda a: th.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.int64)))
+    node_ids, hl, tl, rel_ids, neg_ids = T(nodes), T(inv[:B]), T(inv[B:]), T(rng.integers(0, n_rel, B)), T(rng.integers(0, n_ent, C * Ns))
+
+    # ---- the reference semantics
+    want = [x.clone() for x in (ent0, es0, rel0, rs0)]
+    fb = ko.train_step(hp, *want, node_ids, hl, tl, rel_ids, neg_ids, C, Cs, Ns, neg_head)
+
+    # ---- the emulated device flow
+    own = node_ids[hl if neg_head else tl].reshape(C, Cs)                        # k_negdeg_ids
+    ids2 = th.cat([own, neg_ids.reshape(C, Ns)], 1).reshape(-1)
+    nodes_l = ent0[node_ids].clone().requires_grad_(True)
+    rels_l = rel0[rel_ids].clone().requires_grad_(True)
+    negs_l = ent0[ids2].clone().requires_grad_(True)                             # ONE traced tensor of C * (Cs + Ns) rows
+    hh, tt = nodes_l[hl], nodes_l[tl]
+    pos = ko.positive_score(plain, hh, rels_l, tt)
+    neg = (ko.negative_score(plain, negs_l, rels_l, tt, C, Cs, Nse, True) if neg_head
+           else ko.negative_score(plain, hh, rels_l, negs_l, C, Cs, Nse, False))
+    mask = th.ones(C, Cs, Nse)
+    mask[:, th.arange(Cs), th.arange(Cs)] = 0                                    # k_negdeg_mask_scores / _mask_coef
+    loss, log = ko.loss_terms(plain, pos, (neg * mask).reshape(B, Nse))
+    reg_rows = th.cat([nodes_l, negs_l], 0)
+    reg = hp.reg_coef * (reg_rows.abs().pow(3).sum() + rels_l.abs().pow(3).sum())
+    (loss + reg).backward()
+    is_own = th.zeros(C, Nse, dtype=th.bool)
+    is_own[:, :Cs] = True
+    is_own = is_own.reshape(-1)
+    reg_log = float(reg.detach()) - hp.reg_coef * float(negs_l.detach()[is_own].abs().pow(3).sum())     # k_negdeg_zero_reg
+    g_nodes, g_negs = nodes_l.grad.clone(), negs_l.grad.clone()
+    x_own = negs_l.detach()[is_own]
+    moved = g_negs[is_own] - 3.0 * hp.reg_coef * x_own.abs() * x_own                                      # k_negdeg_scatter
+    g_nodes.index_add_(0, (hl if neg_head else tl), moved)
+    g_negs[is_own] = 0
+    got = [x.clone() for x in (ent0, es0, rel0, rs0)]
+    ko.adagrad_entry(got[0], got[1], node_ids, g_nodes, hp.lr)
+    ko.adagrad_entry(got[0], got[1], ids2, g_negs, hp.lr)            # prepended rows: state += 0, row += 0
+    ko.adagrad_entry(got[2], got[3], rel_ids, rels_l.grad, hp.lr)
+
+    np.testing.assert_allclose(float(loss.detach()), fb["log"]["loss"], rtol=1e-6)
+    np.testing.assert_allclose(reg_log, fb["log"]["regularization"], rtol=1e-5)
+    np.testing.assert_allclose(g_nodes.numpy(), fb["nodes_grad"].numpy(), rtol=1e-4, atol=1e-7)
+    np.testing.assert_allclose(g_negs.reshape(C, Nse, -1)[:, Cs:].reshape(C * Ns, -1).numpy(), fb["negs_grad"].numpy(), rtol=1e-5, atol=1e-8)
+    for a, b in zip(got, want):
+        np.testing.assert_allclose(a.numpy(), b.numpy(), rtol=1e-5, atol=1e-7)
