@@ -475,6 +475,24 @@ def measure(args, workload, rank, world, local_rank, dev, cpu_base, K_steps, ful
         "cpu_baseline": cpu_base,
         "clocks": clocks,
     }
+    if world > 1:
+        # NVLink traffic of one step of one GPU, counted from the batch (not measured by a counter): rows whose owner is a
+        # peer.  Reads = the prefetch of the next batch's tail and negative rows by the fused kernels (or the gather when
+        # not pipelined); writes = the bulk reductions of the update kernel into those same rows.
+        try:
+            f = (world - 1) / world
+            n_nodes_remote = (B if head_range else 2 * B) * f        # heads are local under head-owner placement
+            remote_rows = n_nodes_remote + (B // Cs) * neg * f
+            byts = remote_rows * De * 4
+            t_fused = sum(v for k, v in prof.items() if "k_fused" in k) * 1e-3
+            t_upd = sum(v for k, v in prof.items() if "k_update" in k) * 1e-3
+            line["nvlink"] = {"remote_rows_per_step": int(remote_rows), "read_bytes_per_step": int(byts),
+                              "write_bytes_per_step": int(byts),
+                              "read_GBs_over_the_fused_kernels": (byts / t_fused / 1e9) if (pipelined and t_fused > 0) else None,
+                              "write_GBs_over_k_update": (byts / t_upd / 1e9) if t_upd > 0 else None,
+                              "note": "analytic: (N-1)/N of the tail and negative rows (+ the heads under random placement) x row bytes"}
+        except Exception as e:  # noqa
+            line["nvlink"] = {"error": repr(e)}
     return line
 
 
