@@ -112,21 +112,41 @@ class KEModel(object):
         return g.edata["score"]
 
     def predict_neg_score(self, pos_g, neg_g, to_device=None, gpu_id=-1, trace=False, neg_deg_sample=False):
-        if neg_deg_sample:
-            raise NotImplementedError("neg_deg_sample on the stand-alone (forward-only) negative score, i.e. "
-                                      "--neg_deg_sample_eval, is not implemented; training steps support it")
+        """Forward-only negative scores [C, Cs, Ns] (general_models.py:348-434).  neg_deg_sample (the --neg_deg_sample_eval
+        case: training steps carry the flag in the step configuration instead): the chunk's own corrupted-side rows are scored
+        as chunk_size extra negatives in front of the sampled ones, the score of a positive against its own row is
+        multiplied by 0, and neg_g.neg_sample_size becomes chunk_size + neg_sample_size (:396-403, :417-424, :429-432)."""
         num_chunks, chunk_size, neg_sample_size = neg_g.num_chunks, neg_g.chunk_size, neg_g.neg_sample_size
         head_ids, tail_ids = pos_g.all_edges(order="eid")
         rel = pos_g.edata["emb"]
+
+        def with_own(own_rows, neg_rows):
+            own = own_rows.reshape(num_chunks, chunk_size, -1)
+            cat = th.cat([own, neg_rows.reshape(num_chunks, neg_sample_size, -1)], 1)
+            return cat.reshape(num_chunks * (chunk_size + neg_sample_size), -1).contiguous()
+
         if neg_g.neg_head:
             neg_head = self.entity_emb(neg_g.ndata["id"][neg_g.head_nid], gpu_id, trace)
             tail = pos_g.ndata["emb"][tail_ids.to(rel.device)]
+            if neg_deg_sample:
+                neg_head = with_own(pos_g.ndata["emb"][head_ids.to(rel.device)], neg_head)
+                neg_sample_size = chunk_size + neg_sample_size
             neg_head, tail = self.head_neg_prepare(pos_g.edata["id"], num_chunks, neg_head, tail, gpu_id, trace)
-            return self.head_neg_score(neg_head, rel, tail, num_chunks, chunk_size, neg_sample_size)
-        neg_tail = self.entity_emb(neg_g.ndata["id"][neg_g.tail_nid], gpu_id, trace)
-        head = pos_g.ndata["emb"][head_ids.to(rel.device)]
-        head, neg_tail = self.tail_neg_prepare(pos_g.edata["id"], num_chunks, head, neg_tail, gpu_id, trace)
-        return self.tail_neg_score(head, rel, neg_tail, num_chunks, chunk_size, neg_sample_size)
+            score = self.head_neg_score(neg_head, rel, tail, num_chunks, chunk_size, neg_sample_size)
+        else:
+            neg_tail = self.entity_emb(neg_g.ndata["id"][neg_g.tail_nid], gpu_id, trace)
+            head = pos_g.ndata["emb"][head_ids.to(rel.device)]
+            if neg_deg_sample:
+                neg_tail = with_own(pos_g.ndata["emb"][tail_ids.to(rel.device)], neg_tail)
+                neg_sample_size = chunk_size + neg_sample_size
+            head, neg_tail = self.tail_neg_prepare(pos_g.edata["id"], num_chunks, head, neg_tail, gpu_id, trace)
+            score = self.tail_neg_score(head, rel, neg_tail, num_chunks, chunk_size, neg_sample_size)
+        if neg_deg_sample:
+            neg_g.neg_sample_size = neg_sample_size
+            mask = th.ones((num_chunks, chunk_size * neg_sample_size), dtype=score.dtype, device=score.device)
+            mask[:, 0::(neg_sample_size + 1)] = 0
+            return score * mask.reshape(num_chunks, chunk_size, neg_sample_size)
+        return score
 
     def forward_test(self, pos_g, neg_g, logs, gpu_id=-1):
         """Ranking of each positive among its negatives (general_models.py:436-485):
@@ -135,7 +155,8 @@ class KEModel(object):
         pos_g.edata["emb"] = self.relation_emb(pos_g.edata["id"], gpu_id, False)
         batch_size = pos_g.number_of_edges()
         pos_scores = self.predict_score(pos_g).view(batch_size, -1)
-        neg_scores = self.predict_neg_score(pos_g, neg_g, gpu_id=gpu_id, trace=False).reshape(batch_size, -1)
+        neg_scores = self.predict_neg_score(pos_g, neg_g, gpu_id=gpu_id, trace=False,
+                                            neg_deg_sample=getattr(self.args, "neg_deg_sample_eval", False)).reshape(batch_size, -1)
         hit = neg_scores >= pos_scores
         if getattr(self.args, "eval_filter", False) and "bias" in neg_g.edata:
             hit = hit & (neg_g.edata["bias"].to(hit.device).reshape(batch_size, -1) != -1)

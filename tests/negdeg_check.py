@@ -59,6 +59,34 @@ def main():
         np.testing.assert_allclose(r.cpu().numpy(), o[2].numpy(), rtol=1e-4, atol=5e-5)
         np.testing.assert_allclose(e_s.cpu().numpy(), o[1].numpy(), rtol=1e-4, atol=1e-7)
         print("negdeg fused-step ok:", model, flush=True)
+    # the forward-only variant (--neg_deg_sample_eval): KEModel.predict_neg_score(neg_deg_sample=True) against the oracle
+    from dglke_b200.general_models import KEModel
+    from dglke_b200.graph import build_pos_graph, NegGraph
+    from test_gpu_plugin import _args
+    for model, de in (("DistMult", False), ("TransE_l2", False), ("RotatE", True)):
+        m = KEModel(_args(), model, 200, 6, 32 if not de else 16, 12.0, double_entity_emb=de)
+        hp = ko.Hyper(model=model, hidden_dim=32 if not de else 16, gamma=12.0, double_ent=de)
+        ent, rel = m.entity_emb.emb.cpu(), m.relation_emb.emb.cpu()
+        rng = np.random.default_rng(5)
+        C, Cs, Ns = 3, 8, 16
+        H, R, T_ = rng.integers(0, 200, C * Cs), rng.integers(0, 6, C * Cs), rng.integers(0, 200, C * Cs)
+        ng = th.from_numpy(rng.integers(0, 200, C * Ns).astype(np.int64))
+        for neg_head in (False, True):
+            pg, ngr = build_pos_graph(H, R, T_), NegGraph(ng, C, Cs, Ns, neg_head)
+            pg.ndata["emb"] = m.entity_emb(pg.ndata["id"], 0, False)
+            pg.edata["emb"] = m.relation_emb(pg.edata["id"], 0, False)
+            got = m.predict_neg_score(pg, ngr, gpu_id=0, trace=False, neg_deg_sample=True).cpu()
+            assert ngr.neg_sample_size == Cs + Ns and tuple(got.shape) == (C, Cs, Cs + Ns)
+            h, r, t = ent[th.from_numpy(H)], rel[th.from_numpy(R)], ent[th.from_numpy(T_)]
+            own = (h if neg_head else t).reshape(C, Cs, -1)
+            cat = th.cat([own, ent[ng].reshape(C, Ns, -1)], 1).reshape(C * (Cs + Ns), -1)
+            want = (ko.negative_score(hp, cat, r, t, C, Cs, Cs + Ns, True) if neg_head
+                    else ko.negative_score(hp, h, r, cat, C, Cs, Cs + Ns, False))
+            mask = th.ones(C, Cs * (Cs + Ns))
+            mask[:, 0::(Cs + Ns + 1)] = 0
+            want = want * mask.reshape(C, Cs, Cs + Ns)
+            np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=1e-5, atol=1e-5)
+        print("negdeg eval-variant ok:", model, flush=True)
     print("NEGDEG_CHECK_OK", flush=True)
 
 
