@@ -96,3 +96,48 @@ def test_fixup_algebra_of_kge_negdeg_equals_the_reference_semantics(model, de, n
     np.testing.assert_allclose(g_negs.reshape(C, Nse, -1)[:, Cs:].reshape(C * Ns, -1).numpy(), fb["negs_grad"].numpy(), rtol=1e-5, atol=1e-8)
     for a, b in zip(got, want):
         np.testing.assert_allclose(a.numpy(), b.numpy(), rtol=1e-5, atol=1e-7)
+
+
+def test_predict_neg_score_and_forward_test_logic_with_a_cpu_stand_in():
+    """KEModel.predict_neg_score / forward_test are thin glue over the score kernels: run the glue itself on the CPU with
+    the oracle's score functions standing in for the kernels -- default path (must be the plain chunked score) and the
+    neg_deg_sample path (reference semantics: own rows first, masked diagonal, neg_sample_size updated)."""
+    import types
+    import numpy as np
+    import torch as th
+    import kge_oracle as ko
+    from dglke_b200.general_models import KEModel
+    from dglke_b200.graph import build_pos_graph, NegGraph
+    hp = ko.Hyper(model="DistMult", hidden_dim=8, gamma=12.0)
+    ent, _, rel, _ = ko.init_tables(hp, 40, 3, seed=1)
+    fake = types.SimpleNamespace(
+        entity_emb=lambda ids, gpu_id, trace: ent[ids], relation_emb=lambda ids, gpu_id, trace: rel[ids],
+        head_neg_prepare=lambda rid, C, a, b, gpu_id, trace: (a, b), tail_neg_prepare=lambda rid, C, a, b, gpu_id, trace: (a, b),
+        head_neg_score=lambda hn, r, t, C, Cs, Ns: ko.negative_score(hp, hn, r, t, C, Cs, Ns, True),
+        tail_neg_score=lambda h, r, tn, C, Cs, Ns: ko.negative_score(hp, h, r, tn, C, Cs, Ns, False),
+        args=types.SimpleNamespace(eval_filter=False, neg_deg_sample_eval=False))
+    fake.predict_score = lambda g: ko.positive_score(hp, g.ndata["emb"][g.all_edges()[0]], g.edata["emb"], g.ndata["emb"][g.all_edges()[1]])
+    fake.predict_neg_score = lambda *a, **k: KEModel.predict_neg_score(fake, *a, **k)
+    rng = np.random.default_rng(0)
+    C, Cs, Ns = 2, 4, 6
+    H, R, T_ = rng.integers(0, 40, C * Cs), rng.integers(0, 3, C * Cs), rng.integers(0, 40, C * Cs)
+    ng = th.from_numpy(rng.integers(0, 40, C * Ns).astype(np.int64))
+    h, r, t = ent[th.from_numpy(H)], rel[th.from_numpy(R)], ent[th.from_numpy(T_)]
+    for neg_head in (False, True):
+        pg, ngr = build_pos_graph(H, R, T_), NegGraph(ng, C, Cs, Ns, neg_head)
+        pg.ndata["emb"], pg.edata["emb"] = ent[pg.ndata["id"]], rel[pg.edata["id"]]
+        plain = KEModel.predict_neg_score(fake, pg, ngr)
+        want = ko.negative_score(hp, ent[ng] if neg_head else h, r, t if neg_head else ent[ng], C, Cs, Ns, neg_head)
+        assert th.equal(plain, want) and ngr.neg_sample_size == Ns
+        got = KEModel.predict_neg_score(fake, pg, ngr, neg_deg_sample=True)
+        assert ngr.neg_sample_size == Cs + Ns
+        fbh = ko.Hyper(model="DistMult", hidden_dim=8, gamma=12.0, reg_coef=0.0, neg_deg_sample=True)
+        fb = ko.forward_backward(fbh, ent, rel, pg.ndata["id"], *pg.all_edges(), pg.edata["id"], ng, C, Cs, Ns, neg_head)
+        np.testing.assert_allclose(got.reshape(C * Cs, -1).numpy(), fb["neg_score"].numpy(), rtol=1e-6, atol=1e-7)
+        # forward_test: rank = 1 + #{neg >= pos}
+        logs = []
+        ngr2 = NegGraph(ng, C, Cs, Ns, neg_head)
+        KEModel.forward_test(fake, build_pos_graph(H, R, T_), ngr2, logs, -1)
+        pos = ko.positive_score(hp, h, r, t)
+        ranks = (want.reshape(C * Cs, -1) >= pos.reshape(-1, 1)).sum(1) + 1
+        assert [l["MR"] for l in logs] == [float(x) for x in ranks.tolist()]
